@@ -1,0 +1,65 @@
+"""ctypes binding of include/gabo_b200.h.  There is no fallback: if the CUDA library is missing or a call
+fails, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, 'libgabo_b200.so')
+
+i32, i64, f64, f32, vp, sz = C.c_int, C.c_int64, C.c_double, C.c_float, C.c_void_p, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/gabo_b200.h one to one
+SIGNATURES = {
+    'gabo_abi_version': (i32, []),
+    'gabo_device_info': (i32, [C.POINTER(i32)] * 3),
+    'gabo_status_string': (C.c_char_p, [i32]),
+    'gabo_points_gram_workspace_bytes': (sz, [i64, i64, i32]),
+    'gabo_points_gram_f64': (i32, [i32, vp, i64, i64, vp, i64, i64, i32, f64, f64, vp, i64, i64, i64, i32, vp, sz, vp]),
+    'gabo_points_gram_f32': (i32, [i32, vp, i64, i64, vp, i64, i64, i32, f32, f32, vp, i64, i64, i64, i32, vp, sz, vp]),
+    'gabo_kdiag_const_f64': (i32, [i64, f64, vp, vp]),
+    'gabo_spd_prep_f64': (i32, [vp, i64, i64, i32, vp, vp, vp, vp, vp, vp]),
+    'gabo_spd_gram_f64': (i32, [i32, i32, vp, vp, vp, i64, vp, vp, i64, i32, f64, f64, vp, i64, i64, i64, i32, vp]),
+    'gabo_spd_stein_kdiag_f64': (i32, [vp, i64, f64, f64, vp, vp]),
+    'gabo_potrf_workspace_bytes': (sz, [i64]),
+    'gabo_potrf_f64': (i32, [i64, vp, i64, f64, vp, vp, sz, vp]),
+    'gabo_trsm_workspace_bytes': (sz, [i64, i64]),
+    'gabo_trsm_f64': (i32, [i32, i64, i64, vp, i64, vp, i64, vp, sz, vp]),
+    'gabo_logdet_f64': (i32, [i64, vp, i64, vp, vp]),
+    'gabo_gp_loglik_f64': (i32, [i64, i64, vp, i64, vp, i64, vp, vp]),
+    'gabo_gp_predict_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, f64, vp, vp, vp]),
+    'gabo_gemm_nt_sub_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, i32, vp]),
+}
+
+_lib = None
+
+
+class GaboError(RuntimeError):
+    def __init__(self, fn, status, text):
+        super().__init__(f'{fn} failed with status {status}: {text}')
+        self.status = status
+
+
+def lib():
+    """Load libgabo_b200.so once.  Raises ImportError (loudly) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f'{LIB_PATH} is missing: build it with `python -m gaboflow_b200.build` '
+                '(there is no CPU or PyTorch fallback for the gaboflow_b200 kernels)')
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)   # AttributeError if the ABI and the header ever diverge
+            fn.restype = res
+            fn.argtypes = args
+        if handle.gabo_abi_version() != 1:
+            raise ImportError('libgabo_b200.so ABI version mismatch; rebuild')
+        _lib = handle
+    return _lib
+
+
+def check(fn_name, status):
+    if status != 0:
+        raise GaboError(fn_name, status, lib().gabo_status_string(status).decode())

@@ -1,0 +1,47 @@
+// Small C-ABI entry points that are not kernels of their own: version, device query, status text, Kdiag fill.
+#include "gabo_common.cuh"
+
+namespace gabo {
+
+int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMsB200;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return kNumSMsB200;
+    return n;
+}
+
+namespace {
+__global__ void fill_kernel(double* out, int64_t n, double v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+}  // namespace
+}  // namespace gabo
+
+extern "C" int gabo_abi_version(void) { return GABO_ABI_VERSION; }
+
+extern "C" int gabo_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    GABO_CUDA_TRY(cudaGetDevice(&dev));
+    if (sm_count) GABO_CUDA_TRY(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+    if (cc_major) GABO_CUDA_TRY(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (cc_minor) GABO_CUDA_TRY(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return 0;
+}
+
+extern "C" const char* gabo_status_string(int status) {
+    if (status == 0) return "ok";
+    if (status <= GABO_ERR_CUDA) return cudaGetErrorString((cudaError_t)(GABO_ERR_CUDA - status));
+    if (status < 0) return "invalid argument (index = -status, 1-based)";
+    return "numerical failure (LAPACK-style info > 0)";
+}
+
+// Kdiag = fill([n], variance): kernels_sphere_tf.py:105,221; kernels_spd_tf.py:265,417,550,658.
+extern "C" int gabo_kdiag_const_f64(int64_t n, double variance, double* out, gabo_stream_t stream) {
+    if (n < 0) return -1;
+    if (n == 0) return 0;
+    if (out == nullptr) return -3;
+    gabo::fill_kernel<<<(unsigned)gabo::ceil_div64(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, variance);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,569 @@
+// GP linear algebra on B200 (sm_100a): blocked right-looking FP64 Cholesky of K + sigma^2 I, triangular solves,
+// log-determinant, log marginal likelihood and posterior mean/variance.
+//
+// Replaces (third party, called from the reference at examples/kernels/sphere/sphere_kernels.py:131-139,
+// examples/kernels/spd/spd_kernels.py:146-170 and every BO iteration): GPflow 0.5 GPR.build_likelihood /
+// build_predict, i.e. tf.cholesky, tf.matrix_triangular_solve, log(diag_part), reduce_sum on TensorFlow's CPU kernels.
+//
+// Factorisation layout: row-major, lower triangle, in place.  Two-level blocking:
+//   outer block column NB = 512:  trailing update  A22 -= L21 L21^T  with k = 512 on the DMMA GEMM core (lower tiles);
+//   inner block column nb = 128:  diagonal block factored and inverted by one CTA in shared memory (potf2_inv_kernel),
+//                                 panel below it  L21 = A21 * inv(L11)^T  as a DMMA product (panel_trsm_kernel),
+//                                 panel-internal update of the remaining columns of the outer block column (k = 128).
+// sigma^2 is added to each diagonal entry when its diagonal block is loaded for factorisation (each entry is loaded
+// exactly once), so K itself is never rewritten.  A non-positive pivot records LAPACK-style info and the factorisation
+// continues (the caller decides; the reference's TF op would raise).
+//
+// Triangular solves use the same trick: the 128x128 diagonal blocks of L are inverted once (one CTA each, all in
+// parallel), after which forward/backward substitution is a chain of DMMA products (or of HBM-bound GEMV updates when
+// there are at most 4 right-hand sides).
+#include "dgemm_core.cuh"
+
+namespace gabo {
+
+// ------------------------------------------------------------------------------------------------------------------
+int launch_gemm(bool a_kmaj, bool b_kmaj, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                const double* B, int64_t ldb, bool beta0, double* C, int64_t ldc, bool lower, cudaStream_t stream) {
+    if (m <= 0 || n <= 0) return 0;
+    GemmParams p;
+    p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.m = m; p.n = n; p.k = k;
+    p.lower = lower ? 1 : 0;
+    p.vecA = aligned16(A, lda) ? 1 : 0; p.vecB = aligned16(B, ldb) ? 1 : 0; p.vecC = aligned16(C, ldc) ? 1 : 0;
+    p.alpha = alpha; p.beta0 = beta0 ? 1 : 0;
+    dim3 grid((unsigned)ceil_div64(n, GT), (unsigned)ceil_div64(m, GT));
+    const int smem = (int)GEMM_SMEM_BYTES;
+#define GABO_GEMM_LAUNCH(AK, BK_)                                                                                   \
+    do {                                                                                                            \
+        GABO_CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        gemm_kernel<AK, BK_><<<grid, GTHREADS, smem, stream>>>(p);                                                  \
+    } while (0)
+    if (a_kmaj && b_kmaj) GABO_GEMM_LAUNCH(true, true);
+    else if (a_kmaj && !b_kmaj) GABO_GEMM_LAUNCH(true, false);
+    else if (!a_kmaj && !b_kmaj) GABO_GEMM_LAUNCH(false, false);
+    else GABO_GEMM_LAUNCH(false, true);
+#undef GABO_GEMM_LAUNCH
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+
+namespace {
+
+constexpr int NB_IN = 128;      // inner block (diagonal block factored by one CTA)
+constexpr int NB_OUT = 512;     // outer block column (k of the big trailing update)
+constexpr int PLD = NB_IN + 1;  // leading dimension of the diagonal block in shared memory (column walks conflict-free)
+constexpr int WLD = NB_IN + 4;  // 132 = 4 (mod 16): conflict-free DMMA fragment loads of a 128-wide K-major tile
+constexpr int CH = 64;          // rows (panel) or right-hand sides (solve) one CTA multiplies by a 128x128 inverse
+constexpr int CLD = CH + 4;     // 68 = 4 (mod 16)
+constexpr size_t POTF2_SMEM = (size_t)NB_IN * PLD * sizeof(double);                       // 132,096
+constexpr size_t PANEL_SMEM = (size_t)(NB_IN * WLD + CH * WLD) * sizeof(double);          // 202,752
+constexpr size_t DIAGAPPLY_SMEM = (size_t)(NB_IN * WLD + NB_IN * CLD) * sizeof(double);   // 204,800
+
+// In place in shared memory: S (lower, ld PLD, n x n valid, identity beyond) <- inv(S), row by row.
+// W[i][j] = -(sum_{k=j}^{i-1} S[i][k] W[k][j]) / S[i][i]; rows < i already hold W, row i still holds S.
+__device__ __forceinline__ void tri_inverse_inplace_smem(double* S, int tid) {
+    const int jcol = tid >> 2, part = tid & 3;   // 512 threads: 128 columns x 4 partial sums
+    for (int i = 0; i < NB_IN; ++i) {
+        const double rii = 1.0 / S[i * PLD + i];
+        double sum = 0.0;
+        if (jcol < i)
+            for (int k = jcol + part; k < i; k += 4) sum = fma(S[i * PLD + k], S[k * PLD + jcol], sum);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        __syncthreads();                 // every read of row i (still S) is done
+        if (part == 0) {
+            if (jcol < i) S[i * PLD + jcol] = -sum * rii;
+            else if (jcol == i) S[i * PLD + i] = rii;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- diagonal block: L11 = chol(A11 + sigma2 I) in place; Winv = inv(L11) (dense [128][128], zero above) ---------------
+__global__ void __launch_bounds__(512, 1) potf2_inv_kernel(double* __restrict__ A, int64_t lda, int jb, double sigma2,
+                                                           double* __restrict__ Winv, int32_t* __restrict__ info,
+                                                           int info_base) {
+    extern __shared__ double sm_potf2[];
+    double* S = sm_potf2;   // [128][129]
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NB_IN * NB_IN; e += 512) {
+        const int r = e >> 7, c = e & 127;
+        double v = 0.0;
+        if (r < jb && c <= r) v = A[(int64_t)r * lda + c];
+        if (r == c) v = (r < jb) ? v + sigma2 : 1.0;   // identity padding keeps the inverse well defined
+        S[r * PLD + c] = v;
+    }
+    __syncthreads();
+    for (int j = 0; j < jb; ++j) {   // right-looking, one column at a time
+        const double d = S[j * PLD + j];
+        if (!(d > 0.0) && tid == 0) atomicCAS(info, 0, info_base + j + 1);
+        const double ljj = sqrt(d);
+        const double rinv = 1.0 / ljj;
+        __syncthreads();             // everyone has read d before it is overwritten
+        for (int i = j + tid; i < jb; i += 512) S[i * PLD + j] = (i == j) ? ljj : S[i * PLD + j] * rinv;
+        __syncthreads();
+        const int rem = jb - j - 1;  // S[i][c] -= S[i][j] S[c][j] for j < c <= i < jb
+        for (int e = tid; e < rem * rem; e += 512) {
+            const int ii = e / rem, cc = e - ii * rem;
+            if (cc <= ii) {
+                const int i = j + 1 + ii, c = j + 1 + cc;
+                S[i * PLD + c] = fma(-S[i * PLD + j], S[c * PLD + j], S[i * PLD + c]);
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < jb * jb; e += 512) {
+        const int r = e / jb, c = e - r * jb;
+        if (c <= r) A[(int64_t)r * lda + c] = S[r * PLD + c];
+    }
+    __syncthreads();
+    tri_inverse_inplace_smem(S, tid);
+    for (int e = tid; e < NB_IN * NB_IN; e += 512) {
+        const int r = e >> 7, c = e & 127;
+        Winv[e] = (c <= r) ? S[r * PLD + c] : 0.0;
+    }
+}
+
+// ---- inverses of all 128x128 diagonal blocks of a factor L (for the solves): one CTA per block ------------------------
+__global__ void __launch_bounds__(512, 1) trtri_blocks_kernel(const double* __restrict__ L, int64_t ldl, int64_t n,
+                                                              double* __restrict__ Winv_all) {
+    extern __shared__ double sm_trtri[];
+    double* S = sm_trtri;
+    const int tid = threadIdx.x;
+    const int64_t k0 = (int64_t)blockIdx.x * NB_IN;
+    const int jb = (int)((n - k0) < NB_IN ? (n - k0) : NB_IN);
+    for (int e = tid; e < NB_IN * NB_IN; e += 512) {
+        const int r = e >> 7, c = e & 127;
+        double v = 0.0;
+        if (r < jb && c <= r) v = L[(k0 + r) * ldl + k0 + c];
+        if (r == c && r >= jb) v = 1.0;
+        S[r * PLD + c] = v;
+    }
+    __syncthreads();
+    tri_inverse_inplace_smem(S, tid);
+    double* W = Winv_all + (int64_t)blockIdx.x * NB_IN * NB_IN;
+    for (int e = tid; e < NB_IN * NB_IN; e += 512) {
+        const int r = e >> 7, c = e & 127;
+        W[e] = (c <= r) ? S[r * PLD + c] : 0.0;
+    }
+}
+
+// ---- panel: A21 (m x jb, in place) <- A21 * Winv^T.  One CTA owns 64 rows and the whole k = 128 -----------------------
+__global__ void __launch_bounds__(256, 1) panel_trsm_kernel(double* __restrict__ A, int64_t lda, int64_t m, int jb,
+                                                            const double* __restrict__ Winv) {
+    extern __shared__ __align__(16) double sm_panel[];
+    double* sW = sm_panel;                  // [128][132]  Winv rows = output column index, K-major
+    double* sA = sm_panel + NB_IN * WLD;    // [64][132]   panel rows, K-major
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * CH;
+    for (int e = tid; e < NB_IN * NB_IN; e += 256) sW[(e >> 7) * WLD + (e & 127)] = Winv[e];
+    for (int e = tid; e < CH * NB_IN; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        const int64_t gr = row0 + r;
+        sA[r * WLD + c] = (gr < m && c < jb) ? A[gr * lda + c] : 0.0;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;   // 2 x 4 warps, 32 x 32 each
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    // X[r][c] = sum_{k <= c} A[r][k] Winv[c][k]: this warp's columns end at wn*32+31, so k stops there
+    const int kend = (wn + 1) * 32;
+    for (int ks = 0; ks < kend / 4; ++ks) {
+        double a[4], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(wm * 32 + mi * 8 + g) * WLD + ks * 4 + q];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = sW[(wn * 32 + ni * 8 + g) * WLD + ks * 4 + q];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int64_t gr = row0 + wm * 32 + mi * 8 + g;
+        if (gr >= m) continue;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int c = wn * 32 + ni * 8 + 2 * q;
+            if (c < jb) A[gr * lda + c] = acc[mi][ni][0];
+            if (c + 1 < jb) A[gr * lda + c + 1] = acc[mi][ni][1];
+        }
+    }
+}
+
+// ---- solve step: B_k (jb x nrhs, in place) <- W B_k  or  W^T B_k.  One CTA owns 64 right-hand sides --------------------
+template <bool TRANS>
+__global__ void __launch_bounds__(256, 1) diag_apply_kernel(double* __restrict__ B, int64_t ldb, int64_t nrhs, int jb,
+                                                            const double* __restrict__ Winv) {
+    extern __shared__ __align__(16) double sm_apply[];
+    double* sW = sm_apply;                  // [128][132]
+    double* sB = sm_apply + NB_IN * WLD;    // [128 k][68]  N-major
+    const int tid = threadIdx.x;
+    const int64_t c0 = (int64_t)blockIdx.x * CH;
+    for (int e = tid; e < NB_IN * NB_IN; e += 256) sW[(e >> 7) * WLD + (e & 127)] = Winv[e];
+    for (int e = tid; e < NB_IN * CH; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        sB[r * CLD + c] = (r < jb && c0 + c < nrhs) ? B[(int64_t)r * ldb + c0 + c] : 0.0;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;   // 4 x 2 warps, 32 x 32 each: 128 rows x 64 right-hand sides
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    // X[r][c] = sum_k W[r][k] B[k][c] (k <= r), or sum_k W[k][r] B[k][c] (k >= r) when TRANS
+    const int ks_lo = TRANS ? (wm * 32) / 4 : 0;
+    const int ks_hi = TRANS ? NB_IN / 4 : ((wm + 1) * 32) / 4;
+    for (int ks = ks_lo; ks < ks_hi; ++ks) {
+        double a[4], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+            a[mi] = TRANS ? sW[(ks * 4 + q) * WLD + wm * 32 + mi * 8 + g] : sW[(wm * 32 + mi * 8 + g) * WLD + ks * 4 + q];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = sB[(ks * 4 + q) * CLD + wn * 32 + ni * 8 + g];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int r = wm * 32 + mi * 8 + g;
+        if (r >= jb) continue;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int64_t c = c0 + wn * 32 + ni * 8 + 2 * q;
+            if (c < nrhs) B[(int64_t)r * ldb + c] = acc[mi][ni][0];
+            if (c + 1 < nrhs) B[(int64_t)r * ldb + c + 1] = acc[mi][ni][1];
+        }
+    }
+}
+
+// ---- solve step for <= 4 right-hand sides: B[r, :] -= sum_k Lp[r][k] X[k, :], HBM-bound, one warp per row ---------------
+//  TRANS == false: Lp element (r,k) at Lp[r*ldl + k]   (panel below the diagonal block)
+//  TRANS == true : element (r,k) = L[k][r] at Lp[k*ldl + r] (row block left of the diagonal block, read transposed)
+template <int NRHS, bool TRANS>
+__global__ void __launch_bounds__(256) gemv_update_kernel(const double* __restrict__ Lp, int64_t ldl, int64_t m, int jb,
+                                                          const double* __restrict__ X, int64_t ldx,
+                                                          double* __restrict__ Bm, int64_t ldb) {
+    __shared__ double sx[NB_IN][NRHS];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NB_IN * NRHS; e += 256) {
+        const int k = e / NRHS, c = e - k * NRHS;
+        sx[k][c] = (k < jb) ? X[(int64_t)k * ldx + c] : 0.0;
+    }
+    __syncthreads();
+    if (!TRANS) {
+        const int lane = tid & 31;
+        const int64_t r = (int64_t)blockIdx.x * 8 + (tid >> 5);
+        if (r >= m) return;
+        double acc[NRHS];
+#pragma unroll
+        for (int c = 0; c < NRHS; ++c) acc[c] = 0.0;
+        for (int k = lane; k < jb; k += 32) {
+            const double l = Lp[r * ldl + k];
+#pragma unroll
+            for (int c = 0; c < NRHS; ++c) acc[c] = fma(l, sx[k][c], acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NRHS; ++c) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < NRHS; ++c) Bm[r * ldb + c] -= acc[c];
+        }
+    } else {
+        // thread per output row r (coalesced along r for each k)
+        const int64_t r = (int64_t)blockIdx.x * 256 + tid;
+        if (r >= m) return;
+        double acc[NRHS];
+#pragma unroll
+        for (int c = 0; c < NRHS; ++c) acc[c] = 0.0;
+        for (int k = 0; k < jb; ++k) {
+            const double l = Lp[(int64_t)k * ldl + r];
+#pragma unroll
+            for (int c = 0; c < NRHS; ++c) acc[c] = fma(l, sx[k][c], acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NRHS; ++c) Bm[r * ldb + c] -= acc[c];
+    }
+}
+
+// ---- reductions -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* sred) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sred[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (warp == 0) {
+        t = (lane < (int)(blockDim.x >> 5)) ? sred[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    return t;   // valid in warp 0
+}
+
+// out[0] = -0.5 n p log(2pi) - p sum log L_ii - 0.5 sum alpha^2 when alpha != nullptr, else sum log L_ii
+__global__ void __launch_bounds__(1024) loglik_kernel(int64_t n, int64_t p, const double* __restrict__ L, int64_t ldl,
+                                                      const double* __restrict__ alpha, int64_t lda,
+                                                      double* __restrict__ out) {
+    __shared__ double sred[32];
+    double slog = 0.0, ssq = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        slog += log(L[i * ldl + i]);
+        if (alpha != nullptr)
+            for (int64_t c = 0; c < p; ++c) { const double a = alpha[i * lda + c]; ssq = fma(a, a, ssq); }
+    }
+    const double tl = block_sum(slog, sred);
+    const double ts = block_sum(ssq, sred);
+    if (threadIdx.x == 0) {
+        if (alpha == nullptr) out[0] = tl;
+        else out[0] = -0.5 * (double)n * (double)p * 1.8378770664093454836 - (double)p * tl - 0.5 * ts;
+    }
+}
+
+// mean[j][c] = sum_i A[i][j] V[i][c] + mean_const ; var[j] = kdiag[j] - sum_i A[i][j]^2.  CTA = 32 columns x 32 row lanes.
+__global__ void __launch_bounds__(1024) predict_kernel(int64_t n, int64_t M, int64_t p, const double* __restrict__ A,
+                                                       int64_t lda, const double* __restrict__ V, int64_t ldv,
+                                                       const double* __restrict__ kdiag, double mean_const,
+                                                       double* __restrict__ mean, double* __restrict__ var) {
+    __shared__ double sred[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t j = (int64_t)blockIdx.x * 32 + tx;
+    const bool ok = j < M;
+    double sq = 0.0;
+    for (int64_t i = ty; i < n; i += 32) {
+        const double a = ok ? A[i * lda + j] : 0.0;
+        sq = fma(a, a, sq);
+    }
+    sred[ty][tx] = sq;
+    __syncthreads();
+    if (ty == 0 && ok) {
+        double t = 0.0;
+        for (int r = 0; r < 32; ++r) t += sred[r][tx];
+        var[j] = kdiag[j] - t;
+    }
+    for (int64_t c = 0; c < p; ++c) {
+        double s = 0.0;
+        for (int64_t i = ty; i < n; i += 32) {
+            const double a = ok ? A[i * lda + j] : 0.0;
+            s = fma(a, V[i * ldv + c], s);
+        }
+        __syncthreads();
+        sred[ty][tx] = s;
+        __syncthreads();
+        if (ty == 0 && ok) {
+            double t = 0.0;
+            for (int r = 0; r < 32; ++r) t += sred[r][tx];
+            mean[j * p + c] = t + mean_const;
+        }
+    }
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <class K>
+inline int set_smem(K kernel, size_t bytes) {
+    GABO_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+}  // namespace
+}  // namespace gabo
+
+using namespace gabo;
+
+// ----------------------------------------------------------------------------------------------------------------------
+extern "C" size_t gabo_potrf_workspace_bytes(int64_t n) {
+    (void)n;
+    return align256((size_t)NB_IN * NB_IN * sizeof(double));
+}
+
+extern "C" int gabo_potrf_f64(int64_t n, double* A, int64_t lda, double sigma2, int32_t* info, void* workspace,
+                              size_t workspace_bytes, gabo_stream_t stream_) {
+    if (n < 0) return -1;
+    if (n == 0) return 0;
+    if (A == nullptr) return -2;
+    if (lda < n) return -3;
+    if (info == nullptr) return -5;
+    if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return -6;
+    if (workspace_bytes < gabo_potrf_workspace_bytes(n)) return -7;
+    if (n > 2000000000LL) return -1;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    double* Winv = static_cast<double*>(workspace);
+    int rc;
+    if ((rc = set_smem(potf2_inv_kernel, POTF2_SMEM))) return rc;
+    if ((rc = set_smem(panel_trsm_kernel, PANEL_SMEM))) return rc;
+    GABO_CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int32_t), stream));
+
+    for (int64_t k0 = 0; k0 < n; k0 += NB_OUT) {
+        const int64_t kend = (k0 + NB_OUT < n) ? k0 + NB_OUT : n;   // end of this outer block column
+        for (int64_t kk = k0; kk < kend; kk += NB_IN) {
+            const int jb = (int)((kend - kk) < NB_IN ? (kend - kk) : NB_IN);
+            double* Akk = A + kk * lda + kk;
+            potf2_inv_kernel<<<1, 512, POTF2_SMEM, stream>>>(Akk, lda, jb, sigma2, Winv, info, (int)kk);
+            GABO_LAUNCH_CHECK();
+            const int64_t mrest = n - (kk + jb);
+            if (mrest <= 0) continue;
+            double* A21 = A + (kk + jb) * lda + kk;
+            panel_trsm_kernel<<<(unsigned)ceil_div64(mrest, CH), 256, PANEL_SMEM, stream>>>(A21, lda, mrest, jb, Winv);
+            GABO_LAUNCH_CHECK();
+            // panel-internal update: columns kk+jb .. kend of all rows below, lower part (k = jb)
+            const int64_t ncols = kend - (kk + jb);
+            if (ncols > 0) {
+                rc = launch_gemm(true, true, mrest, ncols, jb, -1.0, A21, lda, A21, lda, false,
+                                 A + (kk + jb) * lda + (kk + jb), lda, true, stream);
+                if (rc) return rc;
+            }
+        }
+        // trailing update with the whole outer block column (k = kend - k0)
+        const int64_t mtrail = n - kend;
+        if (mtrail > 0) {
+            const double* L21 = A + kend * lda + k0;
+            rc = launch_gemm(true, true, mtrail, mtrail, kend - k0, -1.0, L21, lda, L21, lda, false,
+                             A + kend * lda + kend, lda, true, stream);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+extern "C" size_t gabo_trsm_workspace_bytes(int64_t n, int64_t nrhs) {
+    (void)nrhs;
+    if (n <= 0) return 256;
+    return align256((size_t)ceil_div64(n, NB_IN) * NB_IN * NB_IN * sizeof(double));
+}
+
+template <int NRHS>
+static int gemv_dispatch(bool trans, const double* Lp, int64_t ldl, int64_t m, int jb, const double* X, int64_t ldx,
+                         double* Bm, int64_t ldb, cudaStream_t stream) {
+    if (!trans) gemv_update_kernel<NRHS, false><<<(unsigned)ceil_div64(m, 8), 256, 0, stream>>>(Lp, ldl, m, jb, X, ldx, Bm, ldb);
+    else gemv_update_kernel<NRHS, true><<<(unsigned)ceil_div64(m, 256), 256, 0, stream>>>(Lp, ldl, m, jb, X, ldx, Bm, ldb);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gabo_trsm_f64(int trans, int64_t n, int64_t nrhs, const double* L, int64_t ldl, double* B, int64_t ldb,
+                             void* workspace, size_t workspace_bytes, gabo_stream_t stream_) {
+    if (n < 0) return -2;
+    if (nrhs < 0) return -3;
+    if (n == 0 || nrhs == 0) return 0;
+    if (L == nullptr) return -4;
+    if (ldl < n) return -5;
+    if (B == nullptr) return -6;
+    if (ldb < nrhs) return -7;
+    if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return -8;
+    if (workspace_bytes < gabo_trsm_workspace_bytes(n, nrhs)) return -9;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    double* Wall = static_cast<double*>(workspace);
+    const int64_t nblk = ceil_div64(n, NB_IN);
+    int rc;
+    if ((rc = set_smem(trtri_blocks_kernel, POTF2_SMEM))) return rc;
+    if ((rc = set_smem(diag_apply_kernel<false>, DIAGAPPLY_SMEM))) return rc;
+    if ((rc = set_smem(diag_apply_kernel<true>, DIAGAPPLY_SMEM))) return rc;
+    trtri_blocks_kernel<<<(unsigned)nblk, 512, POTF2_SMEM, stream>>>(L, ldl, n, Wall);
+    GABO_LAUNCH_CHECK();
+    const unsigned rhs_chunks = (unsigned)ceil_div64(nrhs, CH);
+    for (int64_t b = 0; b < nblk; ++b) {
+        const int64_t kb = trans ? (nblk - 1 - b) : b;
+        const int64_t k0 = kb * NB_IN;
+        const int jb = (int)((n - k0) < NB_IN ? (n - k0) : NB_IN);
+        double* Bk = B + k0 * ldb;
+        const double* Wk = Wall + kb * NB_IN * NB_IN;
+        if (!trans) diag_apply_kernel<false><<<rhs_chunks, 256, DIAGAPPLY_SMEM, stream>>>(Bk, ldb, nrhs, jb, Wk);
+        else diag_apply_kernel<true><<<rhs_chunks, 256, DIAGAPPLY_SMEM, stream>>>(Bk, ldb, nrhs, jb, Wk);
+        GABO_LAUNCH_CHECK();
+        // rows still to be updated: below the block (forward) or above it (backward)
+        const int64_t m = trans ? k0 : n - (k0 + jb);
+        if (m <= 0) continue;
+        const double* Lp = trans ? (L + k0 * ldl) : (L + (k0 + jb) * ldl + k0);
+        double* Brest = trans ? B : (B + (k0 + jb) * ldb);
+        if (nrhs <= 4) {
+            switch (nrhs) {
+                case 1: rc = gemv_dispatch<1>(trans != 0, Lp, ldl, m, jb, Bk, ldb, Brest, ldb, stream); break;
+                case 2: rc = gemv_dispatch<2>(trans != 0, Lp, ldl, m, jb, Bk, ldb, Brest, ldb, stream); break;
+                case 3: rc = gemv_dispatch<3>(trans != 0, Lp, ldl, m, jb, Bk, ldb, Brest, ldb, stream); break;
+                default: rc = gemv_dispatch<4>(trans != 0, Lp, ldl, m, jb, Bk, ldb, Brest, ldb, stream); break;
+            }
+        } else {
+            // Brest[m, nrhs] -= op(Lp)[m, jb] * Bk[jb, nrhs]
+            rc = launch_gemm(!trans, false, m, nrhs, jb, -1.0, Lp, ldl, Bk, ldb, false, Brest, ldb, false, stream);
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int gabo_logdet_f64(int64_t n, const double* L, int64_t ldl, double* out, gabo_stream_t stream) {
+    if (n < 0) return -1;
+    if (out == nullptr) return -4;
+    if (n > 0 && L == nullptr) return -2;
+    if (ldl < n) return -3;
+    loglik_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(n, 1, L, ldl, nullptr, 0, out);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gabo_gp_loglik_f64(int64_t n, int64_t p, const double* L, int64_t ldl, const double* alpha,
+                                  int64_t ldalpha, double* out, gabo_stream_t stream) {
+    if (n < 0) return -1;
+    if (p < 1) return -2;
+    if (n > 0 && L == nullptr) return -3;
+    if (ldl < n) return -4;
+    if (n > 0 && alpha == nullptr) return -5;
+    if (ldalpha < p) return -6;
+    if (out == nullptr) return -7;
+    loglik_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(n, p, L, ldl, alpha, ldalpha, out);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gabo_gp_predict_f64(int64_t n, int64_t M, int64_t p, const double* A, int64_t lda, const double* V,
+                                   int64_t ldv, const double* kdiag, double mean_const, double* mean_out,
+                                   double* var_out, gabo_stream_t stream) {
+    if (n < 0) return -1;
+    if (M < 0) return -2;
+    if (p < 1) return -3;
+    if (M == 0) return 0;
+    if (n > 0 && A == nullptr) return -4;
+    if (lda < M) return -5;
+    if (n > 0 && V == nullptr) return -6;
+    if (ldv < p) return -7;
+    if (kdiag == nullptr) return -8;
+    if (mean_out == nullptr) return -10;
+    if (var_out == nullptr) return -11;
+    predict_kernel<<<(unsigned)ceil_div64(M, 32), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+        n, M, p, A, lda, V, ldv, kdiag, mean_const, mean_out, var_out);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gabo_gemm_nt_sub_f64(int64_t m, int64_t n, int64_t k, const double* A, int64_t lda, const double* B,
+                                    int64_t ldb, double* C, int64_t ldc, int lower, gabo_stream_t stream) {
+    if (m < 0) return -1;
+    if (n < 0) return -2;
+    if (k < 0) return -3;
+    if (m == 0 || n == 0) return 0;
+    if (k > 0 && A == nullptr) return -4;
+    if (lda < k) return -5;
+    if (k > 0 && B == nullptr) return -6;
+    if (ldb < k) return -7;
+    if (C == nullptr) return -8;
+    if (ldc < n) return -9;
+    return launch_gemm(true, true, m, n, k, -1.0, A, lda, B, ldb, false, C, ldc, lower != 0,
+                       static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,346 @@
+// Fused point-set Gram tile kernel (sm_100a): K = f(X . X2^T) for the sphere Gaussian / Laplace kernels and
+// the squared-distance Gaussian kernel, one pass, no N1 x N2 x D intermediates.
+//
+// Replaces  sphere_distance_tf (reference sphere_utils_tf.py:11-60: tile/tile/batched-matmul/clamp/acos)
+//           + SphereGaussianKernel.K / SphereLaplaceKernel.K (kernels_sphere_tf.py:59-88, 179-204)
+//           + the pair stage of SpdFrobeniusGaussianKernel.K / SpdLogEuclideanGaussianKernel.K
+//             (kernels_spd_tf.py:510-533, 618-641).
+//
+// Design (B200):
+//   * points are re-packed once per call into panel layout  P[chunk][row][KLD]  (zero padded to 128 rows and KLD
+//     columns), so that the 128-row operand tile of a chunk is ONE contiguous 128*KLD*8-byte block that a single
+//     TMA bulk copy (cp.async.bulk, SASS UBLKCP) lands in shared memory; KLD = 4 (mod 16) makes every DMMA
+//     fragment load bank-conflict free without swizzling;
+//   * persistent CTAs (one per SM, 16 warps), static round-robin over 128x128 output tiles, two-stage shared
+//     memory ring: the bulk copies of work item i+1 are in flight while item i is computed;
+//   * inner products on the FP64 tensor pipe (mma.sync m8n8k4 -> DMMA.8x8x4), 32x32 outputs per warp held in
+//     registers; the epilogue (clamp, acos, square, scale, exp, variance) runs on those registers and stores
+//     with streaming 128-bit writes; the symmetric mode computes lower tiles only and mirror-stores them
+//     (both stores fill whole 32-byte sectors: 64 B per quad row / per 8-lane column group).
+#include "gabo_common.cuh"
+
+namespace gabo {
+namespace {
+
+constexpr int BT = 128;         // output tile side
+constexpr int NTHREADS = 512;   // 16 warps, 4 x 4, 32x32 outputs each
+constexpr int NSTAGE = 2;
+
+struct GramParams {
+    const double* Ap;      // packed X   [nchunks][n1_pad][KLD]
+    const double* Bp;      // packed X2  [nchunks][n2_pad][KLD]
+    const double* normA;   // squared norms (sqdist kind) or nullptr
+    const double* normB;
+    double* K;
+    int64_t ldk;
+    int64_t n1_pad, n2_pad;
+    int64_t row0, row1;    // global row range produced; K points at row row0
+    int64_t n2;
+    int nchunks;
+    int kind;
+    int uplo;
+    int symmetric;
+    int vec_ok;
+    double beta, variance;
+    int64_t tile_r0;       // row0 / BT
+    int64_t tiles_m, tiles_n, ntiles;
+};
+
+// ---- packing -----------------------------------------------------------------------------------------
+template <int KLD, typename Tin>
+__global__ void pack_points_kernel(const Tin* __restrict__ X, int64_t n, int64_t ldx, int dim, double* __restrict__ P,
+                                   int64_t n_pad, int nchunks, double* __restrict__ norms) {
+    // one warp per row: coalesced reads along the row, writes chunk by chunk
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    int lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    double s = 0.0;
+    int width = nchunks * KLD;
+    for (int k = lane; k < width; k += 32) {
+        double v = 0.0;
+        if (row < n && k < dim) v = (double)X[row * ldx + k];
+        s = fma(v, v, s);
+        int c = k / KLD, kk = k - c * KLD;
+        P[((int64_t)c * n_pad + row) * KLD + kk] = v;
+    }
+    if (norms != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) norms[row] = s;
+    }
+}
+
+// ---- epilogue math -----------------------------------------------------------------------------------
+__device__ __forceinline__ double gram_entry(int kind, double acc, double na, double nb, double beta, double variance) {
+    if (kind == GABO_SQDIST_GAUSSIAN) {
+        double d2 = fma(-2.0, acc, na + nb);
+        d2 = fmax(d2, 0.0);
+        return variance * exp(-beta * d2);
+    }
+    // sphere_utils_tf.py:59-60: clamp to [-1,1], acos
+    double t = fmin(fmax(acc, -1.0), 1.0);
+    double d = acos(t);
+    if (kind == GABO_SPHERE_GAUSSIAN) return variance * exp(-beta * (d * d));   // kernels_sphere_tf.py:83-88
+    return variance * exp(-beta * d);                                            // kernels_sphere_tf.py:199-204
+}
+
+__device__ __forceinline__ void tile_coords(const GramParams& p, int64_t t, int64_t& bi, int64_t& bj) {
+    if (p.uplo == GABO_FULL) {
+        bi = t / p.tiles_n;
+        bj = t - bi * p.tiles_n;
+    } else {
+        // row tile bi (local) owns column tiles 0 .. tile_r0 + bi; tiles before it: bi*tile_r0 + bi(bi+1)/2
+        double g = (double)p.tile_r0 + 0.5;
+        int64_t b = (int64_t)floor(-g + sqrt(g * g + 2.0 * (double)t));
+        if (b < 0) b = 0;
+        while (b * p.tile_r0 + b * (b + 1) / 2 > t) --b;
+        while ((b + 1) * p.tile_r0 + (b + 1) * (b + 2) / 2 <= t) ++b;
+        bi = b;
+        bj = t - (b * p.tile_r0 + b * (b + 1) / 2);
+    }
+}
+
+template <int KLD>
+__global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel(const GramParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr uint32_t TILE_BYTES = BT * KLD * sizeof(double);
+    double* sA[NSTAGE];
+    double* sB[NSTAGE];
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+        sA[s] = reinterpret_cast<double*>(smem_raw + (size_t)s * 2 * TILE_BYTES);
+        sB[s] = reinterpret_cast<double*>(smem_raw + (size_t)s * 2 * TILE_BYTES + TILE_BYTES);
+    }
+    __shared__ __align__(8) uint64_t full_bar[NSTAGE];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&full_bar[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // work items: (tile, chunk) pairs owned by this CTA, linearised
+    const int64_t my_tiles = (p.ntiles > (int64_t)blockIdx.x) ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int64_t nitems = my_tiles * p.nchunks;
+
+    auto issue = [&](int64_t item) {
+        int64_t tl = item / p.nchunks;
+        int c = (int)(item - tl * p.nchunks);
+        int64_t t = (int64_t)blockIdx.x + tl * gridDim.x;
+        int64_t bi, bj;
+        tile_coords(p, t, bi, bj);
+        int s = (int)(item & 1);
+        const double* srcA = p.Ap + ((int64_t)c * p.n1_pad + (p.tile_r0 + bi) * BT) * KLD;
+        const double* srcB = p.Bp + ((int64_t)c * p.n2_pad + bj * BT) * KLD;
+        mbar_arrive_expect_tx(&full_bar[s], 2 * TILE_BYTES);
+        tma_bulk_g2s(sA[s], srcA, TILE_BYTES, &full_bar[s]);
+        tma_bulk_g2s(sB[s], srcB, TILE_BYTES, &full_bar[s]);
+    };
+
+    if (tid == 0 && nitems > 0) issue(0);
+
+    double acc[4][4][2];
+    for (int64_t item = 0; item < nitems; ++item) {
+        const int64_t tl = item / p.nchunks;
+        const int c = (int)(item - tl * p.nchunks);
+        const int s = (int)(item & 1);
+        // every warp is done reading stage s^1 (item-1): refill it with item+1 while this item computes
+        __syncthreads();
+        if (tid == 0 && item + 1 < nitems) issue(item + 1);
+        if (c == 0) {
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        }
+        mbar_wait(&full_bar[s], (uint32_t)((item >> 1) & 1));
+
+        const double* a_base = sA[s] + (wm * 32 + g) * KLD + q;
+        const double* b_base = sB[s] + (wn * 32 + g) * KLD + q;
+#pragma unroll
+        for (int ks = 0; ks < KLD / 4; ++ks) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = a_base[mi * 8 * KLD + ks * 4];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = b_base[ni * 8 * KLD + ks * 4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+        if (c != p.nchunks - 1) continue;
+
+        // ---- epilogue for this tile ----
+        const int64_t t = (int64_t)blockIdx.x + tl * gridDim.x;
+        int64_t bi, bj;
+        tile_coords(p, t, bi, bj);
+        const int64_t grow_tile = (p.tile_r0 + bi) * BT;   // global row of the tile
+        const int64_t gcol_tile = bj * BT;
+        const bool mirror = (p.uplo == GABO_SYMM_MIRROR) && (gcol_tile != grow_tile);
+        const bool diag_tile = p.symmetric && (gcol_tile == grow_tile);
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const int64_t grow = grow_tile + wm * 32 + mi * 8 + g;
+            const bool row_ok = grow < p.row1;
+            double na = 0.0;
+            if (p.kind == GABO_SQDIST_GAUSSIAN) na = p.normA[grow];
+            double* krow = p.K + (grow - p.row0) * p.ldk;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int64_t gcol = gcol_tile + wn * 32 + ni * 8 + 2 * q;
+                double nb0 = 0.0, nb1 = 0.0;
+                if (p.kind == GABO_SQDIST_GAUSSIAN) { nb0 = p.normB[gcol]; nb1 = p.normB[gcol + 1]; }
+                double v0 = gram_entry(p.kind, acc[mi][ni][0], na, nb0, p.beta, p.variance);
+                double v1 = gram_entry(p.kind, acc[mi][ni][1], na, nb1, p.beta, p.variance);
+                if (diag_tile) {   // K(X,X) diagonal is exactly `variance` (matches Kdiag, kernels_sphere_tf.py:105)
+                    if (gcol == grow) v0 = p.variance;
+                    if (gcol + 1 == grow) v1 = p.variance;
+                }
+                if (row_ok) {
+                    if (gcol + 1 < p.n2 && p.vec_ok) {
+                        st_cs_v2(krow + gcol, v0, v1);
+                    } else {
+                        if (gcol < p.n2) st_cs(krow + gcol, v0);
+                        if (gcol + 1 < p.n2) st_cs(krow + gcol + 1, v1);
+                    }
+                    if (mirror) {   // K[col][row] = K[row][col]; 8 lanes of equal q write 64 contiguous bytes
+                        st_cs(p.K + gcol * p.ldk + grow, v0);
+                        st_cs(p.K + (gcol + 1) * p.ldk + grow, v1);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int KLD>
+int launch_points_gram(const GramParams& p, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)NSTAGE * 2 * BT * KLD * sizeof(double);
+    GABO_CUDA_TRY(cudaFuncSetAttribute(points_gram_kernel<KLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = p.ntiles < (int64_t)sm_count() ? p.ntiles : (int64_t)sm_count();
+    if (grid <= 0) return 0;
+    points_gram_kernel<KLD><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+
+inline int pick_kld(int dim) { return dim <= 4 ? 4 : (dim <= 20 ? 20 : 52); }
+
+template <typename Tin>
+int pack_dispatch(int kld, const Tin* X, int64_t n, int64_t ldx, int dim, double* P, int64_t n_pad, int nchunks,
+                  double* norms, cudaStream_t stream) {
+    const int warps = 8;
+    unsigned grid = (unsigned)ceil_div64(n_pad, warps);
+    if (kld == 4) pack_points_kernel<4, Tin><<<grid, warps * 32, 0, stream>>>(X, n, ldx, dim, P, n_pad, nchunks, norms);
+    else if (kld == 20) pack_points_kernel<20, Tin><<<grid, warps * 32, 0, stream>>>(X, n, ldx, dim, P, n_pad, nchunks, norms);
+    else pack_points_kernel<52, Tin><<<grid, warps * 32, 0, stream>>>(X, n, ldx, dim, P, n_pad, nchunks, norms);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct PackPlan {
+    int kld, nchunks;
+    int64_t n1_pad, n2_pad;
+    size_t bytesA, bytesB, bytesNorm1, bytesNorm2;
+};
+
+inline PackPlan make_plan(int64_t n1, int64_t n2, int dim) {
+    PackPlan pl;
+    pl.kld = pick_kld(dim);
+    pl.nchunks = (dim + pl.kld - 1) / pl.kld;
+    if (pl.nchunks < 1) pl.nchunks = 1;
+    pl.n1_pad = ceil_div64(n1, BT) * BT;
+    pl.n2_pad = ceil_div64(n2, BT) * BT;
+    pl.bytesA = align256((size_t)pl.nchunks * pl.n1_pad * pl.kld * sizeof(double));
+    pl.bytesB = align256((size_t)pl.nchunks * pl.n2_pad * pl.kld * sizeof(double));
+    pl.bytesNorm1 = align256((size_t)pl.n1_pad * sizeof(double));
+    pl.bytesNorm2 = align256((size_t)pl.n2_pad * sizeof(double));
+    return pl;
+}
+
+}  // namespace
+
+template <typename Tin>
+int points_gram_impl(int kind, const Tin* X, int64_t n1, int64_t ldx, const Tin* X2, int64_t n2, int64_t ldx2, int dim,
+                     double beta, double variance, double* K, int64_t ldk, int64_t row0, int64_t row1, int uplo,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (kind < GABO_SPHERE_GAUSSIAN || kind > GABO_SQDIST_GAUSSIAN) return -1;
+    if (n1 < 0) return -3;
+    if (n1 == 0) return 0;
+    if (X == nullptr) return -2;
+    if (ldx < dim) return -4;
+    const bool symmetric = (X2 == nullptr);
+    if (symmetric) { n2 = n1; ldx2 = ldx; }
+    if (n2 < 0) return -6;
+    if (ldx2 < dim) return -7;
+    if (dim < 1) return -8;
+    if (K == nullptr) return -11;
+    if (ldk < n2) return -12;
+    if (row0 < 0 || row0 % BT != 0 || row0 > n1) return -13;
+    if (row1 < row0 || row1 > n1) return -14;
+    if (uplo < GABO_FULL || uplo > GABO_SYMM_MIRROR) return -15;
+    if (uplo != GABO_FULL && !symmetric) return -15;
+    if (uplo == GABO_SYMM_MIRROR && !(row0 == 0 && row1 == n1)) return -15;
+    if (row1 == row0 || n2 == 0) return 0;
+
+    PackPlan pl = make_plan(n1, n2, dim);
+    size_t need = pl.bytesA + pl.bytesNorm1 + (symmetric ? 0 : pl.bytesB + pl.bytesNorm2);
+    if (workspace == nullptr) return -16;
+    if (workspace_bytes < need) return -17;
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return -16;
+    double* Ap = reinterpret_cast<double*>(ws);
+    double* nA = reinterpret_cast<double*>(ws + pl.bytesA);
+    double* Bp = Ap;
+    double* nB = nA;
+    const bool want_norm = (kind == GABO_SQDIST_GAUSSIAN);
+    int rc = pack_dispatch<Tin>(pl.kld, X, n1, ldx, dim, Ap, pl.n1_pad, pl.nchunks, want_norm ? nA : nullptr, stream);
+    if (rc) return rc;
+    if (!symmetric) {
+        Bp = reinterpret_cast<double*>(ws + pl.bytesA + pl.bytesNorm1);
+        nB = reinterpret_cast<double*>(ws + pl.bytesA + pl.bytesNorm1 + pl.bytesB);
+        rc = pack_dispatch<Tin>(pl.kld, X2, n2, ldx2, dim, Bp, pl.n2_pad, pl.nchunks, want_norm ? nB : nullptr, stream);
+        if (rc) return rc;
+    }
+
+    GramParams p;
+    p.Ap = Ap; p.Bp = Bp; p.normA = want_norm ? nA : nullptr; p.normB = want_norm ? nB : nullptr;
+    p.K = K; p.ldk = ldk; p.n1_pad = pl.n1_pad; p.n2_pad = pl.n2_pad;
+    p.row0 = row0; p.row1 = row1; p.n2 = n2; p.nchunks = pl.nchunks; p.kind = kind; p.uplo = uplo;
+    p.symmetric = symmetric ? 1 : 0;
+    p.vec_ok = ((ldk % 2) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0) ? 1 : 0;
+    p.beta = beta; p.variance = variance;
+    p.tile_r0 = row0 / BT;
+    p.tiles_m = ceil_div64(row1 - row0, BT);
+    p.tiles_n = ceil_div64(n2, BT);
+    if (uplo == GABO_FULL) p.ntiles = p.tiles_m * p.tiles_n;
+    else p.ntiles = p.tiles_m * p.tile_r0 + p.tiles_m * (p.tiles_m + 1) / 2;
+    if (pl.kld == 4) return launch_points_gram<4>(p, stream);
+    if (pl.kld == 20) return launch_points_gram<20>(p, stream);
+    return launch_points_gram<52>(p, stream);
+}
+
+}  // namespace gabo
+
+extern "C" size_t gabo_points_gram_workspace_bytes(int64_t n1, int64_t n2, int dim) {
+    if (n1 < 0 || n2 < 0 || dim < 1) return 0;
+    gabo::PackPlan pl = gabo::make_plan(n1, n2, dim);
+    return pl.bytesA + pl.bytesNorm1 + pl.bytesB + pl.bytesNorm2;
+}
+
+extern "C" int gabo_points_gram_f64(int kind, const double* X, int64_t n1, int64_t ldx, const double* X2, int64_t n2,
+                                    int64_t ldx2, int dim, double beta, double variance, double* K, int64_t ldk,
+                                    int64_t row0, int64_t row1, int uplo, void* workspace, size_t workspace_bytes,
+                                    gabo_stream_t stream) {
+    return gabo::points_gram_impl<double>(kind, X, n1, ldx, X2, n2, ldx2, dim, beta, variance, K, ldk, row0, row1, uplo,
+                                          workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,123 @@
+"""GP regression on the B200 linear-algebra kernels: the slice of GPflow 0.5's ``gpflow.gpr.GPR`` [3P] that the
+reference drives (``examples/kernels/sphere/sphere_kernels.py:131-139``, ``examples/kernels/spd/spd_kernels.py:146-170``,
+every BO iteration through GPflowOpt).
+
+    K  = kern.K(X) + sigma^2 I         -> Gram tile kernel, lower tiles only
+    L  = chol(K)                       -> gabo_potrf_f64 (sigma^2 added in-kernel)
+    V  = L^-1 (Y - m(X))               -> gabo_trsm_f64
+    ll = -N P/2 log 2pi - P sum log L_ii - 1/2 ||V||^2          -> gabo_gp_loglik_f64
+    A  = L^-1 K(X, X*) ; mean = A^T V + m ; var = Kdiag(X*) - colsum(A^2) ; cov = K(X*) - A^T A
+
+GPflow 0.5 refactorises on every call; here the factor is cached and reused until a hyper-parameter or the data
+changes (same results).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .param import Param, Parameterized, to_device
+
+
+class Gaussian(Parameterized):
+    """``gpflow.likelihoods.Gaussian``: noise variance sigma^2, default 1.0."""
+
+    def __init__(self, variance=1.0):
+        self.variance = Param(variance, transform='positive')
+
+
+class Zero:
+    """``gpflow.mean_functions.Zero``."""
+    c = 0.0
+
+
+class Constant(Parameterized):
+    """``gpflow.mean_functions.Constant`` with a scalar constant."""
+
+    def __init__(self, c=0.0):
+        self.c = Param(c, transform=None)
+
+
+class GPR(Parameterized):
+    def __init__(self, X, Y, kern, mean_function=None):
+        self.X = to_device(X)
+        Yd = to_device(Y)
+        if Yd.dim() == 1:
+            Yd = Yd.unsqueeze(1)
+        if Yd.shape[0] != self.X.shape[0]:
+            Yd = Yd.t().contiguous()
+        self.Y = Yd.contiguous()
+        self.kern = kern
+        self.mean_function = mean_function if mean_function is not None else Zero()
+        self.likelihood = Gaussian()
+        self._cache_key = None
+        self._L = None
+        self._V = None
+
+    # ---- state ------------------------------------------------------------------------------------
+    def _mean_const(self) -> float:
+        return float(self.mean_function.c)
+
+    def _key(self):
+        kp = tuple(sorted((k, float(v)) for k, v in self.kern.params().items()))
+        extra = tuple(sorted((k, v) for k, v in self.kern.__dict__.items() if isinstance(v, (int, float))))
+        return (kp, extra, float(self.likelihood.variance), self._mean_const(), self.X.data_ptr(), self.X._version,
+                self.Y.data_ptr(), self.Y._version)
+
+    def _factorise(self):
+        key = self._key()
+        if self._cache_key == key and self._L is not None:
+            return self._L, self._V
+        n = int(self.X.shape[0])
+        if self._L is None or self._L.shape[0] != n:
+            self._L = torch.empty((n, n), dtype=torch.float64, device=self.X.device)
+        self.kern.K(self.X, uplo='lower', out=self._L)
+        ops.potrf_(self._L, float(self.likelihood.variance), check=True)
+        V = (self.Y - self._mean_const()).contiguous()
+        ops.trsm_(self._L, V, trans=False)
+        self._V = V
+        self._cache_key = key
+        return self._L, self._V
+
+    # ---- device-level graph pieces (GPflow: build_likelihood / build_predict) --------------------------
+    def build_likelihood(self) -> torch.Tensor:
+        L, V = self._factorise()
+        return ops.gp_loglik(L, V)
+
+    def build_predict(self, Xnew, full_cov=False):
+        L, V = self._factorise()
+        Xn = to_device(Xnew)
+        A = self.kern.K(self.X, Xn)                    # [N, M]
+        ops.trsm_(L, A, trans=False)
+        kd = self.kern.Kdiag(Xn)
+        mean, var = ops.gp_predict(A, V, kd, self._mean_const())
+        if not full_cov:
+            p = int(V.shape[1])
+            return mean, var.unsqueeze(1).expand(-1, p).contiguous()
+        cov = self.kern.K(Xn)                          # [M, M]
+        At = A.t().contiguous()                        # [M, N]
+        ops.gemm_nt_sub_(cov, At, At, lower=False)
+        p = int(V.shape[1])
+        return mean, cov.unsqueeze(2).expand(-1, -1, p).contiguous()
+
+    # ---- AutoFlow-style NumPy API ---------------------------------------------------------------------
+    def compute_log_likelihood(self) -> float:
+        return float(self.build_likelihood().item())
+
+    def predict_f(self, Xnew):
+        m, v = self.build_predict(Xnew, full_cov=False)
+        return m.cpu().numpy(), v.cpu().numpy()
+
+    def predict_f_full_cov(self, Xnew):
+        m, c = self.build_predict(Xnew, full_cov=True)
+        return m.cpu().numpy(), c.cpu().numpy()
+
+    def predict_y(self, Xnew):
+        m, v = self.build_predict(Xnew, full_cov=False)
+        return m.cpu().numpy(), (v + float(self.likelihood.variance)).cpu().numpy()
+
+    def optimize(self, *args, **kwargs):
+        raise NotImplementedError(
+            'hyper-parameter optimisation needs the analytic gradients of the path (SURVEY.md section 8f-1); '
+            'set parameters explicitly (kern.update_beta, kern.variance = ..., likelihood.variance = ...)')

@@ -1,0 +1,257 @@
+"""Operator layer: torch CUDA tensors in, C-ABI calls (include/gabo_b200.h) on the current stream, torch tensors out.
+
+PyTorch is only the allocator / stream owner here; all arithmetic happens in libgabo_b200.so.  Every function
+raises if the input is not a CUDA tensor -- there is no CPU path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+SPHERE_GAUSSIAN, SPHERE_LAPLACE, SQDIST_GAUSSIAN = 0, 1, 2
+SPD_AI_GAUSSIAN, SPD_AI_LAPLACE, SPD_STEIN = 0, 1, 2
+FULL, LOWER, SYMM_MIRROR = 0, 1, 2
+_UPLO = {'full': FULL, 'lower': LOWER, 'mirror': SYMM_MIRROR, FULL: FULL, LOWER: LOWER, SYMM_MIRROR: SYMM_MIRROR}
+ROW_BLOCK = 128   # row-sharding granularity of the Gram kernels
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float64) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f'{name} must be a CUDA tensor (gaboflow_b200 has no CPU path)')
+    if t.dtype != dtype:
+        raise TypeError(f'{name} must be {dtype}, got {t.dtype}')
+    return t
+
+
+def _rowmajor2d(t: torch.Tensor) -> torch.Tensor:
+    if t.dim() != 2:
+        raise ValueError('expected a 2-D tensor')
+    if t.stride(1) != 1 and t.shape[1] > 1:
+        t = t.contiguous()
+    if t.shape[1] == 1 and t.stride(0) < 1:
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return max(int(t.stride(0)), int(t.shape[1])) if t.shape[0] > 1 else int(t.shape[1])
+
+
+def device_info():
+    import ctypes as C
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    _lib.check('gabo_device_info', _lib.lib().gabo_device_info(C.byref(a), C.byref(b), C.byref(c)))
+    return {'sm_count': a.value, 'cc': (b.value, c.value)}
+
+
+# --------------------------------------------------------------------------------------------------
+def points_gram(kind: int, X: torch.Tensor, X2: Optional[torch.Tensor] = None, beta: float = 1.0,
+                variance: float = 1.0, out: Optional[torch.Tensor] = None, row0: int = 0,
+                row1: Optional[int] = None, uplo='full', workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K[row0:row1, :] of the sphere Gaussian / Laplace or squared-distance Gaussian Gram (FP64 or FP32 by X.dtype)."""
+    L = _lib.lib()
+    dtype = X.dtype
+    if dtype not in (torch.float64, torch.float32):
+        raise TypeError('X must be float64 or float32')
+    X = _rowmajor2d(_req(X, 'X', dtype))
+    n1, dim = int(X.shape[0]), int(X.shape[1])
+    if X2 is not None:
+        X2 = _rowmajor2d(_req(X2, 'X2', dtype))
+        if X2.shape[1] != dim:
+            raise ValueError('X and X2 must have the same number of columns')
+        n2 = int(X2.shape[0])
+    else:
+        n2 = n1
+    if row1 is None:
+        row1 = n1
+    rows = row1 - row0
+    if out is None:
+        out = torch.empty((rows, n2), dtype=dtype, device=X.device)
+    else:
+        _req(out, 'out', dtype)
+        if out.dim() != 2 or out.shape[0] < rows or out.shape[1] != n2 or (n2 > 1 and out.stride(1) != 1):
+            raise ValueError('out must be a row-major [row1-row0, n2] tensor')
+    nbytes = int(L.gabo_points_gram_workspace_bytes(n1, n2, dim))
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=X.device)
+    fn_name = 'gabo_points_gram_f64' if dtype == torch.float64 else 'gabo_points_gram_f32'
+    st = getattr(L, fn_name)(int(kind), X.data_ptr(), n1, _ld(X),
+                             X2.data_ptr() if X2 is not None else None, n2, _ld(X2) if X2 is not None else 0,
+                             dim, float(beta), float(variance), out.data_ptr(), _ld(out) if rows > 1 else max(n2, int(out.stride(0))),
+                             int(row0), int(row1), _UPLO[uplo], workspace.data_ptr(), workspace.numel(), _stream())
+    _lib.check(fn_name, st)
+    return out
+
+
+def kdiag_const(n: int, variance: float, device) -> torch.Tensor:
+    out = torch.empty((n,), dtype=torch.float64, device=device)
+    _lib.check('gabo_kdiag_const_f64', _lib.lib().gabo_kdiag_const_f64(n, float(variance), out.data_ptr(), _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class SpdPrep:
+    """Per-point quantities of a set of SPD matrices (see gabo_spd_prep_f64)."""
+    d: int
+    n: int
+    S: Optional[torch.Tensor]        # [n, d*d]
+    W: Optional[torch.Tensor]        # [n, d*d]  inverse lower Cholesky factor
+    logdet: Optional[torch.Tensor]   # [n]
+    logm: Optional[torch.Tensor]     # [n, m]    Mandel(logm S)
+    info: torch.Tensor               # [n] int32
+
+
+def spd_prep(Xm: torch.Tensor, d: int, want_S=True, want_W=True, want_logdet=True, want_logm=False) -> SpdPrep:
+    Xm = _rowmajor2d(_req(Xm, 'Xmandel'))
+    n, m = int(Xm.shape[0]), int(Xm.shape[1])
+    if m != d * (d + 1) // 2:
+        raise ValueError(f'Mandel length {m} does not match matrix_dim {d}')
+    dev = Xm.device
+    S = torch.empty((n, d * d), dtype=torch.float64, device=dev) if want_S else None
+    W = torch.empty((n, d * d), dtype=torch.float64, device=dev) if want_W else None
+    ld = torch.empty((n,), dtype=torch.float64, device=dev) if want_logdet else None
+    lm = torch.empty((n, m), dtype=torch.float64, device=dev) if want_logm else None
+    info = torch.zeros((max(n, 1),), dtype=torch.int32, device=dev)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    st = _lib.lib().gabo_spd_prep_f64(Xm.data_ptr(), n, _ld(Xm), d, ptr(S), ptr(W), ptr(ld), ptr(lm),
+                                      info.data_ptr(), _stream())
+    _lib.check('gabo_spd_prep_f64', st)
+    return SpdPrep(d, n, S, W, ld, lm, info[:n])
+
+
+def spd_gram(kind: int, p1: SpdPrep, p2: Optional[SpdPrep] = None, beta: float = 1.0, variance: float = 1.0,
+             out: Optional[torch.Tensor] = None, row0: int = 0, row1: Optional[int] = None, uplo='full') -> torch.Tensor:
+    symmetric = p2 is None
+    if symmetric:
+        p2 = p1
+    if p1.d != p2.d:
+        raise ValueError('matrix_dim mismatch')
+    n1, n2 = p1.n, p2.n
+    if row1 is None:
+        row1 = n1
+    rows = row1 - row0
+    dev = p1.info.device
+    if out is None:
+        out = torch.empty((rows, n2), dtype=torch.float64, device=dev)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    st = _lib.lib().gabo_spd_gram_f64(int(kind), p1.d, ptr(p1.W), ptr(p1.S), ptr(p1.logdet), n1,
+                                      ptr(p2.S), ptr(p2.logdet), n2, 1 if symmetric else 0,
+                                      float(beta), float(variance), out.data_ptr(),
+                                      _ld(out) if rows > 1 else max(n2, int(out.stride(0))),
+                                      int(row0), int(row1), _UPLO[uplo], _stream())
+    _lib.check('gabo_spd_gram_f64', st)
+    return out
+
+
+def spd_stein_kdiag(p: SpdPrep, beta: float, variance: float) -> torch.Tensor:
+    out = torch.empty((p.n,), dtype=torch.float64, device=p.info.device)
+    st = _lib.lib().gabo_spd_stein_kdiag_f64(p.logdet.data_ptr(), p.n, float(beta), float(variance), out.data_ptr(), _stream())
+    _lib.check('gabo_spd_stein_kdiag_f64', st)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def potrf_(A: torch.Tensor, sigma2: float = 0.0, check: bool = True) -> torch.Tensor:
+    """In-place lower Cholesky of A + sigma2*I (row-major, lower triangle).  Returns the device info word;
+    with check=True a non-zero info raises numpy.linalg.LinAlgError (one host sync)."""
+    _req(A, 'A')
+    if A.dim() != 2 or A.shape[0] != A.shape[1] or (A.shape[1] > 1 and A.stride(1) != 1):
+        raise ValueError('A must be a square row-major matrix')
+    n = int(A.shape[0])
+    L = _lib.lib()
+    nbytes = int(L.gabo_potrf_workspace_bytes(n))
+    key = (A.device.index, 'potrf')
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=A.device)
+        _ws_cache[key] = ws
+    info = torch.zeros((1,), dtype=torch.int32, device=A.device)
+    st = L.gabo_potrf_f64(n, A.data_ptr(), _ld(A) if n > 1 else 1, float(sigma2), info.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check('gabo_potrf_f64', st)
+    if check:
+        k = int(info.item())
+        if k != 0:
+            raise np.linalg.LinAlgError(f'Cholesky failed: leading minor of order {k} is not positive definite')
+    return info
+
+
+def trsm_(L_: torch.Tensor, B: torch.Tensor, trans: bool = False) -> torch.Tensor:
+    """B <- L^-1 B (or L^-T B), in place; B is [n, nrhs] row-major."""
+    _req(L_, 'L'); _req(B, 'B')
+    if B.dim() == 1:
+        B = B.unsqueeze(1)
+    n = int(L_.shape[0])
+    if B.shape[0] != n or (B.shape[1] > 1 and B.stride(1) != 1):
+        raise ValueError('B must be a row-major [n, nrhs] tensor')
+    Lh = _lib.lib()
+    nbytes = int(Lh.gabo_trsm_workspace_bytes(n, int(B.shape[1])))
+    key = (L_.device.index, 'trsm')
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=L_.device)
+        _ws_cache[key] = ws
+    st = Lh.gabo_trsm_f64(1 if trans else 0, n, int(B.shape[1]), L_.data_ptr(), _ld(L_) if n > 1 else 1,
+                          B.data_ptr(), max(int(B.stride(0)), int(B.shape[1])) if n > 1 else int(B.shape[1]),
+                          ws.data_ptr(), ws.numel(), _stream())
+    _lib.check('gabo_trsm_f64', st)
+    return B
+
+
+def logdet_half(L_: torch.Tensor) -> torch.Tensor:
+    """sum_i log L_ii as a device scalar tensor."""
+    _req(L_, 'L')
+    n = int(L_.shape[0])
+    out = torch.empty((1,), dtype=torch.float64, device=L_.device)
+    st = _lib.lib().gabo_logdet_f64(n, L_.data_ptr(), _ld(L_) if n > 1 else 1, out.data_ptr(), _stream())
+    _lib.check('gabo_logdet_f64', st)
+    return out
+
+
+def gp_loglik(L_: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
+    _req(L_, 'L'); _req(alpha, 'alpha')
+    n, p = int(alpha.shape[0]), int(alpha.shape[1])
+    out = torch.empty((1,), dtype=torch.float64, device=L_.device)
+    st = _lib.lib().gabo_gp_loglik_f64(n, p, L_.data_ptr(), _ld(L_) if n > 1 else 1, alpha.data_ptr(),
+                                       max(int(alpha.stride(0)), p) if n > 1 else p, out.data_ptr(), _stream())
+    _lib.check('gabo_gp_loglik_f64', st)
+    return out
+
+
+def gp_predict(A: torch.Tensor, V: torch.Tensor, kdiag: torch.Tensor, mean_const: float = 0.0):
+    """mean[M,p] = A^T V + mean_const, var[M] = kdiag - colsum(A*A) from A = L^-1 K(X,X*) and V = L^-1 (y-m)."""
+    _req(A, 'A'); _req(V, 'V'); _req(kdiag, 'kdiag')
+    n, M = int(A.shape[0]), int(A.shape[1])
+    p = int(V.shape[1])
+    mean = torch.empty((M, p), dtype=torch.float64, device=A.device)
+    var = torch.empty((M,), dtype=torch.float64, device=A.device)
+    st = _lib.lib().gabo_gp_predict_f64(n, M, p, A.data_ptr(), max(int(A.stride(0)), M) if n > 1 else M,
+                                        V.data_ptr(), max(int(V.stride(0)), p) if n > 1 else p,
+                                        kdiag.data_ptr(), float(mean_const), mean.data_ptr(), var.data_ptr(), _stream())
+    _lib.check('gabo_gp_predict_f64', st)
+    return mean, var
+
+
+def gemm_nt_sub_(Cm: torch.Tensor, A: torch.Tensor, B: torch.Tensor, lower: bool = False) -> torch.Tensor:
+    """C <- C - A B^T (lower triangle only if lower), all row-major FP64."""
+    _req(Cm, 'C'); _req(A, 'A'); _req(B, 'B')
+    m, n, k = int(Cm.shape[0]), int(Cm.shape[1]), int(A.shape[1])
+    if A.shape[0] != m or B.shape[0] != n or B.shape[1] != k:
+        raise ValueError('shape mismatch in gemm_nt_sub_')
+    ld = lambda t: max(int(t.stride(0)), int(t.shape[1])) if t.shape[0] > 1 else int(t.shape[1])
+    st = _lib.lib().gabo_gemm_nt_sub_f64(m, n, k, A.data_ptr(), ld(A), B.data_ptr(), ld(B), Cm.data_ptr(), ld(Cm),
+                                         1 if lower else 0, _stream())
+    _lib.check('gabo_gemm_nt_sub_f64', st)
+    return Cm

@@ -1,0 +1,110 @@
+"""Minimal stand-ins for the GPflow 0.5 pieces the reference kernel classes lean on [3P]:
+``gpflow.param.Param`` (a named, positive-transformed scalar with ``.value``) and the ``gpflow.kernels.Kern`` base
+(``input_dim``, ``active_dims``, the AutoFlow wrappers ``compute_K`` / ``compute_K_symm`` / ``compute_Kdiag`` that
+the reference examples call with NumPy arrays, e.g. ``examples/kernels/sphere/sphere_kernels.py:127-129``).
+
+Only host logic lives here; all arithmetic is in the CUDA library.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+class Param:
+    """Scalar hyper-parameter.  ``.value`` returns a fresh 1-element float64 array like GPflow 0.5's
+    ``Param.value`` (which is why the reference's ``get_beta()`` returns an array, ``kernels_sphere_tf.py:138``)."""
+
+    def __init__(self, value, transform='positive'):
+        self.transform = transform
+        self._array = np.atleast_1d(np.asarray(value, dtype=np.float64)).copy()
+        self.fixed = False
+
+    @property
+    def value(self):
+        return self._array.copy()
+
+    def assign(self, value):
+        self._array = np.atleast_1d(np.asarray(value, dtype=np.float64)).copy()
+
+    def __float__(self):
+        return float(self._array.reshape(-1)[0])
+
+    # arithmetic used in the kernel bodies (``self.beta_shifted + self.beta_min_value``)
+    def __add__(self, other):
+        return float(self) + float(other)
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return float(self) - float(other)
+
+    def __rsub__(self, other):
+        return float(other) - float(self)
+
+    def __mul__(self, other):
+        return float(self) * float(other)
+
+    __rmul__ = __mul__
+
+    def __repr__(self):
+        return f'Param({float(self)!r}, transform={self.transform!r})'
+
+
+class Parameterized:
+    """Assigning a number to an attribute that already holds a Param updates the Param in place, as GPflow 0.5's
+    ``Parameterized.__setattr__`` does (the reference's ``update_beta`` relies on it: ``kernels_sphere_tf.py:122``)."""
+
+    def __setattr__(self, key, value):
+        cur = self.__dict__.get(key)
+        if isinstance(cur, Param) and not isinstance(value, Param):
+            cur.assign(value)
+        else:
+            object.__setattr__(self, key, value)
+
+    def params(self):
+        return {k: v for k, v in self.__dict__.items() if isinstance(v, Param)}
+
+
+def _cuda_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError('gaboflow_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def to_device(X, dtype=torch.float64):
+    """NumPy array / list / CPU tensor -> CUDA tensor; CUDA tensors pass through untouched (zero-copy)."""
+    if isinstance(X, torch.Tensor):
+        if X.is_cuda:
+            return X if X.dtype == dtype else X.to(dtype)
+        return X.to(device=_cuda_device(), dtype=dtype, non_blocking=True)
+    arr = np.ascontiguousarray(np.asarray(X, dtype=np.float64 if dtype == torch.float64 else np.float32))
+    if arr.ndim == 1:
+        arr = arr[None, :]
+    return torch.from_numpy(arr).to(device=_cuda_device(), non_blocking=True)
+
+
+class Kern(Parameterized):
+    """Base of the manifold kernels: the slice of ``gpflow.kernels.Kern`` (0.5) that the reference uses."""
+
+    def __init__(self, input_dim, active_dims=None):
+        self.input_dim = int(input_dim)
+        # accepted and stored, never applied -- same as the reference, whose K() bodies do not call _slice
+        self.active_dims = list(active_dims) if active_dims is not None else list(range(self.input_dim))
+
+    # subclasses implement K(X, X2=None) and Kdiag(X) on device tensors
+    def K(self, X, X2=None):
+        raise NotImplementedError
+
+    def Kdiag(self, X):
+        raise NotImplementedError
+
+    # AutoFlow-style wrappers: NumPy in, NumPy out (host<->device copies included)
+    def compute_K(self, X, Z):
+        return self.K(X, Z).cpu().numpy()
+
+    def compute_K_symm(self, X):
+        return self.K(X).cpu().numpy()
+
+    def compute_Kdiag(self, X):
+        return self.Kdiag(X).cpu().numpy()

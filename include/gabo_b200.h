@@ -1,0 +1,154 @@
+/* gabo_b200.h -- C ABI of the B200-native (sm_100a) GaBOflow hot path.
+ *
+ * The reference (NoemieJaquier/GaBOflow) has no FFI: its boundary for this path is the Python
+ * kernel-class contract (K / Kdiag on a gpflow.kernels.Kern subclass) plus GPflow 0.5's GPR
+ * linear algebra.  Each entry point below names the reference code it replaces (paths relative
+ * to the reference root).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE pointer unless the name ends in _host;
+ *   - matrices are row-major (NumPy / torch default), leading dimension in ELEMENTS;
+ *   - points are rows; SPD inputs arrive as Mandel vectors [n, d(d+1)/2]
+ *     (SPD_utils_tf.py:11-65 ordering: main diagonal, then super-diagonals 1..d-1, off-diagonal
+ *     slots scaled by sqrt(2));
+ *   - no internal allocation: scratch is passed in, sized by the matching *_workspace_bytes();
+ *   - stream is a cudaStream_t passed as void*; calls are asynchronous on that stream, re-entrant,
+ *     and keep no global state;
+ *   - return value: 0 ok; -k = argument k (1-based) is invalid; GABO_ERR_CUDA-e = CUDA runtime
+ *     error e at launch.  Numerical failures (non-SPD input, failed Cholesky pivot) are reported
+ *     LAPACK-style through device-side info words, never by aborting (the reference's TF ops raise
+ *     InvalidArgumentError on a failed Cholesky and GPflowOpt retries with more jitter).
+ *   - there is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef GABO_B200_H
+#define GABO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GABO_ABI_VERSION 1
+#define GABO_ERR_CUDA (-1000)
+
+typedef void* gabo_stream_t; /* cudaStream_t */
+
+/* Point-set Gram kinds (one fused tile kernel; csrc/points_gram.cu). */
+enum gabo_points_kind {
+    GABO_SPHERE_GAUSSIAN = 0, /* variance*exp(-beta*acos(clamp(x.y))^2)  kernels_sphere_tf.py:59-88 + sphere_utils_tf.py:11-60 */
+    GABO_SPHERE_LAPLACE = 1,  /* variance*exp(-beta*acos(clamp(x.y)))    kernels_sphere_tf.py:179-204 */
+    GABO_SQDIST_GAUSSIAN = 2  /* variance*exp(-beta*||x-y||^2): SpdFrobeniusGaussianKernel.K (kernels_spd_tf.py:495-533)
+                                 on the Mandel vectors, SpdLogEuclideanGaussianKernel.K (:603-641) on Mandel(logm) */
+};
+
+/* SPD pair kinds (csrc/spd_gram.cu). */
+enum gabo_spd_kind {
+    GABO_SPD_AI_GAUSSIAN = 0, /* variance*exp(-beta*d_AI^2)   kernels_spd_tf.py:214-248 + SPD_utils_tf.py:95-139 */
+    GABO_SPD_AI_LAPLACE = 1,  /* variance*exp(-beta*d_AI)     kernels_spd_tf.py:368-400 */
+    GABO_SPD_STEIN = 2        /* variance*det(A B)^beta/det((A+B)/2)^beta, as coded at kernels_spd_tf.py:98-112 */
+};
+
+/* Which part of a symmetric Gram (X2 == NULL) is produced. */
+enum gabo_uplo {
+    GABO_FULL = 0,        /* every entry computed (what K(X) returns in the reference) */
+    GABO_LOWER = 1,       /* tiles on/below the diagonal only (input of gabo_potrf_f64); upper part untouched */
+    GABO_SYMM_MIRROR = 2  /* lower tiles computed once and mirror-stored: full, exactly symmetric matrix; needs row0==0,row1==n */
+};
+
+int gabo_abi_version(void);
+/* Fills SM count and compute capability of the current device. */
+int gabo_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Static, human-readable text for a status code returned by any call below. */
+const char* gabo_status_string(int status);
+
+/* ---- Point-set Gram: sphere Gaussian / Laplace, squared-distance Gaussian -------------------------
+ * Replaces sphere_distance_tf (sphere_utils_tf.py:11-60) + SphereGaussianKernel.K / SphereLaplaceKernel.K
+ * (kernels_sphere_tf.py:59-88, 179-204) and the pair stage of the Frobenius / Log-Euclidean kernels.
+ * K[(i-row0)*ldk + j] = k(X[i], X2[j]) for row0 <= i < row1, 0 <= j < n2.  X2 == NULL means X2 = X
+ * (kernels_sphere_tf.py:75-76); in that case the diagonal is exactly `variance`.
+ * row0 must be a multiple of 128 (row-block sharding across GPUs uses 128-row granularity). */
+size_t gabo_points_gram_workspace_bytes(int64_t n1, int64_t n2, int dim);
+int gabo_points_gram_f64(int kind, const double* X, int64_t n1, int64_t ldx,
+                         const double* X2, int64_t n2, int64_t ldx2, int dim,
+                         double beta, double variance,
+                         double* K, int64_t ldk, int64_t row0, int64_t row1, int uplo,
+                         void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+/* FP32 mode of the same kernel (north_star: 1e-5 relative). */
+int gabo_points_gram_f32(int kind, const float* X, int64_t n1, int64_t ldx,
+                         const float* X2, int64_t n2, int64_t ldx2, int dim,
+                         float beta, float variance,
+                         float* K, int64_t ldk, int64_t row0, int64_t row1, int uplo,
+                         void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+
+/* Kdiag = fill([n], variance)   (kernels_sphere_tf.py:105,221; kernels_spd_tf.py:265,417,550,658). */
+int gabo_kdiag_const_f64(int64_t n, double variance, double* out, gabo_stream_t stream);
+
+/* ---- SPD per-point preparation ---------------------------------------------------------------------
+ * Replaces vector_to_symmetric_matrix_tf (SPD_utils_tf.py:11-65) and hoists the per-PAIR inverse / sqrtm /
+ * logm of the reference (SPD_utils_tf.py:129, kernels_spd_tf.py:634) to once per point:
+ *   S[i]      d x d symmetric matrix of Mandel row i                    (out_S, [n,d*d], may be NULL)
+ *   W[i]      inverse of the lower Cholesky factor of S[i]              (out_W, [n,d*d], may be NULL)
+ *   logdet[i] log det S[i]                                              (out_logdet, [n], may be NULL)
+ *   logm[i]   Mandel vector of the matrix logarithm (Jacobi eigen)      (out_logm_mandel, [n,m], may be NULL)
+ *   info[i]   0, or k>0 if the k-th Cholesky pivot of S[i] is not positive (outputs for i are NaN)
+ * 2 <= d <= 8. */
+int gabo_spd_prep_f64(const double* Xmandel, int64_t n, int64_t ldx, int d,
+                      double* out_S, double* out_W, double* out_logdet, double* out_logm_mandel,
+                      int32_t* info, gabo_stream_t stream);
+
+/* ---- SPD pair Gram -----------------------------------------------------------------------------------
+ * Affine-invariant kinds replace affine_invariant_distance_tf (SPD_utils_tf.py:95-139):
+ *   d_AI(i,j)^2 = sum_k log^2 lambda_k( W1[i] S2[j] W1[i]^T ), eigenvalues by cyclic Jacobi in registers.
+ * Stein replaces kernels_spd_tf.py:98-112: exp(beta*(logdet1[i]+logdet2[j]-logdet((S1[i]+S2[j])/2))).
+ * W1 / S1 / logdet1 describe X (rows), S2 / logdet2 describe X2 (columns); `symmetric` != 0 states that
+ * both describe the same point set (enables uplo modes and the exact diagonal for the AI kinds).
+ * Unused inputs for a kind may be NULL (AI: S1, logdet1, logdet2; Stein: W1). */
+int gabo_spd_gram_f64(int kind, int d,
+                      const double* W1, const double* S1, const double* logdet1, int64_t n1,
+                      const double* S2, const double* logdet2, int64_t n2, int symmetric,
+                      double beta, double variance,
+                      double* K, int64_t ldk, int64_t row0, int64_t row1, int uplo,
+                      gabo_stream_t stream);
+/* SpdSteinGaussianKernel.Kdiag = diag_part(K(X)) (kernels_spd_tf.py:129) = variance*exp(beta*logdet[i]). */
+int gabo_spd_stein_kdiag_f64(const double* logdet, int64_t n, double beta, double variance,
+                             double* out, gabo_stream_t stream);
+
+/* ---- GP linear algebra (GPflow 0.5 GPR.build_likelihood / build_predict; call sites
+ *      examples/kernels/sphere/sphere_kernels.py:131-139, examples/kernels/spd/spd_kernels.py:146-170) ----
+ * gabo_potrf_f64: A <- chol(A + sigma2*I), lower triangle of the row-major n x n matrix, in place
+ *   (tf.cholesky of K + sigma^2 I).  Blocked right-looking; trailing updates on the FP64 DMMA pipe.
+ *   *info (device int32) = 0, or k>0 if the leading minor of order k is not positive definite.
+ *   The strictly upper triangle is neither read nor written. */
+size_t gabo_potrf_workspace_bytes(int64_t n);
+int gabo_potrf_f64(int64_t n, double* A, int64_t lda, double sigma2, int32_t* info,
+                   void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+/* gabo_trsm_f64: B <- L^-1 B (trans == 0) or L^-T B (trans != 0); L lower n x n row-major, B [n, nrhs]
+ *   row-major, in place (tf.matrix_triangular_solve).  The workspace holds the inverses of the 128 x 128
+ *   diagonal blocks of L, after which the substitution is a chain of DMMA products. */
+size_t gabo_trsm_workspace_bytes(int64_t n, int64_t nrhs);
+int gabo_trsm_f64(int trans, int64_t n, int64_t nrhs, const double* L, int64_t ldl,
+                  double* B, int64_t ldb, void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+/* out[0] = sum_i log L_ii  (half the log-determinant of K + sigma^2 I). */
+int gabo_logdet_f64(int64_t n, const double* L, int64_t ldl, double* out, gabo_stream_t stream);
+/* out[0] = -0.5*n*p*log(2 pi) - p*sum_i log L_ii - 0.5*||alpha||_F^2, alpha = L^-1 (y - m) already solved,
+ *   [n,p] row-major (GPflow 0.5 densities.multivariate_normal summed over the p output columns). */
+int gabo_gp_loglik_f64(int64_t n, int64_t p, const double* L, int64_t ldl,
+                       const double* alpha, int64_t ldalpha, double* out, gabo_stream_t stream);
+/* Posterior at M test points from A = L^-1 K(X,X*) [n,M] and V = L^-1 (y-m) [n,p]:
+ *   mean[M,p] = A^T V + mean_const ;  var[M] = kdiag[M] - colsum(A*A)   (GPR.build_predict, full_cov False). */
+int gabo_gp_predict_f64(int64_t n, int64_t M, int64_t p, const double* A, int64_t lda,
+                        const double* V, int64_t ldv, const double* kdiag, double mean_const,
+                        double* mean_out, double* var_out, gabo_stream_t stream);
+/* C <- C - A B^T on the lower triangle only when `lower` != 0 (SYRK-shaped when A == B), else full:
+ *   C [m,n], A [m,k], B [n,k] row-major.  The DMMA trailing-update kernel of the Cholesky, exported
+ *   because the multi-GPU block-cyclic factorisation and predict_f_full_cov (cov = K** - A^T A) reuse it. */
+int gabo_gemm_nt_sub_f64(int64_t m, int64_t n, int64_t k, const double* A, int64_t lda,
+                         const double* B, int64_t ldb, double* C, int64_t ldc, int lower,
+                         gabo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GABO_B200_H */

@@ -1,0 +1,233 @@
+"""Parity of the CUDA Gram kernels (through the C-ABI / kernel classes) against the NumPy oracle and the golden
+fixtures generated from the reference's own NumPy code.  Tolerance: 1e-12 relative for FP64 Gram entries
+(BASELINE.json north_star), 1e-5 in FP32 mode."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gabo_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-12
+
+
+def rel_err(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def offdiag_mask(n):
+    return ~np.eye(n, dtype=bool)
+
+
+# ----------------------------------------------------------------------------------------------- sphere
+def test_sphere_gaussian_golden(cuda, golden):
+    from gaboflow_b200 import SphereGaussianKernel
+    g = golden['sphere_s2']
+    k = SphereGaussianKernel(input_dim=3, active_dims=range(3), beta_min=7.0, beta=10.0, variance=1.)   # sphere_kernels.py:125
+    K1 = k.compute_K_symm(g['x_man'])
+    K12 = k.compute_K(g['x_man'], g['x_test'])
+    K2 = k.compute_K_symm(g['x_test'])
+    # the points are separated by >= 1e-3 rad, and nowhere antipodal: Gaussian entries are well conditioned
+    assert rel_err(K1, g['Kgauss11']) < RTOL64
+    assert rel_err(K12, g['Kgauss12']) < RTOL64
+    assert rel_err(K2, g['Kgauss22']) < RTOL64
+    assert np.array_equal(K1, K1.T)
+    assert np.all(np.diag(K1) == 1.0)
+    # known answers of SURVEY.md 8(c)
+    assert abs(K1[0, 1] - 0.8647594661093245) < 1e-13
+    assert abs(K1[3, 7] / 7.674432431725071e-06 - 1) < RTOL64
+    assert np.allclose(k.compute_Kdiag(g['x_test']), 1.0, rtol=0, atol=0)
+
+
+def test_sphere_laplace_golden(cuda, golden):
+    from gaboflow_b200 import SphereLaplaceKernel
+    g = golden['sphere_s2']
+    k = SphereLaplaceKernel(input_dim=3, active_dims=range(3), beta=10.0, variance=1.)
+    K1 = k.compute_K_symm(g['x_man'])
+    K12 = k.compute_K(g['x_man'], g['x_test'])
+    m = offdiag_mask(20)
+    assert rel_err(K1[m], g['Klaplace11'][m]) < RTOL64
+    assert rel_err(K12, g['Klaplace12']) < RTOL64
+    # diagonal: exactly variance here; the reference's own value carries acos(1-k*eps) ~ 1e-8 noise (hazard i)
+    assert np.all(np.diag(K1) == 1.0)
+    assert np.max(np.abs(np.diag(g['Klaplace11']) - 1.0)) < 10.0 * 4e-8
+
+
+@pytest.mark.parametrize('kind', ['gauss', 'laplace'])
+@pytest.mark.parametrize('n1,n2,dim', [(1, 1, 3), (5, 7, 3), (127, 129, 3), (130, 257, 51), (300, 200, 53), (64, 64, 120)])
+def test_sphere_vs_oracle_shapes(cuda, kind, n1, n2, dim):
+    from gaboflow_b200 import SphereGaussianKernel, SphereLaplaceKernel
+    X = orc.synth_sphere(n1, dim, seed=7 + n1)
+    X2 = orc.synth_sphere(n2, dim, seed=11 + n2)
+    if kind == 'gauss':
+        k = SphereGaussianKernel(dim, range(dim), beta_min=0.5, beta=1.5, variance=0.7)
+        ref = orc.sphere_gaussian_K(X, X2, beta=2.0, variance=0.7)
+        refs = orc.sphere_gaussian_K(X, beta=2.0, variance=0.7)
+    else:
+        k = SphereLaplaceKernel(dim, range(dim), beta=2.0, variance=0.7)
+        ref = orc.sphere_laplace_K(X, X2, beta=2.0, variance=0.7)
+        refs = orc.sphere_laplace_K(X, beta=2.0, variance=0.7)
+    # dots of independent points on S^2 can come near +-1 where acos is ill conditioned: tolerance scaled by the
+    # condition number 1/sin(d) of the reference computation itself (both sides see different 1-ulp dot products)
+    t = np.clip(X @ X2.T, -1, 1)
+    cond = 1.0 / np.maximum(np.sqrt(1 - t * t), 1e-8)
+    got = k.compute_K(X, X2)
+    assert np.all(np.abs(got - ref) <= RTOL64 * np.maximum(cond, 1.0) * np.abs(ref) + 1e-300)
+    gots = k.compute_K_symm(X)
+    m = offdiag_mask(n1)
+    ts = np.clip(X @ X.T, -1, 1)
+    conds = 1.0 / np.maximum(np.sqrt(1 - ts * ts), 1e-8)
+    assert np.all((np.abs(gots - refs) <= RTOL64 * np.maximum(conds, 1.0) * np.abs(refs))[m])
+    assert np.all(np.diag(gots) == 0.7)
+    assert np.array_equal(gots, gots.T)
+
+
+def test_sphere_uplo_and_row_blocks(cuda):
+    from gaboflow_b200 import SphereGaussianKernel
+    n, dim = 700, 51
+    X = torch.from_numpy(orc.synth_sphere(n, dim, seed=3)).cuda()
+    k = SphereGaussianKernel(dim, range(dim), beta_min=0.0, beta=2.0)
+    full = k.K(X, uplo='full')
+    mirror = k.K(X, uplo='mirror')
+    assert torch.equal(full, full.t()) or torch.allclose(full, full.t(), rtol=1e-15, atol=0)
+    assert torch.equal(mirror, mirror.t())
+    assert torch.equal(torch.tril(full), torch.tril(mirror))
+    low = torch.full((n, n), float('nan'), dtype=torch.float64, device='cuda')
+    k.K(X, uplo='lower', out=low)
+    assert torch.equal(torch.tril(low), torch.tril(full))
+    # row-block sharding (what each rank of a multi-GPU run produces): bitwise equal to the single call
+    parts = [k.K(X, uplo='full', row0=r0, row1=min(r0 + 256, n)) for r0 in range(0, n, 256)]
+    assert torch.equal(torch.cat(parts, 0), full)
+    lowparts = []
+    for r0 in range(0, n, 256):
+        r1 = min(r0 + 256, n)
+        buf = torch.zeros((r1 - r0, n), dtype=torch.float64, device='cuda')
+        k.K(X, uplo='lower', row0=r0, row1=r1, out=buf)
+        lowparts.append(buf)
+    assert torch.equal(torch.tril(torch.cat(lowparts, 0)), torch.tril(full))
+
+
+def test_sphere_clamp_and_empty(cuda):
+    from gaboflow_b200 import SphereGaussianKernel, ops
+    k = SphereGaussianKernel(3, range(3), beta_min=0.0, beta=1.0)
+    X = np.array([[1.0, 0, 0], [-1.0, 0, 0], [1.0000000000000002, 0, 0], [0, 1.0, 0]])
+    K = k.compute_K_symm(X)
+    assert abs(K[0, 1] - np.exp(-np.pi ** 2)) < 1e-15          # antipodal: acos(-1) = pi
+    assert K[0, 2] == 1.0                                        # dot slightly above 1 is clamped (sphere_utils_tf.py:59)
+    assert abs(K[0, 3] - np.exp(-(np.pi / 2) ** 2)) < 1e-15
+    e = ops.points_gram(ops.SPHERE_GAUSSIAN, torch.zeros((0, 3), dtype=torch.float64, device='cuda'), None)
+    assert e.shape == (0, 0)
+
+
+def test_sphere_fp32_mode(cuda):
+    from gaboflow_b200 import ops
+    n, dim = 513, 51
+    X = orc.synth_sphere(n, dim, seed=5)
+    X2 = orc.synth_sphere(200, dim, seed=6)
+    ref = orc.sphere_gaussian_K(X, X2, beta=2.0)
+    got = ops.points_gram(ops.SPHERE_GAUSSIAN, torch.from_numpy(X.astype(np.float32)).cuda(),
+                          torch.from_numpy(X2.astype(np.float32)).cuda(), beta=2.0).cpu().numpy()
+    assert got.dtype == np.float32
+    assert rel_err(got.astype(np.float64), ref) < 1e-5
+    refs = orc.sphere_gaussian_K(X, beta=2.0)
+    gots = ops.points_gram(ops.SPHERE_GAUSSIAN, torch.from_numpy(X.astype(np.float32)).cuda(), None, beta=2.0,
+                           uplo='mirror').cpu().numpy()
+    assert rel_err(gots.astype(np.float64), refs) < 1e-5
+    assert np.array_equal(gots, gots.T)
+
+
+# ----------------------------------------------------------------------------------------------- SPD
+def test_spd_golden_s2pp(cuda, golden):
+    from gaboflow_b200 import (SpdAffineInvariantGaussianKernel, SpdAffineInvariantLaplaceKernel, SpdSteinGaussianKernel,
+                               SpdFrobeniusGaussianKernel, SpdLogEuclideanGaussianKernel)
+    g = golden['spd_s2pp']
+    x, xt = g['x_man'], g['x_test']
+    m = offdiag_mask(x.shape[0])
+    k_ai = SpdAffineInvariantGaussianKernel(input_dim=3, active_dims=range(3), beta=1.0, variance=1., beta_min=0.6)  # spd_kernels.py:177
+    assert k_ai.matrix_dim == 2
+    # the C.mat trajectory contains near-duplicate neighbours (K = 1 - 7.7e-13): compare with an absolute floor on d^2
+    K = k_ai.compute_K_symm(x)
+    assert np.max(np.abs(K - g['Kai11'])) < 2e-13
+    assert rel_err(K[m], g['Kai11'][m]) < 5e-12
+    assert rel_err(k_ai.compute_K(x, xt), g['Kai12']) < 5e-12
+    assert abs(K[0, 40] - 0.1681804160600421) < 1e-13
+    k_ail = SpdAffineInvariantLaplaceKernel(3, range(3), beta=1.0)
+    Kl = k_ail.compute_K_symm(x)
+    # Laplace kernel: relative error = beta * abs error of d; d itself carries ~1e-9 for near-duplicate matrices in the
+    # reference's eig(inv(S1) S2) route, so parity is asserted where d > 1e-3
+    far = (g['Dai11'] > 1e-3)
+    assert rel_err(Kl[far], g['Kailap11'][far]) < 1e-11
+    k_st = SpdSteinGaussianKernel(3, range(3), beta=1.0, variance=1.)
+    assert k_st.continuous_param_space_limit == 0.5
+    Ks = k_st.compute_K_symm(x)
+    assert rel_err(Ks, g['Kstein11']) < RTOL64 * 10
+    assert rel_err(k_st.compute_K(x, xt), g['Kstein12']) < RTOL64 * 10
+    assert rel_err(k_st.compute_Kdiag(x), np.diag(g['Kstein11'])) < RTOL64 * 10
+    assert abs(Ks[0, 0] - 3.7935618844967043) < 1e-11
+    k_fr = SpdFrobeniusGaussianKernel(3, range(3), beta=1.0)
+    assert np.max(np.abs(k_fr.compute_K_symm(x) - g['Kfrob11'])) < 1e-13
+    assert rel_err(k_fr.compute_K(x, xt), g['Kfrob12']) < 1e-11
+    k_le = SpdLogEuclideanGaussianKernel(3, range(3), beta=1.0)
+    assert np.max(np.abs(k_le.compute_K_symm(x) - g['Klogeuc11'])) < 1e-13
+    assert rel_err(k_le.compute_K(x, xt), g['Klogeuc12']) < 1e-11
+
+
+def test_spd_golden_s6pp(cuda, golden):
+    from gaboflow_b200 import SpdAffineInvariantGaussianKernel, SpdSteinGaussianKernel, SpdLogEuclideanGaussianKernel
+    g = golden['spd_s6pp']
+    x = g['x']
+    k = SpdAffineInvariantGaussianKernel(21, range(21), beta_min=0.5, beta=0.5)
+    assert k.matrix_dim == 6
+    K = k.compute_K_symm(x)
+    assert rel_err(K, g['Kai']) < RTOL64
+    assert np.array_equal(K, K.T) and np.all(np.diag(K) == 1.0)
+    ks = SpdSteinGaussianKernel(21, range(21), beta=3.0)
+    assert rel_err(ks.compute_K_symm(x), g['Kstein']) < RTOL64 * 10
+    kl = SpdLogEuclideanGaussianKernel(21, range(21), beta=1.0)
+    assert rel_err(kl.compute_K_symm(x), g['Klogeuc']) < 2e-12
+
+
+@pytest.mark.parametrize('d', [2, 3, 4, 5, 6, 7, 8])
+def test_spd_ai_all_dims_vs_oracle(cuda, d):
+    from gaboflow_b200 import SpdAffineInvariantGaussianKernel, SpdAffineInvariantLaplaceKernel, SpdSteinGaussianKernel
+    m = d * (d + 1) // 2
+    X = orc.synth_spd_mandel(150, d, seed=100 + d)
+    X2 = orc.synth_spd_mandel(70, d, seed=200 + d)
+    k = SpdAffineInvariantGaussianKernel(m, range(m), beta_min=0.25, beta=0.75, variance=1.3)
+    assert rel_err(k.compute_K(X, X2), orc.spd_ai_gaussian_K(X, X2, beta=1.0, variance=1.3)) < RTOL64
+    Ks = k.compute_K_symm(X)
+    assert rel_err(Ks, orc.spd_ai_gaussian_K(X, beta=1.0, variance=1.3)) < RTOL64
+    assert np.array_equal(Ks, Ks.T)
+    kl = SpdAffineInvariantLaplaceKernel(m, range(m), beta=1.0)
+    assert rel_err(kl.compute_K(X, X2), orc.spd_ai_laplace_K(X, X2, beta=1.0)) < RTOL64
+    beta = 0.5 * (d - 1) + 0.5
+    kst = SpdSteinGaussianKernel(m, range(m), beta=beta)
+    assert rel_err(kst.compute_K(X, X2), orc.spd_stein_K(X, X2, beta=beta)) < 5e-12
+    assert rel_err(kst.compute_Kdiag(X), orc.stein_kdiag(X, beta=beta)) < 5e-12
+
+
+def test_spd_row_blocks_and_lower(cuda):
+    from gaboflow_b200 import SpdAffineInvariantGaussianKernel
+    X = torch.from_numpy(orc.synth_spd_mandel(300, 6, seed=9)).cuda()
+    k = SpdAffineInvariantGaussianKernel(21, range(21), beta_min=0.0, beta=1.0)
+    p = k.prepare(X)
+    full = k.K(p, uplo='full')
+    mir = k.K(p, uplo='mirror')
+    assert torch.equal(torch.tril(full), torch.tril(mir)) and torch.equal(mir, mir.t())
+    parts = [k.K(p, uplo='full', row0=r0, row1=min(r0 + 96, 300)) for r0 in range(0, 300, 96)]
+    assert torch.equal(torch.cat(parts, 0), full)
+    low = torch.zeros((300, 300), dtype=torch.float64, device='cuda')
+    k.K(p, uplo='lower', out=low)
+    assert torch.equal(torch.tril(low), torch.tril(full))
+
+
+def test_spd_non_spd_input_reports(cuda):
+    from gaboflow_b200 import ops
+    X = orc.synth_spd_mandel(8, 3, seed=1)
+    X[3, :3] = [-1.0, 1.0, 1.0]          # negative diagonal entry: not SPD
+    p = ops.spd_prep(torch.from_numpy(X).cuda(), 3, want_logm=True)
+    info = p.info.cpu().numpy()
+    assert info[3] > 0 and np.all(np.delete(info, 3) == 0)
+    K = ops.spd_gram(ops.SPD_AI_GAUSSIAN, p).cpu().numpy()
+    assert np.all(np.isnan(K[3, [0, 1, 2, 4]])) and np.all(np.isfinite(np.delete(np.delete(K, 3, 0), 3, 1)))

@@ -1,0 +1,134 @@
+"""Parity of the FP64 Cholesky / triangular solves / GP log-likelihood / posterior against the oracle.
+Tolerances (BASELINE.json north_star): log marginal likelihood and posterior mean/variance 1e-8 relative;
+factor entries are checked far tighter on well-conditioned inputs."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+import torch
+
+from oracle import gabo_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def spd_matrix(n, seed, cond_shift=None):
+    rng = np.random.default_rng(seed)
+    G = rng.standard_normal((n, max(n // 2, 4)))
+    A = G @ G.T / G.shape[1]
+    A[np.diag_indices(n)] += (cond_shift if cond_shift is not None else 0.5)
+    return A
+
+
+@pytest.mark.parametrize('n', [1, 2, 17, 128, 129, 300, 512, 513, 640, 1100, 2049])
+def test_potrf_vs_scipy(cuda, n):
+    from gaboflow_b200 import ops
+    A = spd_matrix(n, n)
+    ref = sla.cholesky(A + 0.01 * np.eye(n), lower=True)
+    d = torch.from_numpy(A).cuda()
+    d_up = torch.triu(d, 1).clone()
+    info = ops.potrf_(d, sigma2=0.01)
+    assert int(info.item()) == 0
+    got = d.cpu().numpy()
+    assert np.max(np.abs(np.tril(got) - ref)) / np.max(np.abs(ref)) < 1e-13
+    assert torch.equal(torch.triu(d, 1), d_up)        # strictly upper triangle untouched
+
+
+def test_potrf_reports_non_pd(cuda):
+    from gaboflow_b200 import ops
+    n = 400
+    A = spd_matrix(n, 5)
+    A[250, 250] = -1.0
+    d = torch.from_numpy(A).cuda()
+    info = ops.potrf_(d, check=False)
+    assert int(info.item()) == 251
+    with pytest.raises(np.linalg.LinAlgError):
+        ops.potrf_(torch.from_numpy(A).cuda(), check=True)
+
+
+@pytest.mark.parametrize('n,nrhs', [(5, 1), (130, 1), (700, 3), (700, 4), (300, 5), (1000, 64), (1000, 200), (257, 130)])
+@pytest.mark.parametrize('trans', [False, True])
+def test_trsm_vs_scipy(cuda, n, nrhs, trans):
+    from gaboflow_b200 import ops
+    L = np.linalg.cholesky(spd_matrix(n, 3 * n))
+    B = np.random.default_rng(n + nrhs).standard_normal((n, nrhs))
+    ref = sla.solve_triangular(L, B, lower=True, trans='T' if trans else 'N')
+    Ld = torch.from_numpy(L).cuda()
+    Bd = torch.from_numpy(B).cuda()
+    ops.trsm_(Ld, Bd, trans=trans)
+    assert np.max(np.abs(Bd.cpu().numpy() - ref)) / np.max(np.abs(ref)) < 1e-12
+
+
+@pytest.mark.parametrize('m,n,k,lower', [(128, 128, 16, False), (300, 200, 77, False), (513, 513, 128, True), (260, 130, 512, True)])
+def test_gemm_nt_sub(cuda, m, n, k, lower):
+    from gaboflow_b200 import ops
+    rng = np.random.default_rng(m + n + k)
+    A, B, C = rng.standard_normal((m, k)), rng.standard_normal((n, k)), rng.standard_normal((m, n))
+    ref = C - A @ B.T
+    Cd = torch.from_numpy(C).cuda()
+    ops.gemm_nt_sub_(Cd, torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), lower=lower)
+    got = Cd.cpu().numpy()
+    if lower:
+        mask = np.tril(np.ones((m, n), dtype=bool))
+        assert np.max(np.abs(got[mask] - ref[mask])) < 1e-12 * k
+        assert np.array_equal(got[~mask], C[~mask])
+    else:
+        assert np.max(np.abs(got - ref)) < 1e-12 * k
+
+
+def test_gpr_sphere_example_known_answers(cuda, golden):
+    """examples/kernels/sphere/sphere_kernels.py:125-139 with the kernel parameters as constructed
+    (no optimize()); known answers from SURVEY.md 8(c)."""
+    from gaboflow_b200 import GPR, SphereGaussianKernel
+    g = golden['sphere_s2']
+    k = SphereGaussianKernel(input_dim=3, active_dims=range(3), beta_min=7.0, beta=10.0, variance=1.)
+    m = GPR(g['x_man'], g['y_train'], kern=k, mean_function=None)
+    ll = m.compute_log_likelihood()
+    assert abs(ll / -23.67939289441117 - 1) < 1e-8
+    mean, var = m.predict_f(g['x_test'])
+    Kor = orc.sphere_gaussian_K(g['x_man'], beta=17.0)
+    mo, vo = orc.gp_predict(Kor, orc.sphere_gaussian_K(g['x_man'], g['x_test'], beta=17.0), np.ones(10), g['y_train'], 1.0)
+    assert np.max(np.abs(mean - mo) / np.maximum(np.abs(mo), 1e-12)) < 1e-8
+    assert np.max(np.abs(var - vo) / np.abs(vo)) < 1e-8
+    assert np.allclose(mean[:3, 0], [1.2854030824754458e-03, 2.7761803306368668e-08, 9.6917159395751379e-02], rtol=1e-8, atol=0)
+    assert np.allclose(var[:3, 0], [0.9998564833587267, 0.9999999999999013, 0.5014023044062732], rtol=1e-8, atol=0)
+    mean2, cov = m.predict_f_full_cov(g['x_test'])
+    _, co = orc.gp_predict(Kor, orc.sphere_gaussian_K(g['x_man'], g['x_test'], beta=17.0),
+                           orc.sphere_gaussian_K(g['x_test'], beta=17.0), g['y_train'], 1.0, full_cov=True)
+    assert cov.shape == (10, 10, 1)
+    assert np.max(np.abs(cov[:, :, 0] - co)) < 1e-10
+    # hyper-parameter change invalidates the cached factor
+    k.update_beta(12.0)
+    assert abs(m.compute_log_likelihood() - orc.gp_loglik(orc.sphere_gaussian_K(g['x_man'], beta=12.0), g['y_train'], 1.0)) < 1e-8
+
+
+def test_gpr_spd_example_known_answers(cuda, golden):
+    """examples/kernels/spd/spd_kernels.py:176-194 (affine-invariant kernel on the C.mat fixture)."""
+    from gaboflow_b200 import GPR, SpdAffineInvariantGaussianKernel
+    g = golden['spd_s2pp']
+    k = SpdAffineInvariantGaussianKernel(input_dim=3, active_dims=range(3), beta=1.0, variance=1., beta_min=0.6)
+    m = GPR(g['x_man'], g['y'], kern=k, mean_function=None)
+    assert abs(m.compute_log_likelihood() / -27621.519513872187 - 1) < 1e-8
+    mean, var = m.predict_f(g['x_test'])
+    Kor = orc.spd_ai_gaussian_K(g['x_man'], beta=1.6)
+    mo, vo = orc.gp_predict(Kor, orc.spd_ai_gaussian_K(g['x_man'], g['x_test'], beta=1.6), np.ones(100), g['y'], 1.0)
+    assert np.max(np.abs(mean - mo) / np.maximum(np.abs(mo), 1e-9)) < 1e-8
+    assert np.max(np.abs(var - vo) / np.abs(vo)) < 1e-8
+
+
+@pytest.mark.parametrize('n', [1500, 4096])
+def test_gp_pipeline_synthetic_sphere(cuda, n):
+    """BASELINE config 4 at oracle-checkable size: sphere Gaussian Gram on S^50, sigma^2 = 1e-2, loglik + posterior."""
+    from gaboflow_b200 import GPR, SphereGaussianKernel
+    X = orc.synth_sphere(n, 51, seed=20240)
+    y = np.random.default_rng(20241).standard_normal((n, 1))
+    Xs = orc.synth_sphere(300, 51, seed=99)
+    k = SphereGaussianKernel(51, range(51), beta_min=0.0, beta=2.0)
+    m = GPR(X, y, kern=k)
+    m.likelihood.variance = 1e-2
+    Kor = orc.sphere_gaussian_K(X, beta=2.0)
+    ll_ref = orc.gp_loglik(Kor, y, 1e-2)
+    assert abs(m.compute_log_likelihood() / ll_ref - 1) < 1e-8
+    mean, var = m.predict_f(Xs)
+    mo, vo = orc.gp_predict(Kor, orc.sphere_gaussian_K(X, Xs, beta=2.0), np.ones(300), y, 1e-2)
+    assert np.max(np.abs(mean - mo)) / np.max(np.abs(mo)) < 1e-8
+    assert np.max(np.abs(var - vo) / np.abs(vo)) < 1e-8
