@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Headline benchmark of the GaBOflow hot path on B200 (BASELINE.json metric):
+manifold Gram entries/s + FP64 Cholesky time of K + sigma^2 I at N = 32,768.
+
+    python bench.py --gpus N --steps K --warmup W             # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference math on the host CPU cores
+
+A step is one pass of the hot path over one synthetic batch (BASELINE.json configs[3]):
+    gram   sphere Gaussian Gram K(X,X), N = 65,536 points on S^50 (D = 51), beta = 2, variance = 1, full dense FP64
+    potrf  in-place FP64 Cholesky of the leading 32,768 block of K + 1e-2 I            (the metric's Cholesky)
+    solve  alpha = L^-1 y, log marginal likelihood (one scalar)
+`value` = Gram entries per second over the gram phase (max over ranks); `ms_per_step` covers the whole step and
+`phases_ms` / `cholesky` split it.  Inputs are synthetic (seeded), already resident in HBM for `value`; `e2e` repeats
+the steps through the public kernel-class / GPR API from pinned HOST buffers with the host<->device copies inside the
+timed region.  The working set (34 GB of K) is >> the 126 MB L2, so no explicit flush is needed between iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED_X, SEED_Y = 20240, 20241
+BETA, VARIANCE, SIGMA2 = 2.0, 1.0, 1e-2
+DIM = 51
+FP64_PEAK_TFLOPS = 37.2                # measured on this pool: tools/fp64_probe.cu -> profiles/r01_fp64_probe.txt (DMMA.8x8x4)
+F_TR = 100                             # declared transcendental flops per sphere Gram entry
+
+
+def synth_sphere(n, dim, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, dim))
+    return X / np.linalg.norm(X, axis=1, keepdims=True)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'MEASURED_PEAKS.json'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons in a background thread during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0, period=0.2):
+        self.index, self.period, self.rows, self._stop, self._t = index, period, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=10)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '', 1).isdigit()]
+        smax = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '', 1).isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(n_gram, n_chol_sample=8192, gram_rows=2048, n_chol_metric=32768):
+    """The reference math on the host cores (NumPy/OpenBLAS oracle port), bounded sample of the bench workload."""
+    from oracle import gabo_oracle as orc   # the ONE place bench.py executes oracle/: the CPU baseline
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get('num_threads', 1) for p in threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    X = synth_sphere(n_gram, DIM, SEED_X)
+    rows = min(gram_rows, n_gram)
+    t0 = time.perf_counter()
+    Kb = orc.sphere_gaussian_K(X[:rows], X, beta=BETA, variance=VARIANCE, block=1024)
+    t_gram = time.perf_counter() - t0
+    del Kb
+    nc = min(n_chol_sample, n_gram)
+    Kc = orc.sphere_gaussian_K(X[:nc], X[:nc], beta=BETA, variance=VARIANCE, block=1024)
+    y = np.random.default_rng(SEED_Y).standard_normal((nc, 1))
+    t0 = time.perf_counter()
+    ll = orc.gp_loglik(Kc, y, SIGMA2)
+    t_chol = time.perf_counter() - t0
+    gflops = nc ** 3 / 3 / t_chol * 1e-9
+    return {
+        'value': rows * n_gram / t_gram, 'unit': 'entries/s', 'cores': int(cores), 'kind': 'port',
+        'sample': f'gram rows [0,{rows}) x {n_gram} cols of the same workload in {t_gram:.2f} s; Cholesky+solve+loglik at N={nc} '
+                  f'in {t_chol:.2f} s (NumPy/SciPy OpenBLAS oracle port; TF1/GPflow 0.5 not installable)',
+        'cholesky': {'n': nc, 'seconds': t_chol, 'gflops': gflops,
+                     'extrapolated_n%d_s' % n_chol_metric: t_chol * (n_chol_metric / nc) ** 3},
+        'loglik_sample': ll,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    n_gram, n_chol = args.n_gram, args.n_chol
+    times, last = [], None
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        last = cpu_reference_sample(n_gram, n_chol_sample=min(args.ref_chol_n, n_chol), gram_rows=args.ref_gram_rows,
+                                    n_chol_metric=n_chol)
+        if it >= args.warmup:
+            times.append((time.perf_counter() - t0, last))
+    val = float(np.mean([t[1]['value'] for t in times]))
+    chol = times[-1][1]['cholesky']
+    line = {
+        'impl': 'reference', 'metric': 'sphere_gram_entries_per_s', 'value': val, 'unit': 'entries/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean([t[0] for t in times])) * 1e3,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'sphere Gaussian Gram N={n_gram} on S^50 (D=51) + FP64 Cholesky of K+1e-2 I at N={n_chol} + solve + loglik',
+                   'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2,
+                   'note': 'each step is a bounded sample of the workload on the host CPU cores (see cpu_baseline.sample)'},
+        'cholesky': chol,
+        'cpu_baseline': {k: last[k] for k in ('unit', 'cores', 'kind', 'sample')} | {'value': val},
+        'e2e': {'value': val, 'unit': 'entries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gaboflow_b200 import GPR, SphereGaussianKernel, ops, _lib
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.lib()
+
+    N, NC = args.n_gram, min(args.n_chol, args.n_gram)
+    Xh = torch.from_numpy(synth_sphere(N, DIM, SEED_X)).pin_memory()
+    yh = torch.from_numpy(np.random.default_rng(SEED_Y).standard_normal((N, 1))).pin_memory()
+    X = Xh.to(dev)
+    y = yh.to(dev)
+    kern = SphereGaussianKernel(DIM, range(DIM), beta_min=0.0, beta=BETA, variance=VARIANCE)
+
+    # row-block sharding of the Gram across ranks (128-row granularity, no data-path collective)
+    blk = ops.ROW_BLOCK
+    nblk = (N + blk - 1) // blk
+    b0 = (nblk * rank) // world
+    b1 = (nblk * (rank + 1)) // world
+    row0, row1 = b0 * blk, min(b1 * blk, N)
+    rows = row1 - row0
+    K = torch.empty((rows, N), dtype=torch.float64, device=dev)
+    ws = torch.empty(int(lib.gabo_points_gram_workspace_bytes(N, N, DIM)), dtype=torch.uint8, device=dev)
+    uplo = 'mirror' if world == 1 else 'full'
+    do_chol = (rank == 0 and rows >= NC)     # the leading NC block lives on rank 0 when its row block is tall enough
+    V = torch.empty((NC, 1), dtype=torch.float64, device=dev)
+    ll_dev = torch.zeros((1,), dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(events=None, from_host=False):
+        nonlocal ll_dev
+        Xd, yd = X, y
+        if from_host:
+            Xd = Xh.to(dev, non_blocking=True)
+            yd = yh.to(dev, non_blocking=True)
+        if events is not None:
+            events[0].record()
+        ops.points_gram(ops.SPHERE_GAUSSIAN, Xd, None, beta=BETA, variance=VARIANCE, out=K, row0=row0, row1=row1,
+                        uplo=uplo, workspace=ws)
+        if events is not None:
+            events[1].record()
+        if do_chol:
+            A = K[:NC, :NC]                       # leading block, ld = N, factored in place (K is regenerated next step)
+            ops.potrf_(A, SIGMA2, check=False)
+            if events is not None:
+                events[2].record()
+            V.copy_(yd[:NC])
+            ops.trsm_(A, V)
+            ll_dev = ops.gp_loglik(A, V)
+        elif events is not None:
+            events[2].record()
+        if events is not None:
+            events[3].record()
+        if from_host:
+            return float(ll_dev.item())          # device -> host read of the step's result
+        return None
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- device-resident timing: K steps, per-phase events, max over ranks ----
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    launches0 = lib.gabo_launch_count()
+    with ClockSampler(index=local_rank) as clocks:
+        barrier()
+        t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for s in range(args.steps):
+            step(evs[s])
+        t_end.record()
+        barrier()
+    launches = lib.gabo_launch_count() - launches0
+    total_ms = t_start.elapsed_time(t_end)
+    gram_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    potrf_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    solve_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
+    ll_val = float(ll_dev.item()) if do_chol else None
+
+    # ---- end to end from pinned host buffers through the public API ----
+    for _ in range(min(args.warmup, 2)):
+        step(from_host=True)
+    barrier()
+    e_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    pre = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e0.record()
+    for s in range(args.steps):
+        pre[s].record()
+        step(e_evs[s], from_host=True)
+    e1.record()
+    barrier()
+    e2e_total_ms = e0.elapsed_time(e1)
+    e2e_gram_ms = float(np.mean([pre[s].elapsed_time(e_evs[s][1]) for s in range(args.steps)]))   # H2D + pack + gram
+
+    def reduce_max(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    total_ms = reduce_max(total_ms)
+    gram_ms = reduce_max(gram_ms)
+    potrf_ms = reduce_max(potrf_ms)
+    solve_ms = reduce_max(solve_ms)
+    e2e_total_ms = reduce_max(e2e_total_ms)
+    e2e_gram_ms = reduce_max(e2e_gram_ms)
+    launches_all = int(reduce_max(float(launches)))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    hbm_peak, hbm_src = measured_peaks()
+    entries = float(N) * float(N)
+    value = entries / (gram_ms * 1e-3)
+    potrf_s = potrf_ms * 1e-3
+    potrf_tflops = (NC ** 3 / 3) / potrf_s * 1e-12 if potrf_s > 0 else None
+    sym = (world == 1)
+    gram_flops = entries * (2 * DIM + F_TR) * (0.5 if sym else 1.0)    # symmetric tiles are computed once and mirrored
+    line = {
+        'metric': 'sphere_gram_entries_per_s', 'value': value, 'unit': 'entries/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'sphere Gaussian Gram N={N} on S^50 (D={DIM}) + FP64 Cholesky of K+1e-2 I at N={NC} + solve + loglik',
+                   'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2, 'seeds': [SEED_X, SEED_Y],
+                   'gram_mode': 'lower tiles computed once, mirror-stored (full dense K)' if sym else 'row blocks of the full dense K, one per rank',
+                   'l2': f'no flush: {rows * N * 8 / 1e9:.1f} GB of K per GPU >> 126 MB L2',
+                   'parallelism': 'single GPU' if world == 1 else f'Gram rows sharded over {world} ranks, no collective; Cholesky on rank 0'},
+        'phases_ms': {'gram': gram_ms, 'potrf': potrf_ms, 'solve_loglik': solve_ms},
+        'cholesky': {'n': NC, 'seconds': potrf_s, 'tflops': potrf_tflops,
+                     'frac_fp64_tensor_peak': (potrf_tflops / FP64_PEAK_TFLOPS) if potrf_tflops else None},
+        'loglik': ll_val,
+        'gpu_launches': launches_all,
+        'clocks': clocks.summary(),
+        'e2e': {'value': entries / (e2e_gram_ms * 1e-3), 'unit': 'entries/s',
+                'h2d_bytes_per_step': int(Xh.numel() * 8 + yh.numel() * 8), 'd2h_bytes_per_step': 8,
+                'ms_per_step': e2e_total_ms / args.steps,
+                'api': 'pinned host X,y -> device, ops.points_gram / potrf_ / trsm_ / gp_loglik (C-ABI), loglik.item()'},
+        'roofline': {'bound': 'tensor', 'kernel': 'gabo_potrf_f64 (95% in gemm_kernel<true,true>, DMMA.8x8x4)',
+                     'achieved': potrf_tflops, 'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                     'frac': (potrf_tflops / FP64_PEAK_TFLOPS) if potrf_tflops else None, 'traffic': None,
+                     'flops_per_launch': NC ** 3 / 3,
+                     'peak_source': 'FP64 tensor peak is not in MEASURED_PEAKS.json: measured on this pool with tools/fp64_probe.cu '
+                                    '(profiles/r01_fp64_probe.txt, DMMA 37.2 TFLOP/s; cuBLAS DGEMM 36.2)'},
+        'roofline_gram': {'bound': 'fp64', 'kernel': 'points_gram_kernel<52>', 'achieved': gram_flops / (gram_ms * 1e-3) * 1e-12,
+                          'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                          'frac': gram_flops / (gram_ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS,
+                          'hbm_write_gbs': rows * N * 8 / (gram_ms * 1e-3) * 1e-9, 'hbm_peak_gbs': hbm_peak, 'hbm_peak_source': hbm_src,
+                          'flops_per_entry_declared': 2 * DIM + F_TR},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_reference_sample(N, n_chol_sample=min(args.ref_chol_n, NC), gram_rows=args.ref_gram_rows,
+                                                    n_chol_metric=NC)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--n-gram', type=int, default=65536)
+    ap.add_argument('--n-chol', type=int, default=32768)
+    ap.add_argument('--ref-gram-rows', type=int, default=2048)
+    ap.add_argument('--ref-chol-n', type=int, default=8192)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

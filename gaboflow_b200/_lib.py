@@ -13,6 +13,7 @@ i32, i64, f64, f32, vp, sz = C.c_int, C.c_int64, C.c_double, C.c_float, C.c_void
 # name -> (restype, argtypes); mirrors include/gabo_b200.h one to one
 SIGNATURES = {
     'gabo_abi_version': (i32, []),
+    'gabo_launch_count': (C.c_longlong, []),
     'gabo_device_info': (i32, [C.POINTER(i32)] * 3),
     'gabo_status_string': (C.c_char_p, [i32]),
     'gabo_points_gram_workspace_bytes': (sz, [i64, i64, i32]),

@@ -1,7 +1,11 @@
 // Small C-ABI entry points that are not kernels of their own: version, device query, status text, Kdiag fill.
+#include <atomic>
 #include "gabo_common.cuh"
 
 namespace gabo {
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
     int dev = 0, n = 0;
@@ -19,6 +23,8 @@ __global__ void fill_kernel(double* out, int64_t n, double v) {
 }  // namespace gabo
 
 extern "C" int gabo_abi_version(void) { return GABO_ABI_VERSION; }
+
+extern "C" long long gabo_launch_count(void) { return gabo::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int gabo_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;

@@ -11,12 +11,18 @@
         if (e_ != cudaSuccess) return GABO_ERR_CUDA - (int)e_;                 \
     } while (0)
 
-#define GABO_LAUNCH_CHECK() GABO_CUDA_TRY(cudaPeekAtLastError())
+// every kernel launch of the library passes through here: error check + diagnostic launch counter
+#define GABO_LAUNCH_CHECK()                                \
+    do {                                                   \
+        ::gabo::count_launch();                            \
+        GABO_CUDA_TRY(cudaPeekAtLastError());              \
+    } while (0)
 
 namespace gabo {
 
 constexpr int kNumSMsB200 = 148;
 
+void count_launch();   // bumps the process-wide diagnostic counter read by gabo_launch_count() (gabo_api.cu)
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device (gabo_api.cu)
 
 // D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor pipe.  Fragment ownership (lane = 4*g + q):

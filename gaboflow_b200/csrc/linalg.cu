@@ -78,48 +78,166 @@ __device__ __forceinline__ void tri_inverse_inplace_smem(double* S, int tid) {
     }
 }
 
+// ---- 32x32 building block, one warp, registers + shuffles ---------------------------------------------------------------
+// Lane i holds row i of the block (a[k], k <= i).  On return a = Cholesky factor L (row i in lane i) and w = column
+// `lane` of inv(L) (w[i], i >= lane).  Returns the 1-based index of the first non-positive pivot, or 0.
+__device__ __forceinline__ int warp_chol32_inv(double (&a)[32], double (&w)[32], int lane) {
+    const unsigned FULL = 0xffffffffu;
+    double rinv[32];
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const double d = __shfl_sync(FULL, a[j], j);
+        if (!(d > 0.0) && bad == 0) bad = j + 1;
+        const double ljj = sqrt(d);
+        rinv[j] = 1.0 / ljj;
+        if (lane == j) a[j] = ljj;
+        else if (lane > j) a[j] *= rinv[j];
+#pragma unroll
+        for (int k = j + 1; k < 32; ++k) {
+            const double lkj = __shfl_sync(FULL, a[j], k);
+            if (lane >= k) a[k] = fma(-a[j], lkj, a[k]);
+        }
+    }
+    // inverse: lane = column c of W; w[i] = (delta_ic - sum_{k<i} L[i][k] w[k]) / L[i][i]
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        double s = (lane == i) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+            const double lik = __shfl_sync(FULL, a[k], i);
+            s = fma(-lik, w[k], s);
+        }
+        w[i] = (lane <= i) ? s * rinv[i] : 0.0;
+    }
+    return bad;
+}
+
+constexpr int DLD = 36;   // leading dimension of the 32x32 scratch blocks (4 mod 16)
+constexpr size_t POTF2V2_SMEM = (size_t)(NB_IN * WLD + 4 * 32 * DLD + 32 * DLD) * sizeof(double);   // 181,248
+
+// one 8x8 output tile per call: acc += A[8 x K] * B[8 x K]^T, both K-major in shared memory
+__device__ __forceinline__ void dmma_tile_nt(double& c0, double& c1, const double* A, int lda, const double* B, int ldb,
+                                             int ksteps, int g, int q) {
+    for (int ks = 0; ks < ksteps; ++ks) dmma884(c0, c1, A[g * lda + ks * 4 + q], B[g * ldb + ks * 4 + q]);
+}
+
 // ---- diagonal block: L11 = chol(A11 + sigma2 I) in place; Winv = inv(L11) (dense [128][128], zero above) ---------------
-__global__ void __launch_bounds__(512, 1) potf2_inv_kernel(double* __restrict__ A, int64_t lda, int jb, double sigma2,
+// Blocked by 32 inside one CTA (8 warps): warp 0 factors and inverts each 32x32 diagonal block in registers, the
+// panel below it (x inv^T), the trailing update and the assembly of the 128x128 inverse run on DMMA from shared memory.
+__global__ void __launch_bounds__(256, 1) potf2_inv_kernel(double* __restrict__ A, int64_t lda, int jb, double sigma2,
                                                            double* __restrict__ Winv, int32_t* __restrict__ info,
                                                            int info_base) {
-    extern __shared__ double sm_potf2[];
-    double* S = sm_potf2;   // [128][129]
-    const int tid = threadIdx.x;
-    for (int e = tid; e < NB_IN * NB_IN; e += 512) {
+    extern __shared__ __align__(16) double sm_potf2[];
+    double* S = sm_potf2;                      // [128][132] the block (lower part), later its inverse (off-diagonal blocks)
+    double* Dv = sm_potf2 + NB_IN * WLD;       // [4][32][36] inverses of the diagonal 32x32 blocks
+    double* T = Dv + 4 * 32 * DLD;             // [32][36] scratch
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    for (int e = tid; e < NB_IN * NB_IN; e += 256) {
         const int r = e >> 7, c = e & 127;
         double v = 0.0;
         if (r < jb && c <= r) v = A[(int64_t)r * lda + c];
         if (r == c) v = (r < jb) ? v + sigma2 : 1.0;   // identity padding keeps the inverse well defined
-        S[r * PLD + c] = v;
+        S[r * WLD + c] = v;
     }
     __syncthreads();
-    for (int j = 0; j < jb; ++j) {   // right-looking, one column at a time
-        const double d = S[j * PLD + j];
-        if (!(d > 0.0) && tid == 0) atomicCAS(info, 0, info_base + j + 1);
-        const double ljj = sqrt(d);
-        const double rinv = 1.0 / ljj;
-        __syncthreads();             // everyone has read d before it is overwritten
-        for (int i = j + tid; i < jb; i += 512) S[i * PLD + j] = (i == j) ? ljj : S[i * PLD + j] * rinv;
+    for (int kb = 0; kb < 4; ++kb) {
+        const int o = kb * 32;
+        if (warp == 0) {
+            double a[32], w[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) a[k] = (k <= lane) ? S[(o + lane) * WLD + o + k] : 0.0;
+            const int bad = warp_chol32_inv(a, w, lane);
+            if (bad != 0 && o + bad <= jb && lane == 0) atomicCAS(info, 0, info_base + o + bad);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if (k <= lane) S[(o + lane) * WLD + o + k] = a[k];
+                Dv[(kb * 32 + k) * DLD + lane] = w[k];          // W[k][lane]
+            }
+        }
         __syncthreads();
-        const int rem = jb - j - 1;  // S[i][c] -= S[i][j] S[c][j] for j < c <= i < jb
-        for (int e = tid; e < rem * rem; e += 512) {
-            const int ii = e / rem, cc = e - ii * rem;
-            if (cc <= ii) {
-                const int i = j + 1 + ii, c = j + 1 + cc;
-                S[i * PLD + c] = fma(-S[i * PLD + j], S[c * PLD + j], S[i * PLD + c]);
+        // panel: rows below, 8-row strips; X = A_strip * W_kk^T (each strip reads only its own rows: no cross-warp hazard)
+        const int nstrips = (NB_IN - o - 32) / 8;
+        for (int st = warp; st < nstrips; st += 8) {
+            const int r0 = o + 32 + st * 8;
+            double c[4][2];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                c[ni][0] = c[ni][1] = 0.0;
+                dmma_tile_nt(c[ni][0], c[ni][1], S + r0 * WLD + o, WLD, Dv + (kb * 32 + ni * 8) * DLD, DLD, 8, g, q);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                S[(r0 + g) * WLD + o + ni * 8 + 2 * q] = c[ni][0];
+                S[(r0 + g) * WLD + o + ni * 8 + 2 * q + 1] = c[ni][1];
+            }
+        }
+        __syncthreads();
+        // trailing update of the lower part: S[i][j] -= sum_k S[i][o+k] S[j][o+k], 8x8 tiles, strips by warp
+        for (int st = warp; st < nstrips; st += 8) {
+            const int r0 = o + 32 + st * 8;
+            for (int ct = 0; ct <= st; ++ct) {
+                const int c0 = o + 32 + ct * 8;
+                double u0 = 0.0, u1 = 0.0;
+                dmma_tile_nt(u0, u1, S + r0 * WLD + o, WLD, S + c0 * WLD + o, WLD, 8, g, q);
+                S[(r0 + g) * WLD + c0 + 2 * q] -= u0;
+                S[(r0 + g) * WLD + c0 + 2 * q + 1] -= u1;
             }
         }
         __syncthreads();
     }
-    for (int e = tid; e < jb * jb; e += 512) {
+    // the factor goes back to global memory before its off-diagonal blocks are overwritten by the inverse
+    for (int e = tid; e < jb * jb; e += 256) {
         const int r = e / jb, c = e - r * jb;
-        if (c <= r) A[(int64_t)r * lda + c] = S[r * PLD + c];
+        if (c <= r) A[(int64_t)r * lda + c] = S[r * WLD + c];
     }
     __syncthreads();
-    tri_inverse_inplace_smem(S, tid);
-    for (int e = tid; e < NB_IN * NB_IN; e += 512) {
+    // inverse, block columns left to right: W_ij = -W_ii (sum_{k=j}^{i-1} L_ik W_kj), i > j.  16 tiles of 8x8 per block,
+    // two per warp.  W_jj lives in Dv; W_kj (j < k < i) already overwrote L_kj in S.
+    for (int j = 0; j < 3; ++j) {
+        for (int i = j + 1; i < 4; ++i) {
+            // T = sum_k L_ik W_kj : A = L_ik (K-major rows), B = W_kj read as [k][n] (N-major)
+            double t[2][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int tile = warp * 2 + h, tm = tile >> 2, tn = tile & 3;
+                t[h][0] = t[h][1] = 0.0;
+                for (int k = j; k < i; ++k) {
+                    const double* Lik = S + (i * 32 + tm * 8) * WLD + k * 32;
+                    const double* Wkj = (k == j) ? (Dv + j * 32 * DLD) : (S + (k * 32) * WLD + j * 32);
+                    const int ldw = (k == j) ? DLD : WLD;
+                    for (int ks = 0; ks < 8; ++ks)
+                        dmma884(t[h][0], t[h][1], Lik[g * WLD + ks * 4 + q], Wkj[(ks * 4 + q) * ldw + tn * 8 + g]);
+                }
+            }
+            __syncthreads();   // all reads of L_ij (k == j term) done before T / W_ij are written
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int tile = warp * 2 + h, tm = tile >> 2, tn = tile & 3;
+                T[(tm * 8 + g) * DLD + tn * 8 + 2 * q] = t[h][0];
+                T[(tm * 8 + g) * DLD + tn * 8 + 2 * q + 1] = t[h][1];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int tile = warp * 2 + h, tm = tile >> 2, tn = tile & 3;
+                double u0 = 0.0, u1 = 0.0;
+                const double* Wii = Dv + (i * 32 + tm * 8) * DLD;
+                for (int ks = 0; ks < 8; ++ks) dmma884(u0, u1, Wii[g * DLD + ks * 4 + q], T[(ks * 4 + q) * DLD + tn * 8 + g]);
+                S[(i * 32 + tm * 8 + g) * WLD + j * 32 + tn * 8 + 2 * q] = -u0;
+                S[(i * 32 + tm * 8 + g) * WLD + j * 32 + tn * 8 + 2 * q + 1] = -u1;
+            }
+            __syncthreads();
+        }
+    }
+    for (int e = tid; e < NB_IN * NB_IN; e += 256) {
         const int r = e >> 7, c = e & 127;
-        Winv[e] = (c <= r) ? S[r * PLD + c] : 0.0;
+        double v = 0.0;
+        if ((r >> 5) == (c >> 5)) v = Dv[((r >> 5) * 32 + (r & 31)) * DLD + (c & 31)];   // zero above the diagonal already
+        else if (c < r) v = S[r * WLD + c];
+        Winv[e] = v;
     }
 }
 
@@ -405,7 +523,7 @@ extern "C" int gabo_potrf_f64(int64_t n, double* A, int64_t lda, double sigma2, 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     double* Winv = static_cast<double*>(workspace);
     int rc;
-    if ((rc = set_smem(potf2_inv_kernel, POTF2_SMEM))) return rc;
+    if ((rc = set_smem(potf2_inv_kernel, POTF2V2_SMEM))) return rc;
     if ((rc = set_smem(panel_trsm_kernel, PANEL_SMEM))) return rc;
     GABO_CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int32_t), stream));
 
@@ -414,7 +532,7 @@ extern "C" int gabo_potrf_f64(int64_t n, double* A, int64_t lda, double sigma2, 
         for (int64_t kk = k0; kk < kend; kk += NB_IN) {
             const int jb = (int)((kend - kk) < NB_IN ? (kend - kk) : NB_IN);
             double* Akk = A + kk * lda + kk;
-            potf2_inv_kernel<<<1, 512, POTF2_SMEM, stream>>>(Akk, lda, jb, sigma2, Winv, info, (int)kk);
+            potf2_inv_kernel<<<1, 256, POTF2V2_SMEM, stream>>>(Akk, lda, jb, sigma2, Winv, info, (int)kk);
             GABO_LAUNCH_CHECK();
             const int64_t mrest = n - (kk + jb);
             if (mrest <= 0) continue;

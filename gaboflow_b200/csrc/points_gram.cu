@@ -18,6 +18,7 @@
 //     with streaming 128-bit writes; the symmetric mode computes lower tiles only and mirror-stores them
 //     (both stores fill whole 32-byte sectors: 64 B per quad row / per 8-lane column group).
 #include "gabo_common.cuh"
+#include "gabo_math.cuh"
 
 namespace gabo {
 namespace {
@@ -71,17 +72,17 @@ __global__ void pack_points_kernel(const Tin* __restrict__ X, int64_t n, int64_t
 }
 
 // ---- epilogue math -----------------------------------------------------------------------------------
-__device__ __forceinline__ double gram_entry(int kind, double acc, double na, double nb, double beta, double variance) {
+__device__ __forceinline__ double gram_entry(int kind, double acc, double na, double nb, double beta, double variance,
+                                             const double* __restrict__ exptab) {
+    double arg;
     if (kind == GABO_SQDIST_GAUSSIAN) {
-        double d2 = fma(-2.0, acc, na + nb);
-        d2 = fmax(d2, 0.0);
-        return variance * exp(-beta * d2);
+        arg = fmax(fma(-2.0, acc, na + nb), 0.0);                 // ||a-b||^2 = |a|^2 + |b|^2 - 2 a.b
+    } else {
+        const double t = fmin(fmax(acc, -1.0), 1.0);              // sphere_utils_tf.py:59: clamp to [-1,1]
+        const double d = acos_fast(t);                            // sphere_utils_tf.py:60
+        arg = (kind == GABO_SPHERE_GAUSSIAN) ? d * d : d;         // kernels_sphere_tf.py:83-86 / :199-202
     }
-    // sphere_utils_tf.py:59-60: clamp to [-1,1], acos
-    double t = fmin(fmax(acc, -1.0), 1.0);
-    double d = acos(t);
-    if (kind == GABO_SPHERE_GAUSSIAN) return variance * exp(-beta * (d * d));   // kernels_sphere_tf.py:83-88
-    return variance * exp(-beta * d);                                            // kernels_sphere_tf.py:199-204
+    return variance * exp_neg_fast(-beta * arg, exptab);          // kernels_sphere_tf.py:88 / :204
 }
 
 __device__ __forceinline__ void tile_coords(const GramParams& p, int64_t t, int64_t& bi, int64_t& bj) {
@@ -104,14 +105,10 @@ template <int KLD>
 __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel(const GramParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr uint32_t TILE_BYTES = BT * KLD * sizeof(double);
-    double* sA[NSTAGE];
-    double* sB[NSTAGE];
-#pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) {
-        sA[s] = reinterpret_cast<double*>(smem_raw + (size_t)s * 2 * TILE_BYTES);
-        sB[s] = reinterpret_cast<double*>(smem_raw + (size_t)s * 2 * TILE_BYTES + TILE_BYTES);
-    }
+    constexpr int TILE_DOUBLES = BT * KLD;
+    double* const smem_d = reinterpret_cast<double*>(smem_raw);   // stage s: A tile at 2*s*TILE_DOUBLES, B tile right after
     __shared__ __align__(8) uint64_t full_bar[NSTAGE];
+    __shared__ double exptab[32];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -123,6 +120,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel(const GramPara
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
     }
+    if (tid < 32) exptab[tid] = kExp2Tab[tid];
     __syncthreads();
 
     // work items: (tile, chunk) pairs owned by this CTA, linearised
@@ -139,13 +137,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel(const GramPara
         const double* srcA = p.Ap + ((int64_t)c * p.n1_pad + (p.tile_r0 + bi) * BT) * KLD;
         const double* srcB = p.Bp + ((int64_t)c * p.n2_pad + bj * BT) * KLD;
         mbar_arrive_expect_tx(&full_bar[s], 2 * TILE_BYTES);
-        tma_bulk_g2s(sA[s], srcA, TILE_BYTES, &full_bar[s]);
-        tma_bulk_g2s(sB[s], srcB, TILE_BYTES, &full_bar[s]);
+        tma_bulk_g2s(smem_d + 2 * s * TILE_DOUBLES, srcA, TILE_BYTES, &full_bar[s]);
+        tma_bulk_g2s(smem_d + (2 * s + 1) * TILE_DOUBLES, srcB, TILE_BYTES, &full_bar[s]);
     };
 
     if (tid == 0 && nitems > 0) issue(0);
 
-    double acc[4][4][2];
+    double acc[32];   // [mi][ni][e] flattened: the epilogue rotates it so that a rolled loop can index it statically
     for (int64_t item = 0; item < nitems; ++item) {
         const int64_t tl = item / p.nchunks;
         const int c = (int)(item - tl * p.nchunks);
@@ -157,12 +155,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel(const GramPara
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                for (int ni = 0; ni < 4; ++ni) acc[(mi * 4 + ni) * 2] = acc[(mi * 4 + ni) * 2 + 1] = 0.0;
         }
         mbar_wait(&full_bar[s], (uint32_t)((item >> 1) & 1));
 
-        const double* a_base = sA[s] + (wm * 32 + g) * KLD + q;
-        const double* b_base = sB[s] + (wn * 32 + g) * KLD + q;
+        const double* a_base = smem_d + 2 * s * TILE_DOUBLES + (wm * 32 + g) * KLD + q;
+        const double* b_base = smem_d + (2 * s + 1) * TILE_DOUBLES + (wn * 32 + g) * KLD + q;
 #pragma unroll
         for (int ks = 0; ks < KLD / 4; ++ks) {
             double a[4], b[4];
@@ -173,7 +171,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel(const GramPara
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[(mi * 4 + ni) * 2], acc[(mi * 4 + ni) * 2 + 1], a[mi], b[ni]);
         }
         if (c != p.nchunks - 1) continue;
 
@@ -185,34 +183,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel(const GramPara
         const int64_t gcol_tile = bj * BT;
         const bool mirror = (p.uplo == GABO_SYMM_MIRROR) && (gcol_tile != grow_tile);
         const bool diag_tile = p.symmetric && (gcol_tile == grow_tile);
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
+        // Rolled loop (8 trips x 4 entries) so the epilogue code stays small enough for the instruction cache; the
+        // accumulator array is rotated by 4 each trip, which keeps every register index static.
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+            const int mi = it >> 1, nb2 = (it & 1) * 2;
             const int64_t grow = grow_tile + wm * 32 + mi * 8 + g;
             const bool row_ok = grow < p.row1;
             double na = 0.0;
             if (p.kind == GABO_SQDIST_GAUSSIAN) na = p.normA[grow];
             double* krow = p.K + (grow - p.row0) * p.ldk;
+            double v[4];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                const int64_t gcol = gcol_tile + wn * 32 + ni * 8 + 2 * q;
+            for (int h = 0; h < 2; ++h) {
+                const int64_t gcol = gcol_tile + wn * 32 + (nb2 + h) * 8 + 2 * q;
                 double nb0 = 0.0, nb1 = 0.0;
                 if (p.kind == GABO_SQDIST_GAUSSIAN) { nb0 = p.normB[gcol]; nb1 = p.normB[gcol + 1]; }
-                double v0 = gram_entry(p.kind, acc[mi][ni][0], na, nb0, p.beta, p.variance);
-                double v1 = gram_entry(p.kind, acc[mi][ni][1], na, nb1, p.beta, p.variance);
+                v[2 * h] = gram_entry(p.kind, acc[2 * h], na, nb0, p.beta, p.variance, exptab);
+                v[2 * h + 1] = gram_entry(p.kind, acc[2 * h + 1], na, nb1, p.beta, p.variance, exptab);
                 if (diag_tile) {   // K(X,X) diagonal is exactly `variance` (matches Kdiag, kernels_sphere_tf.py:105)
-                    if (gcol == grow) v0 = p.variance;
-                    if (gcol + 1 == grow) v1 = p.variance;
+                    if (gcol == grow) v[2 * h] = p.variance;
+                    if (gcol + 1 == grow) v[2 * h + 1] = p.variance;
                 }
-                if (row_ok) {
+            }
+#pragma unroll
+            for (int k = 0; k < 28; ++k) acc[k] = acc[k + 4];
+            if (row_ok) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t gcol = gcol_tile + wn * 32 + (nb2 + h) * 8 + 2 * q;
                     if (gcol + 1 < p.n2 && p.vec_ok) {
-                        st_cs_v2(krow + gcol, v0, v1);
+                        st_cs_v2(krow + gcol, v[2 * h], v[2 * h + 1]);
                     } else {
-                        if (gcol < p.n2) st_cs(krow + gcol, v0);
-                        if (gcol + 1 < p.n2) st_cs(krow + gcol + 1, v1);
+                        if (gcol < p.n2) st_cs(krow + gcol, v[2 * h]);
+                        if (gcol + 1 < p.n2) st_cs(krow + gcol + 1, v[2 * h + 1]);
                     }
                     if (mirror) {   // K[col][row] = K[row][col]; 8 lanes of equal q write 64 contiguous bytes
-                        st_cs(p.K + gcol * p.ldk + grow, v0);
-                        st_cs(p.K + (gcol + 1) * p.ldk + grow, v1);
+                        st_cs(p.K + gcol * p.ldk + grow, v[2 * h]);
+                        st_cs(p.K + (gcol + 1) * p.ldk + grow, v[2 * h + 1]);
                     }
                 }
             }

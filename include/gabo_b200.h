@@ -58,6 +58,8 @@ enum gabo_uplo {
 };
 
 int gabo_abi_version(void);
+/* Diagnostic only: number of CUDA kernels this library has launched in this process so far. */
+long long gabo_launch_count(void);
 /* Fills SM count and compute capability of the current device. */
 int gabo_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Static, human-readable text for a status code returned by any call below. */
