@@ -30,7 +30,7 @@ int launch_gemm(bool a_kmaj, bool b_kmaj, int64_t m, int64_t n, int64_t k, doubl
     p.lower = lower ? 1 : 0;
     p.vecA = aligned16(A, lda) ? 1 : 0; p.vecB = aligned16(B, ldb) ? 1 : 0; p.vecC = aligned16(C, ldc) ? 1 : 0;
     p.alpha = alpha; p.beta0 = beta0 ? 1 : 0;
-    dim3 grid((unsigned)ceil_div64(n, GT), (unsigned)ceil_div64(m, GT));
+    dim3 grid((unsigned)ceil_div64(n, GTN), (unsigned)ceil_div64(m, GTM));
     const int smem = (int)GEMM_SMEM_BYTES;
 #define GABO_GEMM_LAUNCH(AK, BK_)                                                                                   \
     do {                                                                                                            \
@@ -78,30 +78,31 @@ __device__ __forceinline__ void tri_inverse_inplace_smem(double* S, int tid) {
     }
 }
 
-// ---- 32x32 building block, one warp, registers + shuffles ---------------------------------------------------------------
-// Lane i holds row i of the block (a[k], k <= i).  On return a = Cholesky factor L (row i in lane i) and w = column
-// `lane` of inv(L) (w[i], i >= lane).  Returns the 1-based index of the first non-positive pivot, or 0.
-__device__ __forceinline__ int warp_chol32_inv(double (&a)[32], double (&w)[32], int lane) {
+// ---- 16x16 building block, one warp (lanes 0..15 hold rows), registers + shuffles ----------------------------------------
+// Kept at 16 so that the unrolled code (~1k instructions) is reused by all 8 diagonal steps from the instruction cache.
+// On return a = Cholesky factor L (row `lane` in lane), w = column `lane` of inv(L) (w[i], i >= lane).
+// Returns the 1-based index of the first non-positive pivot, or 0.
+constexpr int BS = 16;              // register block
+constexpr int NBLK = NB_IN / BS;    // 8 diagonal steps
+__device__ __forceinline__ int warp_chol16_inv(double (&a)[BS], double (&w)[BS], int lane) {
     const unsigned FULL = 0xffffffffu;
-    double rinv[32];
+    double rinv[BS];
     int bad = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < BS; ++j) {
         const double d = __shfl_sync(FULL, a[j], j);
         if (!(d > 0.0) && bad == 0) bad = j + 1;
-        const double ljj = sqrt(d);
-        rinv[j] = 1.0 / ljj;
-        if (lane == j) a[j] = ljj;
+        rinv[j] = rsqrt(d);
+        if (lane == j) a[j] = d * rinv[j];
         else if (lane > j) a[j] *= rinv[j];
 #pragma unroll
-        for (int k = j + 1; k < 32; ++k) {
+        for (int k = j + 1; k < BS; ++k) {
             const double lkj = __shfl_sync(FULL, a[j], k);
             if (lane >= k) a[k] = fma(-a[j], lkj, a[k]);
         }
     }
-    // inverse: lane = column c of W; w[i] = (delta_ic - sum_{k<i} L[i][k] w[k]) / L[i][i]
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < BS; ++i) {   // lane = column c of W: w[i] = (delta_ic - sum_{k<i} L[i][k] w[k]) / L[i][i]
         double s = (lane == i) ? 1.0 : 0.0;
 #pragma unroll
         for (int k = 0; k < i; ++k) {
@@ -113,25 +114,19 @@ __device__ __forceinline__ int warp_chol32_inv(double (&a)[32], double (&w)[32],
     return bad;
 }
 
-constexpr int DLD = 36;   // leading dimension of the 32x32 scratch blocks (4 mod 16)
-constexpr size_t POTF2V2_SMEM = (size_t)(NB_IN * WLD + 4 * 32 * DLD + 32 * DLD) * sizeof(double);   // 181,248
-
-// one 8x8 output tile per call: acc += A[8 x K] * B[8 x K]^T, both K-major in shared memory
-__device__ __forceinline__ void dmma_tile_nt(double& c0, double& c1, const double* A, int lda, const double* B, int ldb,
-                                             int ksteps, int g, int q) {
-    for (int ks = 0; ks < ksteps; ++ks) dmma884(c0, c1, A[g * lda + ks * 4 + q], B[g * ldb + ks * 4 + q]);
-}
+constexpr int DLD = 20;   // leading dimension of the 16-wide scratch blocks (4 mod 16)
+constexpr size_t POTF2V2_SMEM = (size_t)(NB_IN * WLD + NB_IN * DLD + NB_IN * DLD) * sizeof(double);   // 176,128
 
 // ---- diagonal block: L11 = chol(A11 + sigma2 I) in place; Winv = inv(L11) (dense [128][128], zero above) ---------------
-// Blocked by 32 inside one CTA (8 warps): warp 0 factors and inverts each 32x32 diagonal block in registers, the
-// panel below it (x inv^T), the trailing update and the assembly of the 128x128 inverse run on DMMA from shared memory.
+// Blocked by 16 inside one CTA (8 warps): warp 0 factors and inverts each 16x16 diagonal block in registers; the panel
+// below it (x inv^T), the trailing update and the assembly of the 128x128 inverse run on DMMA from shared memory.
 __global__ void __launch_bounds__(256, 1) potf2_inv_kernel(double* __restrict__ A, int64_t lda, int jb, double sigma2,
                                                            double* __restrict__ Winv, int32_t* __restrict__ info,
                                                            int info_base) {
     extern __shared__ __align__(16) double sm_potf2[];
-    double* S = sm_potf2;                      // [128][132] the block (lower part), later its inverse (off-diagonal blocks)
-    double* Dv = sm_potf2 + NB_IN * WLD;       // [4][32][36] inverses of the diagonal 32x32 blocks
-    double* T = Dv + 4 * 32 * DLD;             // [32][36] scratch
+    double* S = sm_potf2;                      // [128][132] the block (lower part); its strictly-lower blocks become the inverse
+    double* Dv = sm_potf2 + NB_IN * WLD;       // [8][16][20] inverses of the diagonal 16x16 blocks, row-major
+    double* Y = Dv + NB_IN * DLD;              // [112][20] scratch of the inverse assembly
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
     for (int e = tid; e < NB_IN * NB_IN; e += 256) {
@@ -142,49 +137,57 @@ __global__ void __launch_bounds__(256, 1) potf2_inv_kernel(double* __restrict__ 
         S[r * WLD + c] = v;
     }
     __syncthreads();
-    for (int kb = 0; kb < 4; ++kb) {
-        const int o = kb * 32;
+#pragma unroll 1
+    for (int kb = 0; kb < NBLK; ++kb) {
+        const int o = kb * BS;
         if (warp == 0) {
-            double a[32], w[32];
+            double a[BS], w[BS];
+            const int ln = lane & (BS - 1);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) a[k] = (k <= lane) ? S[(o + lane) * WLD + o + k] : 0.0;
-            const int bad = warp_chol32_inv(a, w, lane);
+            for (int k = 0; k < BS; ++k) a[k] = (k <= ln) ? S[(o + ln) * WLD + o + k] : 0.0;
+            const int bad = warp_chol16_inv(a, w, lane);
             if (bad != 0 && o + bad <= jb && lane == 0) atomicCAS(info, 0, info_base + o + bad);
+            if (lane < BS) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                if (k <= lane) S[(o + lane) * WLD + o + k] = a[k];
-                Dv[(kb * 32 + k) * DLD + lane] = w[k];          // W[k][lane]
+                for (int k = 0; k < BS; ++k) {
+                    if (k <= lane) S[(o + lane) * WLD + o + k] = a[k];
+                    Dv[(o + k) * DLD + lane] = w[k];            // W[k][lane]
+                }
             }
         }
         __syncthreads();
-        // panel: rows below, 8-row strips; X = A_strip * W_kk^T (each strip reads only its own rows: no cross-warp hazard)
-        const int nstrips = (NB_IN - o - 32) / 8;
+        // panel: rows below, 8-row strips; X = A_strip * W_kk^T.  A strip reads only its own rows: no cross-warp hazard.
+        const int nstrips = (NB_IN - o - BS) / 8;
         for (int st = warp; st < nstrips; st += 8) {
-            const int r0 = o + 32 + st * 8;
-            double c[4][2];
+            const double* Ar = S + (o + BS + st * 8 + g) * WLD + o + q;
+            double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                c[ni][0] = c[ni][1] = 0.0;
-                dmma_tile_nt(c[ni][0], c[ni][1], S + r0 * WLD + o, WLD, Dv + (kb * 32 + ni * 8) * DLD, DLD, 8, g, q);
+            for (int ks = 0; ks < BS / 4; ++ks) {
+                const double av = Ar[ks * 4];
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) dmma884(c[ni][0], c[ni][1], av, Dv[(o + ni * 8 + g) * DLD + ks * 4 + q]);
             }
             __syncwarp();
+            double* Xr = S + (o + BS + st * 8 + g) * WLD + o + 2 * q;
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                S[(r0 + g) * WLD + o + ni * 8 + 2 * q] = c[ni][0];
-                S[(r0 + g) * WLD + o + ni * 8 + 2 * q + 1] = c[ni][1];
-            }
+            for (int ni = 0; ni < 2; ++ni) { Xr[ni * 8] = c[ni][0]; Xr[ni * 8 + 1] = c[ni][1]; }
         }
         __syncthreads();
-        // trailing update of the lower part: S[i][j] -= sum_k S[i][o+k] S[j][o+k], 8x8 tiles, strips by warp
-        for (int st = warp; st < nstrips; st += 8) {
-            const int r0 = o + 32 + st * 8;
-            for (int ct = 0; ct <= st; ++ct) {
-                const int c0 = o + 32 + ct * 8;
-                double u0 = 0.0, u1 = 0.0;
-                dmma_tile_nt(u0, u1, S + r0 * WLD + o, WLD, S + c0 * WLD + o, WLD, 8, g, q);
-                S[(r0 + g) * WLD + c0 + 2 * q] -= u0;
-                S[(r0 + g) * WLD + c0 + 2 * q + 1] -= u1;
-            }
+        // trailing update of the lower part: S[i][j] -= sum_k S[i][o+k] S[j][o+k]; 8x8 tiles dealt round-robin to warps
+        const int ntiles = nstrips * (nstrips + 1) / 2;
+        for (int t = warp; t < ntiles; t += 8) {
+            int st = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while (st * (st + 1) / 2 > t) --st;
+            while ((st + 1) * (st + 2) / 2 <= t) ++st;
+            const int ct = t - st * (st + 1) / 2;
+            const double* Ar = S + (o + BS + st * 8 + g) * WLD + o + q;
+            const double* Br = S + (o + BS + ct * 8 + g) * WLD + o + q;
+            double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < BS / 4; ++ks) dmma884(u0, u1, Ar[ks * 4], Br[ks * 4]);
+            double* Cr = S + (o + BS + st * 8 + g) * WLD + o + BS + ct * 8 + 2 * q;
+            Cr[0] -= u0;
+            Cr[1] -= u1;
         }
         __syncthreads();
     }
@@ -194,48 +197,52 @@ __global__ void __launch_bounds__(256, 1) potf2_inv_kernel(double* __restrict__ 
         if (c <= r) A[(int64_t)r * lda + c] = S[r * WLD + c];
     }
     __syncthreads();
-    // inverse, block columns left to right: W_ij = -W_ii (sum_{k=j}^{i-1} L_ik W_kj), i > j.  16 tiles of 8x8 per block,
-    // two per warp.  W_jj lives in Dv; W_kj (j < k < i) already overwrote L_kj in S.
-    for (int j = 0; j < 3; ++j) {
-        for (int i = j + 1; i < 4; ++i) {
-            // T = sum_k L_ik W_kj : A = L_ik (K-major rows), B = W_kj read as [k][n] (N-major)
-            double t[2][2];
+    // inverse, block columns right to left: W[j+1:, j] = -W[j+1:, j+1:] * (L[j+1:, j] * W_jj).  Column j of S still holds L,
+    // everything to its right already holds W, so both products have no sequential block dependency.
+#pragma unroll 1
+    for (int j = NBLK - 2; j >= 0; --j) {
+        const int o = j * BS, r1 = o + BS, nstr = (NB_IN - r1) / 8;
+        // Y = L[r1:, o:o+16] * W_jj   (W_jj read as [k][n])
+        for (int st = warp; st < nstr; st += 8) {
+            const double* Ar = S + (r1 + st * 8 + g) * WLD + o + q;
+            double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int tile = warp * 2 + h, tm = tile >> 2, tn = tile & 3;
-                t[h][0] = t[h][1] = 0.0;
-                for (int k = j; k < i; ++k) {
-                    const double* Lik = S + (i * 32 + tm * 8) * WLD + k * 32;
-                    const double* Wkj = (k == j) ? (Dv + j * 32 * DLD) : (S + (k * 32) * WLD + j * 32);
-                    const int ldw = (k == j) ? DLD : WLD;
-                    for (int ks = 0; ks < 8; ++ks)
-                        dmma884(t[h][0], t[h][1], Lik[g * WLD + ks * 4 + q], Wkj[(ks * 4 + q) * ldw + tn * 8 + g]);
-                }
-            }
-            __syncthreads();   // all reads of L_ij (k == j term) done before T / W_ij are written
+            for (int ks = 0; ks < BS / 4; ++ks) {
+                const double av = Ar[ks * 4];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int tile = warp * 2 + h, tm = tile >> 2, tn = tile & 3;
-                T[(tm * 8 + g) * DLD + tn * 8 + 2 * q] = t[h][0];
-                T[(tm * 8 + g) * DLD + tn * 8 + 2 * q + 1] = t[h][1];
+                for (int ni = 0; ni < 2; ++ni) dmma884(c[ni][0], c[ni][1], av, Dv[(o + ks * 4 + q) * DLD + ni * 8 + g]);
             }
-            __syncthreads();
+            double* Yr = Y + (st * 8 + g) * DLD + 2 * q;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int tile = warp * 2 + h, tm = tile >> 2, tn = tile & 3;
-                double u0 = 0.0, u1 = 0.0;
-                const double* Wii = Dv + (i * 32 + tm * 8) * DLD;
-                for (int ks = 0; ks < 8; ++ks) dmma884(u0, u1, Wii[g * DLD + ks * 4 + q], T[(ks * 4 + q) * DLD + tn * 8 + g]);
-                S[(i * 32 + tm * 8 + g) * WLD + j * 32 + tn * 8 + 2 * q] = -u0;
-                S[(i * 32 + tm * 8 + g) * WLD + j * 32 + tn * 8 + 2 * q + 1] = -u1;
-            }
-            __syncthreads();
+            for (int ni = 0; ni < 2; ++ni) { Yr[ni * 8] = c[ni][0]; Yr[ni * 8 + 1] = c[ni][1]; }
         }
+        __syncthreads();
+        // W[r1 + r, o + c] = -sum_{k <= r} Wt[r][k] Y[k][c];  Wt = inverse of the trailing block (diagonal blocks from Dv)
+        for (int st = warp; st < nstr; st += 8) {
+            const int rr = st * 8;                      // first row of the strip inside the trailing block
+            double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            const int kdiag = (rr / BS) * BS;           // start of the diagonal block this strip belongs to
+            for (int k0 = 0; k0 < kdiag; k0 += 4) {     // strictly-lower part: from S
+                const double av = S[(r1 + rr + g) * WLD + r1 + k0 + q];
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) dmma884(c[ni][0], c[ni][1], av, Y[(k0 + q) * DLD + ni * 8 + g]);
+            }
+#pragma unroll
+            for (int ks = 0; ks < BS / 4; ++ks) {       // diagonal block: from Dv (zero above the diagonal)
+                const double av = Dv[(r1 + rr + g) * DLD + ks * 4 + q];
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) dmma884(c[ni][0], c[ni][1], av, Y[(kdiag + ks * 4 + q) * DLD + ni * 8 + g]);
+            }
+            double* Wr = S + (r1 + rr + g) * WLD + o + 2 * q;
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) { Wr[ni * 8] = -c[ni][0]; Wr[ni * 8 + 1] = -c[ni][1]; }
+        }
+        __syncthreads();
     }
     for (int e = tid; e < NB_IN * NB_IN; e += 256) {
         const int r = e >> 7, c = e & 127;
         double v = 0.0;
-        if ((r >> 5) == (c >> 5)) v = Dv[((r >> 5) * 32 + (r & 31)) * DLD + (c & 31)];   // zero above the diagonal already
+        if ((r / BS) == (c / BS)) v = Dv[r * DLD + (c & (BS - 1))];   // diagonal blocks (zero above the diagonal already)
         else if (c < r) v = S[r * WLD + c];
         Winv[e] = v;
     }
