@@ -107,7 +107,7 @@ struct SpdGramParams {
 };
 
 template <int D, int KIND>
-__global__ void __launch_bounds__(TJ) spd_gram_kernel(const SpdGramParams p) {
+__global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_gram_kernel(const SpdGramParams p) {
     constexpr int DD = D * D;
     constexpr int MP = D * (D + 1) / 2;   // packed lower triangle: entry (a,k), k <= a, at a(a+1)/2 + k
     __shared__ double sR[TI][MP];
@@ -190,30 +190,45 @@ __global__ void __launch_bounds__(TJ) spd_gram_kernel(const SpdGramParams p) {
                 } else {
                     // M = W_i S_j W_i^T  (W lower): T = W S row by row, then M[a][b] = sum_k T[a][k] W[b][k]
                     double Mx[D][D];
+                    auto congruence = [&]() {
 #pragma unroll
-                    for (int a = 0; a < D; ++a) {
-                        double T[D];
+                        for (int a = 0; a < D; ++a) {
+                            double T[D];
 #pragma unroll
-                        for (int c = 0; c < D; ++c) {
-                            double v = 0.0;
+                            for (int c = 0; c < D; ++c) {
+                                double v = 0.0;
 #pragma unroll
-                            for (int k = 0; k <= a; ++k) v = fma(sR[r][a * (a + 1) / 2 + k], GABO_SYM(B, k, c), v);
-                            T[c] = v;
+                                for (int k = 0; k <= a; ++k) v = fma(sR[r][a * (a + 1) / 2 + k], GABO_SYM(B, k, c), v);
+                                T[c] = v;
+                            }
+#pragma unroll
+                            for (int b = 0; b <= a; ++b) {
+                                double v = 0.0;
+#pragma unroll
+                                for (int k = 0; k <= b; ++k) v = fma(T[k], sR[r][b * (b + 1) / 2 + k], v);
+                                Mx[b][a] = v;   // upper storage
+                            }
                         }
+                    };
+                    congruence();
+                    // eigenvalues: Householder + implicit QL (fast path); cyclic Jacobi when the spectrum is wide enough
+                    // that the absolute accuracy of QL would eat into the 1e-12 relative budget of log(lambda)
+                    double ev[D];
+                    tridiag_ql_eigvals<D>(Mx, ev);
+                    double emin = ev[0], emax = ev[0];
 #pragma unroll
-                        for (int b = 0; b <= a; ++b) {
-                            double v = 0.0;
+                    for (int k = 1; k < D; ++k) { emin = fmin(emin, ev[k]); emax = fmax(emax, ev[k]); }
+                    if (!(emin > 0.02 * emax)) {
+                        congruence();
+                        double dummy[1][1];
+                        jacobi_eig<D, false>(Mx, dummy);
 #pragma unroll
-                            for (int k = 0; k <= b; ++k) v = fma(T[k], sR[r][b * (b + 1) / 2 + k], v);
-                            Mx[b][a] = v;   // upper storage
-                        }
+                        for (int k = 0; k < D; ++k) ev[k] = Mx[k][k];
                     }
-                    double dummy[1][1];
-                    jacobi_eig<D, false>(Mx, dummy);
                     double s2 = 0.0;
 #pragma unroll
                     for (int k = 0; k < D; ++k) {
-                        const double lg = log(Mx[k][k]);   // SPD_utils_tf.py:136-139
+                        const double lg = log(ev[k]);   // SPD_utils_tf.py:136-139
                         s2 = fma(lg, lg, s2);
                     }
                     if (KIND == GABO_SPD_AI_GAUSSIAN) val = p.variance * exp(-p.beta * s2);          // kernels_spd_tf.py:241-248
