@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             print(out)
     tmp = LIB_PATH + '.tmp'
-    subprocess.run([nvcc, '-shared', '-o', tmp, *objs, '-lcudart'], check=True)
+    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', tmp, *objs, '-lcudart'], check=True)
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
