@@ -31,6 +31,10 @@ SIGNATURES = {
     'gabo_gp_loglik_f64': (i32, [i64, i64, vp, i64, vp, i64, vp, vp]),
     'gabo_gp_predict_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, f64, vp, vp, vp]),
     'gabo_gemm_nt_sub_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, i32, vp]),
+    'gabo_trsm_right_workspace_bytes': (sz, [i64]),
+    'gabo_trsm_right_f64': (i32, [i64, i64, vp, i64, vp, i64, vp, sz, vp]),
+    'gabo_syrk_cyclic_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, i32, vp]),
+    'gabo_solve_update_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]),
 }
 
 _lib = None

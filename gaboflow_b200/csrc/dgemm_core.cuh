@@ -34,7 +34,11 @@ struct GemmParams {
     const double* B; int64_t ldb;
     double* C; int64_t ldc;
     int64_t m, n, k;
-    int lower;       // 1: only entries with col <= row are produced (tiles above the diagonal are skipped)
+    int lower;       // 1: only entries with global col <= global row are produced (tiles above the diagonal are skipped)
+    // global coordinates for the mask: gcol = col_base + col; grow = row_base + row, or, for rows stored block-cyclically
+    // (cyc_nb > 0: local row block b = row / cyc_nb is global block b * cyc_world + cyc_rank), the mapped global row
+    int64_t row_base, col_base;
+    int cyc_nb, cyc_world, cyc_rank;
     int vecA, vecB, vecC;   // 16-byte access allowed (even leading dimension, 16 B aligned base)
     double alpha;    // C <- C + alpha * op(A) op(B)   (alpha = -1 for the updates; +1 with beta0 for products)
     int beta0;       // 1: C <- alpha * op(A) op(B)  (C not read)
@@ -134,6 +138,14 @@ __device__ __forceinline__ void gemm_tile_mainloop(const GemmParams& p, int64_t 
     cp_async_wait<0>();
 }
 
+__device__ __forceinline__ int64_t gemm_global_row(const GemmParams& p, int64_t row) {
+    if (p.cyc_nb > 0) {
+        const int64_t b = row / p.cyc_nb;
+        return p.row_base + (b * p.cyc_world + p.cyc_rank) * p.cyc_nb + (row - b * p.cyc_nb);
+    }
+    return p.row_base + row;
+}
+
 // C tile <- C tile + alpha*acc (or alpha*acc when beta0), honouring the bounds and the lower-triangle mask.
 __device__ __forceinline__ void gemm_tile_epilogue(const GemmParams& p, int64_t row0, int64_t col0,
                                                    const double (&acc)[4][4][2]) {
@@ -145,7 +157,11 @@ __device__ __forceinline__ void gemm_tile_epilogue(const GemmParams& p, int64_t 
         const int64_t row = row0 + wm * 32 + mi * 8 + g;
         if (row >= p.m) continue;
         double* crow = p.C + row * p.ldc;
-        const int64_t lim = p.lower ? (row + 1 < p.n ? row + 1 : p.n) : p.n;   // valid columns: col < lim
+        int64_t lim = p.n;   // valid columns: col < lim
+        if (p.lower) {
+            const int64_t l2 = gemm_global_row(p, row) + 1 - p.col_base;
+            lim = l2 < p.n ? l2 : p.n;
+        }
         if (p.vecC && !p.beta0) {
             // issue the four 16-byte loads of this row first, then update and store
             double2 c[4];
@@ -183,7 +199,10 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_kernel(const GemmParams p) {
     extern __shared__ __align__(16) double gemm_smem[];
     const int64_t bi = blockIdx.y, bj = blockIdx.x;
     const int64_t row0 = bi * GTM, col0 = bj * GTN;
-    if (p.lower && col0 > row0 + GTM - 1) return;   // tile strictly above the diagonal
+    if (p.lower) {   // tile strictly above the diagonal (global coordinates of its last row / first column)
+        const int64_t last = (row0 + GTM - 1 < p.m) ? row0 + GTM - 1 : p.m - 1;
+        if (p.col_base + col0 > gemm_global_row(p, last)) return;
+    }
     double acc[4][4][2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
@@ -197,7 +216,12 @@ inline bool aligned16(const void* ptr, int64_t ld) { return (reinterpret_cast<ui
 
 // C[m,n] (+)= alpha * op(A) op(B).  a_kmaj: A given as [m,k] row-major (else [k,m]); b_kmaj: B given as [n,k] row-major
 // (else [k,n]).
+struct GemmMask {   // lower-triangle mask in global coordinates (all zero: local coordinates, C(0,0) on the diagonal)
+    int64_t row_base = 0, col_base = 0;
+    int cyc_nb = 0, cyc_world = 1, cyc_rank = 0;
+};
 int launch_gemm(bool a_kmaj, bool b_kmaj, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
-                const double* B, int64_t ldb, bool beta0, double* C, int64_t ldc, bool lower, cudaStream_t stream);
+                const double* B, int64_t ldb, bool beta0, double* C, int64_t ldc, bool lower, cudaStream_t stream,
+                const GemmMask& mask = GemmMask());
 
 }  // namespace gabo

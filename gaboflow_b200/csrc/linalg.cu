@@ -23,9 +23,12 @@ namespace gabo {
 
 // ------------------------------------------------------------------------------------------------------------------
 int launch_gemm(bool a_kmaj, bool b_kmaj, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
-                const double* B, int64_t ldb, bool beta0, double* C, int64_t ldc, bool lower, cudaStream_t stream) {
+                const double* B, int64_t ldb, bool beta0, double* C, int64_t ldc, bool lower, cudaStream_t stream,
+                const GemmMask& mask) {
     if (m <= 0 || n <= 0) return 0;
     GemmParams p;
+    p.row_base = mask.row_base; p.col_base = mask.col_base;
+    p.cyc_nb = mask.cyc_nb; p.cyc_world = mask.cyc_world; p.cyc_rank = mask.cyc_rank;
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.m = m; p.n = n; p.k = k;
     p.lower = lower ? 1 : 0;
     p.vecA = aligned16(A, lda) ? 1 : 0; p.vecB = aligned16(B, ldb) ? 1 : 0; p.vecC = aligned16(C, ldc) ? 1 : 0;
@@ -691,4 +694,84 @@ extern "C" int gabo_gemm_nt_sub_f64(int64_t m, int64_t n, int64_t k, const doubl
     if (ldc < n) return -9;
     return launch_gemm(true, true, m, n, k, -1.0, A, lda, B, ldb, false, C, ldc, lower != 0,
                        static_cast<cudaStream_t>(stream));
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Building blocks of the multi-GPU (1-D block-cyclic by row panels) factorisation; see gaboflow_b200/dist.py.
+
+// A[m, nb] <- A * L^-T with L lower nb x nb (the panel step of a right-looking Cholesky for rows that live on this rank).
+extern "C" size_t gabo_trsm_right_workspace_bytes(int64_t nb) { return gabo_trsm_workspace_bytes(nb, 1); }
+
+extern "C" int gabo_trsm_right_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, double* A, int64_t lda,
+                                   void* workspace, size_t workspace_bytes, gabo_stream_t stream_) {
+    if (m < 0) return -1;
+    if (nb < 0) return -2;
+    if (m == 0 || nb == 0) return 0;
+    if (L == nullptr) return -3;
+    if (ldl < nb) return -4;
+    if (A == nullptr) return -5;
+    if (lda < nb) return -6;
+    if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return -7;
+    if (workspace_bytes < gabo_trsm_right_workspace_bytes(nb)) return -8;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    double* Wall = static_cast<double*>(workspace);
+    const int64_t nblk = ceil_div64(nb, NB_IN);
+    int rc;
+    if ((rc = set_smem(trtri_blocks_kernel, POTF2_SMEM))) return rc;
+    if ((rc = set_smem(panel_trsm_kernel, PANEL_SMEM))) return rc;
+    trtri_blocks_kernel<<<(unsigned)nblk, 512, POTF2_SMEM, stream>>>(L, ldl, nb, Wall);
+    GABO_LAUNCH_CHECK();
+    for (int64_t b = 0; b < nblk; ++b) {
+        const int64_t j0 = b * NB_IN;
+        const int jb = (int)((nb - j0) < NB_IN ? (nb - j0) : NB_IN);
+        if (j0 > 0) {   // A[:, j0:j0+jb] -= A[:, 0:j0] * L[j0:j0+jb, 0:j0]^T
+            rc = launch_gemm(true, true, m, jb, j0, -1.0, A, lda, L + j0 * ldl, ldl, false, A + j0, lda, false, stream);
+            if (rc) return rc;
+        }
+        panel_trsm_kernel<<<(unsigned)ceil_div64(m, CH), 256, PANEL_SMEM, stream>>>(A + j0, lda, m, jb, Wall + b * NB_IN * NB_IN);
+        GABO_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// C[m, n] -= A[m, k] * B[n, k]^T on the entries whose GLOBAL column (col_base + c) does not exceed their GLOBAL row, where
+// local row r of C belongs to a block-cyclic row distribution: block r / cyc_nb of this rank is global block
+// (r / cyc_nb) * cyc_world + cyc_rank, offset by row_base.  cyc_nb == 0 means rows are not permuted (global row = row_base + r).
+extern "C" int gabo_syrk_cyclic_f64(int64_t m, int64_t n, int64_t k, const double* A, int64_t lda, const double* B,
+                                    int64_t ldb, double* C, int64_t ldc, int64_t row_base, int64_t col_base, int cyc_nb,
+                                    int cyc_world, int cyc_rank, gabo_stream_t stream) {
+    if (m < 0) return -1;
+    if (n < 0) return -2;
+    if (k < 0) return -3;
+    if (m == 0 || n == 0) return 0;
+    if (k > 0 && A == nullptr) return -4;
+    if (lda < k) return -5;
+    if (k > 0 && B == nullptr) return -6;
+    if (ldb < k) return -7;
+    if (C == nullptr) return -8;
+    if (ldc < n) return -9;
+    if (cyc_nb < 0) return -12;
+    if (cyc_world < 1) return -13;
+    if (cyc_rank < 0 || cyc_rank >= cyc_world) return -14;
+    GemmMask mask;
+    mask.row_base = row_base; mask.col_base = col_base; mask.cyc_nb = cyc_nb; mask.cyc_world = cyc_world; mask.cyc_rank = cyc_rank;
+    return launch_gemm(true, true, m, n, k, -1.0, A, lda, B, ldb, false, C, ldc, true, static_cast<cudaStream_t>(stream), mask);
+}
+
+// y[m, nrhs] -= Lp[m, k] * x[k, nrhs]   (forward-substitution update of the rows this rank owns; nrhs <= 4 uses the
+// HBM-bound GEMV kernel, larger nrhs the DMMA core).
+extern "C" int gabo_solve_update_f64(int64_t m, int64_t k, int64_t nrhs, const double* Lp, int64_t ldl, const double* X,
+                                     int64_t ldx, double* Y, int64_t ldy, gabo_stream_t stream_) {
+    if (m < 0) return -1;
+    if (k < 0 || k > NB_IN * 64) return -2;
+    if (nrhs < 0) return -3;
+    if (m == 0 || k == 0 || nrhs == 0) return 0;
+    if (Lp == nullptr) return -4;
+    if (ldl < k) return -5;
+    if (X == nullptr) return -6;
+    if (ldx < nrhs) return -7;
+    if (Y == nullptr) return -8;
+    if (ldy < nrhs) return -9;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    return launch_gemm(true, false, m, nrhs, k, -1.0, Lp, ldl, X, ldx, false, Y, ldy, false, stream);
 }

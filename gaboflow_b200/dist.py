@@ -1,0 +1,223 @@
+"""Multi-GPU layer: one process per GPU, torch.distributed for the plumbing (NCCL over NVLink on the GPU box, gloo in the
+CPU tests of the host logic), the C-ABI kernels for all local arithmetic.
+
+Layout: the Gram matrix is distributed by ROW PANELS of nb rows, 1-D block-cyclic: global panel p
+lives on rank p % world in local slot p // world, each rank storing full rows [local_rows, n] (row-major, so a "column
+panel" of the symmetric matrix is a row panel here).
+  * Gram generation needs no exchange: X is replicated (<= 27 MB) and every rank produces its own row panels.
+  * Cholesky is right-looking over panels: the owner factors the nb x nb diagonal block (gabo_potrf_f64) and broadcasts
+    it; every rank solves its rows of the block column (gabo_trsm_right_f64); the block column is all-gathered so that
+    each rank can update the lower part of its own rows (gabo_syrk_cyclic_f64, mask in global coordinates).
+  * Forward substitution is pipelined over panels with an nb-vector broadcast per step; log-likelihood terms are
+    summed with one all-reduce.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class BlockCyclic:
+    """1-D block-cyclic distribution of n rows in panels of nb over `world` ranks."""
+    n: int
+    nb: int
+    world: int
+    rank: int
+
+    @property
+    def npanels(self) -> int:
+        return (self.n + self.nb - 1) // self.nb
+
+    def owner(self, p: int) -> int:
+        return p % self.world
+
+    def slot(self, p: int) -> int:
+        return p // self.world
+
+    def panels_of(self, rank: int) -> List[int]:
+        return list(range(rank, self.npanels, self.world))
+
+    def my_panels(self) -> List[int]:
+        return self.panels_of(self.rank)
+
+    def panel_rows(self, p: int) -> int:
+        return min(self.nb, self.n - p * self.nb)
+
+    def local_rows_of(self, rank: int) -> int:
+        return sum(self.panel_rows(p) for p in self.panels_of(rank))
+
+    @property
+    def local_rows(self) -> int:
+        return self.local_rows_of(self.rank)
+
+    def slots_after(self, kp: int, rank: Optional[int] = None) -> int:
+        """First local slot of `rank` whose global panel index is > kp."""
+        r = self.rank if rank is None else rank
+        return 0 if kp < r else (kp - r) // self.world + 1
+
+    def global_rows(self) -> torch.Tensor:
+        """Global row index of every local row (CPU int64)."""
+        idx = [torch.arange(p * self.nb, p * self.nb + self.panel_rows(p)) for p in self.my_panels()]
+        return torch.cat(idx) if idx else torch.empty(0, dtype=torch.int64)
+
+
+class CudaLocalOps:
+    """Local arithmetic through the C-ABI (the only implementation in the product)."""
+
+    @staticmethod
+    def potrf_(A, sigma2):
+        from . import ops
+        return ops.potrf_(A, sigma2, check=False)
+
+    @staticmethod
+    def trsm_right_(A, L):
+        from . import ops
+        return ops.trsm_right_(A, L)
+
+    @staticmethod
+    def syrk_cyclic_(C, A, B, row_base, col_base, nb, world, rank):
+        from . import ops
+        return ops.syrk_cyclic_(C, A, B, row_base, col_base, nb, world, rank)
+
+    @staticmethod
+    def trsm_left_(L, B):
+        from . import ops
+        return ops.trsm_(L, B, trans=False)
+
+    @staticmethod
+    def solve_update_(Y, Lp, X):
+        from . import ops
+        return ops.solve_update_(Y, Lp, X)
+
+    @staticmethod
+    def loglik_block(Lblk, Vblk):
+        from . import ops
+        return ops.gp_loglik(Lblk, Vblk)          # the Gaussian log-density is additive over row blocks
+
+
+def _world(group=None):
+    return dist.get_world_size(group) if dist.is_initialized() else 1
+
+
+def gram_block_cyclic(gram_rows, layout: BlockCyclic, out: Optional[torch.Tensor] = None, dtype=torch.float64,
+                      device=None) -> torch.Tensor:
+    """Fill this rank's row panels: gram_rows(row0, row1, out_view) writes K[row0:row1, :] into out_view."""
+    if out is None:
+        out = torch.empty((layout.local_rows, layout.n), dtype=dtype, device=device)
+    for p in layout.my_panels():
+        s = layout.slot(p)
+        r0 = p * layout.nb
+        r1 = r0 + layout.panel_rows(p)
+        gram_rows(r0, r1, out[s * layout.nb: s * layout.nb + (r1 - r0)])
+    return out
+
+
+def potrf_block_cyclic_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: float, n_factor: Optional[int] = None,
+                        local=CudaLocalOps, group=None) -> int:
+    """In-place distributed Cholesky of the leading n_factor x n_factor block (default: everything) of the symmetric
+    matrix whose lower triangle is stored block-cyclically in A_loc [local_rows, >= n_factor].  Returns LAPACK-style info
+    (0, or the order of the first non-positive-definite leading minor), identical on every rank."""
+    W, rank, nb = layout.world, layout.rank, layout.nb
+    n = layout.n if n_factor is None else n_factor
+    if n % nb != 0 and n != layout.n:
+        raise ValueError('n_factor must be a multiple of the panel size')
+    npan = (n + nb - 1) // nb
+    dev = A_loc.device
+    Lkk = torch.empty((nb, nb), dtype=A_loc.dtype, device=dev)
+    first_bad = torch.full((1,), 2 ** 62, dtype=torch.int64, device=dev)
+    # local rows that belong to the factored block: panels p < npan
+    my = [p for p in layout.my_panels() if p < npan]
+    rows_f = sum(min(nb, n - p * nb) for p in my)
+    for kp in range(npan):
+        k0 = kp * nb
+        kb = min(nb, n - k0)
+        k1 = k0 + kb
+        owner = layout.owner(kp)
+        if rank == owner:
+            s = layout.slot(kp)
+            blk = A_loc[s * nb: s * nb + kb, k0:k1]
+            info = local.potrf_(blk, sigma2)
+            bad = info.to(torch.int64)
+            first_bad = torch.minimum(first_bad, torch.where(bad > 0, bad + k0, torch.full_like(bad, 2 ** 62)))
+            Lkk[:kb, :kb].copy_(blk)
+        if W > 1:
+            dist.broadcast(Lkk, src=owner, group=group)
+        if k1 >= n:
+            break
+        s0 = layout.slots_after(kp)
+        lr0 = s0 * nb
+        m = rows_f - lr0
+        if m > 0:
+            local.trsm_right_(A_loc[lr0:rows_f, k0:k1], Lkk[:kb, :kb])
+        # all-gather the block column below the diagonal block, in global row order
+        nbelow = npan - (kp + 1)                      # panels below
+        maxslots = (nbelow + W - 1) // W
+        if W > 1:
+            send = torch.zeros((maxslots * nb, kb), dtype=A_loc.dtype, device=dev)
+            if m > 0:
+                send[:m].copy_(A_loc[lr0:rows_f, k0:k1])
+            recv = torch.empty((W, maxslots * nb, kb), dtype=A_loc.dtype, device=dev)
+            dist.all_gather_into_tensor(recv.view(-1, kb), send, group=group)
+            # panel kp+1+t sits on rank (kp+1+t) % W, relative slot t // W
+            shift = (kp + 1) % W
+            order = [(shift + i) % W for i in range(W)]
+            P = recv[order].view(W, maxslots, nb, kb).permute(1, 0, 2, 3).reshape(-1, kb)[: n - k1]
+            if not P.is_contiguous():
+                P = P.contiguous()
+        else:
+            P = A_loc[lr0:rows_f, k0:k1]
+        if m > 0:
+            local.syrk_cyclic_(A_loc[lr0:rows_f, k1:n], A_loc[lr0:rows_f, k0:k1], P, s0 * W * nb, k1, nb, W, rank)
+    if W > 1:
+        dist.all_reduce(first_bad, op=dist.ReduceOp.MIN, group=group)
+    fb = int(first_bad.item())
+    return 0 if fb >= 2 ** 62 else fb
+
+
+def solve_lower_block_cyclic_(A_loc: torch.Tensor, B_loc: torch.Tensor, layout: BlockCyclic,
+                              n_factor: Optional[int] = None, local=CudaLocalOps, group=None) -> torch.Tensor:
+    """B_loc <- L^-1 B for the block-cyclically stored factor; B_loc [local_rows(, of the factored block), nrhs]."""
+    W, rank, nb = layout.world, layout.rank, layout.nb
+    n = layout.n if n_factor is None else n_factor
+    npan = (n + nb - 1) // nb
+    nrhs = int(B_loc.shape[1])
+    my = [p for p in layout.my_panels() if p < npan]
+    rows_f = sum(min(nb, n - p * nb) for p in my)
+    xk = torch.empty((nb, nrhs), dtype=B_loc.dtype, device=B_loc.device)
+    for kp in range(npan):
+        k0 = kp * nb
+        kb = min(nb, n - k0)
+        owner = layout.owner(kp)
+        if rank == owner:
+            s = layout.slot(kp)
+            bk = B_loc[s * nb: s * nb + kb]
+            local.trsm_left_(A_loc[s * nb: s * nb + kb, k0:k0 + kb], bk)
+            xk[:kb].copy_(bk)
+        if W > 1:
+            dist.broadcast(xk, src=owner, group=group)
+        lr0 = layout.slots_after(kp) * nb
+        if rows_f - lr0 > 0:
+            local.solve_update_(B_loc[lr0:rows_f], A_loc[lr0:rows_f, k0:k0 + kb], xk[:kb])
+    return B_loc
+
+
+def gp_loglik_block_cyclic(A_loc: torch.Tensor, V_loc: torch.Tensor, layout: BlockCyclic, n_factor: Optional[int] = None,
+                           local=CudaLocalOps, group=None) -> float:
+    """-0.5 n p log(2 pi) - p sum log L_ii - 0.5 ||V||^2 from the distributed factor and V = L^-1 (y - m)."""
+    W, nb = layout.world, layout.nb
+    n = layout.n if n_factor is None else n_factor
+    npan = (n + nb - 1) // nb
+    acc = torch.zeros((1,), dtype=torch.float64, device=A_loc.device)
+    for p in layout.my_panels():
+        if p >= npan:
+            continue
+        s = layout.slot(p)
+        kb = min(nb, n - p * nb)
+        acc += local.loglik_block(A_loc[s * nb: s * nb + kb, p * nb: p * nb + kb], V_loc[s * nb: s * nb + kb])
+    if W > 1:
+        dist.all_reduce(acc, group=group)
+    return float(acc.item())

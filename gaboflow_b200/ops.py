@@ -255,3 +255,50 @@ def gemm_nt_sub_(Cm: torch.Tensor, A: torch.Tensor, B: torch.Tensor, lower: bool
                                          1 if lower else 0, _stream())
     _lib.check('gabo_gemm_nt_sub_f64', st)
     return Cm
+
+
+# ---- local building blocks of the multi-GPU factorisation (gaboflow_b200/dist.py) ------------------------------------
+def _ldm(t: torch.Tensor) -> int:
+    return max(int(t.stride(0)), int(t.shape[1])) if t.shape[0] > 1 else max(int(t.shape[1]), int(t.stride(0)))
+
+
+def trsm_right_(A: torch.Tensor, L_: torch.Tensor) -> torch.Tensor:
+    """A[m, nb] <- A L^-T in place (L lower nb x nb)."""
+    _req(A, 'A'); _req(L_, 'L')
+    m, nb = int(A.shape[0]), int(A.shape[1])
+    if m == 0 or nb == 0:
+        return A
+    Lh = _lib.lib()
+    nbytes = int(Lh.gabo_trsm_right_workspace_bytes(nb))
+    key = (A.device.index, 'trsm_right')
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=A.device)
+        _ws_cache[key] = ws
+    st = Lh.gabo_trsm_right_f64(m, nb, L_.data_ptr(), _ldm(L_), A.data_ptr(), _ldm(A), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check('gabo_trsm_right_f64', st)
+    return A
+
+
+def syrk_cyclic_(Cm: torch.Tensor, A: torch.Tensor, B: torch.Tensor, row_base: int, col_base: int, cyc_nb: int = 0,
+                 cyc_world: int = 1, cyc_rank: int = 0) -> torch.Tensor:
+    """C[m,n] -= A[m,k] B[n,k]^T where global col <= global row (see gabo_syrk_cyclic_f64)."""
+    _req(Cm, 'C'); _req(A, 'A'); _req(B, 'B')
+    m, n, k = int(Cm.shape[0]), int(Cm.shape[1]), int(A.shape[1])
+    if m == 0 or n == 0:
+        return Cm
+    st = _lib.lib().gabo_syrk_cyclic_f64(m, n, k, A.data_ptr(), _ldm(A), B.data_ptr(), _ldm(B), Cm.data_ptr(), _ldm(Cm),
+                                         int(row_base), int(col_base), int(cyc_nb), int(cyc_world), int(cyc_rank), _stream())
+    _lib.check('gabo_syrk_cyclic_f64', st)
+    return Cm
+
+
+def solve_update_(Y: torch.Tensor, Lp: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+    """Y[m,nrhs] -= Lp[m,k] X[k,nrhs]."""
+    _req(Y, 'Y'); _req(Lp, 'Lp'); _req(X, 'X')
+    m, k, nrhs = int(Lp.shape[0]), int(Lp.shape[1]), int(X.shape[1])
+    if m == 0 or k == 0 or nrhs == 0:
+        return Y
+    st = _lib.lib().gabo_solve_update_f64(m, k, nrhs, Lp.data_ptr(), _ldm(Lp), X.data_ptr(), _ldm(X), Y.data_ptr(), _ldm(Y), _stream())
+    _lib.check('gabo_solve_update_f64', st)
+    return Y

@@ -150,6 +150,23 @@ int gabo_gemm_nt_sub_f64(int64_t m, int64_t n, int64_t k, const double* A, int64
                          const double* B, int64_t ldb, double* C, int64_t ldc, int lower,
                          gabo_stream_t stream);
 
+/* ---- Building blocks of the multi-GPU factorisation (1-D block-cyclic by row panels) --------
+ * The host side (gaboflow_b200/dist.py) broadcasts the factored diagonal block and all-gathers the panel over NCCL;
+ * these calls do the local work of each rank.
+ * gabo_trsm_right_f64: A[m, nb] <- A * L^-T, L lower nb x nb (panel rows owned by this rank). */
+size_t gabo_trsm_right_workspace_bytes(int64_t nb);
+int gabo_trsm_right_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, double* A, int64_t lda,
+                        void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+/* gabo_syrk_cyclic_f64: C[m,n] -= A[m,k] B[n,k]^T restricted to GLOBAL col <= GLOBAL row, where local row r of C is
+ *   global row row_base + ((r / cyc_nb) * cyc_world + cyc_rank) * cyc_nb + r % cyc_nb (cyc_nb == 0: row_base + r) and
+ *   local column c is global column col_base + c. */
+int gabo_syrk_cyclic_f64(int64_t m, int64_t n, int64_t k, const double* A, int64_t lda, const double* B, int64_t ldb,
+                         double* C, int64_t ldc, int64_t row_base, int64_t col_base, int cyc_nb, int cyc_world,
+                         int cyc_rank, gabo_stream_t stream);
+/* gabo_solve_update_f64: Y[m,nrhs] -= Lp[m,k] X[k,nrhs] (substitution update of the rows a rank owns). */
+int gabo_solve_update_f64(int64_t m, int64_t k, int64_t nrhs, const double* Lp, int64_t ldl, const double* X, int64_t ldx,
+                          double* Y, int64_t ldy, gabo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

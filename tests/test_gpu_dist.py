@@ -1,0 +1,69 @@
+"""GPU: the CUDA building blocks of the multi-GPU factorisation against torch-CPU references, and the distributed driver
+with world_size 1 (same code path, no collectives).  The world_size>1 logic is covered on CPU by test_dist_gloo.py and on
+2+ GPUs by tools/dist_check.py (run under torchrun)."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_trsm_right(cuda):
+    from gaboflow_b200 import ops
+    rng = np.random.default_rng(0)
+    for m, nb in [(70, 128), (700, 512), (300, 200), (5, 17)]:
+        G = rng.standard_normal((nb, nb)); L = np.linalg.cholesky(G @ G.T / nb + np.eye(nb))
+        A = rng.standard_normal((m, nb))
+        ref = sla.solve_triangular(L, A.T, lower=True).T
+        big = torch.from_numpy(np.concatenate([A, np.zeros((m, 6))], axis=1)).cuda()     # non-trivial leading dimension
+        ops.trsm_right_(big[:, :nb], torch.from_numpy(L).cuda())
+        assert np.max(np.abs(big[:, :nb].cpu().numpy() - ref)) / np.max(np.abs(ref)) < 1e-12
+
+
+@pytest.mark.parametrize('world,rank', [(1, 0), (2, 1), (4, 2)])
+def test_syrk_cyclic_mask(cuda, world, rank):
+    from gaboflow_b200 import ops
+    rng = np.random.default_rng(world + rank)
+    nb, slots, k, n = 128, 3, 128, 900
+    m = slots * nb
+    A, B, C = rng.standard_normal((m, k)), rng.standard_normal((n, k)), rng.standard_normal((m, n))
+    row_base, col_base = 2 * world * nb, 256
+    r = np.arange(m)
+    grow = row_base + ((r // nb) * world + rank) * nb + r % nb
+    mask = (col_base + np.arange(n))[None, :] <= grow[:, None]
+    ref = np.where(mask, C - A @ B.T, C)
+    Cd = torch.from_numpy(C).cuda()
+    ops.syrk_cyclic_(Cd, torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), row_base, col_base, nb, world, rank)
+    got = Cd.cpu().numpy()
+    assert np.array_equal(got[~mask], C[~mask])
+    assert np.max(np.abs(got - ref)) < 1e-11
+
+
+def test_solve_update(cuda):
+    from gaboflow_b200 import ops
+    rng = np.random.default_rng(3)
+    for m, k, nrhs in [(500, 128, 1), (777, 512, 3), (300, 256, 40)]:
+        Lp, X, Y = rng.standard_normal((m, k)), rng.standard_normal((k, nrhs)), rng.standard_normal((m, nrhs))
+        Yd = torch.from_numpy(Y).cuda()
+        ops.solve_update_(Yd, torch.from_numpy(Lp).cuda(), torch.from_numpy(X).cuda())
+        assert np.max(np.abs(Yd.cpu().numpy() - (Y - Lp @ X))) < 1e-11
+
+
+def test_block_cyclic_driver_world1(cuda):
+    from gaboflow_b200 import SphereGaussianKernel, ops
+    from gaboflow_b200.dist import BlockCyclic, gram_block_cyclic, potrf_block_cyclic_, solve_lower_block_cyclic_, gp_loglik_block_cyclic
+    from oracle import gabo_oracle as orc
+    n = 1536
+    X = orc.synth_sphere(n, 51, seed=4)
+    y = np.random.default_rng(5).standard_normal((n, 1))
+    Xd = torch.from_numpy(X).cuda()
+    k = SphereGaussianKernel(51, range(51), beta_min=0.0, beta=2.0)
+    lay = BlockCyclic(n, 512, 1, 0)
+    A = gram_block_cyclic(lambda r0, r1, out: k.K(Xd, uplo='lower', row0=r0, row1=r1, out=out), lay, device='cuda')
+    assert potrf_block_cyclic_(A, lay, 1e-2, n_factor=1024) == 0
+    V = torch.from_numpy(y[:1024]).cuda()
+    solve_lower_block_cyclic_(A, V, lay, n_factor=1024)
+    ll = gp_loglik_block_cyclic(A, V, lay, n_factor=1024)
+    ref = orc.gp_loglik(orc.sphere_gaussian_K(X[:1024], beta=2.0), y[:1024], 1e-2)
+    assert abs(ll / ref - 1) < 1e-8

@@ -1,0 +1,48 @@
+"""Multi-GPU correctness check, run under torchrun (one rank per GPU, NCCL):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py [N]
+Distributed Gram (block-cyclic row panels) + Cholesky + solve + loglik against the single-GPU path on rank 0."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, '.')
+from gaboflow_b200 import SphereGaussianKernel, ops  # noqa: E402
+from gaboflow_b200.dist import (BlockCyclic, gram_block_cyclic, potrf_block_cyclic_, solve_lower_block_cyclic_,  # noqa: E402
+                                gp_loglik_block_cyclic)
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+rank, world, lr = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(lr)
+dev = torch.device('cuda', lr)
+dist.init_process_group('nccl', device_id=dev)
+rng = np.random.default_rng(20240)
+X = rng.standard_normal((N, 51)); X /= np.linalg.norm(X, axis=1, keepdims=True)
+y = np.random.default_rng(20241).standard_normal((N, 1))
+Xd = torch.from_numpy(X).to(dev)
+k = SphereGaussianKernel(51, range(51), beta_min=0.0, beta=2.0)
+lay = BlockCyclic(N, 512, world, rank)
+A = gram_block_cyclic(lambda r0, r1, out: k.K(Xd, uplo='lower', row0=r0, row1=r1, out=out), lay, device=dev)
+info = potrf_block_cyclic_(A, lay, 1e-2)
+grow = lay.global_rows()
+V = torch.from_numpy(y[grow.numpy()]).to(dev)
+solve_lower_block_cyclic_(A, V, lay)
+ll = gp_loglik_block_cyclic(A, V, lay)
+# single-GPU reference on every rank (cheap at this size)
+Kf = torch.empty((N, N), dtype=torch.float64, device=dev)
+k.K(Xd, uplo='lower', out=Kf)
+ops.potrf_(Kf, 1e-2)
+v1 = torch.from_numpy(y).to(dev)
+ops.trsm_(Kf, v1)
+ll1 = float(ops.gp_loglik(Kf, v1).item())
+Lref = torch.tril(Kf)[grow.to(dev)]
+mask = torch.arange(N, device=dev)[None, :] <= grow.to(dev)[:, None]
+err = float(torch.where(mask, (A - Lref).abs(), torch.zeros_like(A)).max().item())
+verr = float((V - v1[grow.to(dev)]).abs().max().item())
+ok = info == 0 and err < 1e-10 and verr < 1e-9 and abs(ll / ll1 - 1) < 1e-10
+print(f'[rank {rank}/{world}] info={info} max|L-Lref|={err:.2e} max|v-vref|={verr:.2e} loglik {ll:.6f} vs {ll1:.6f}  {"OK" if ok else "FAIL"}', flush=True)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
