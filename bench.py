@@ -33,6 +33,7 @@ SEED_X, SEED_Y = 20240, 20241
 BETA, VARIANCE, SIGMA2 = 2.0, 1.0, 1e-2
 DIM = 51
 FP64_PEAK_TFLOPS = 37.2                # measured on this pool: tools/fp64_probe.cu -> profiles/r01_fp64_probe.txt (DMMA.8x8x4)
+POTRF_DRAM_TRAFFIC_BYTES = None        # dram read+write of one potrf at N=32768 from the ncu capture in profiles/ (filled when captured)
 F_TR = 100                             # declared transcendental flops per sphere Gram entry
 
 
@@ -174,18 +175,21 @@ def run_ours(args):
     y = yh.to(dev)
     kern = SphereGaussianKernel(DIM, range(DIM), beta_min=0.0, beta=BETA, variance=VARIANCE)
 
-    # row-block sharding of the Gram across ranks (128-row granularity, no data-path collective)
-    blk = ops.ROW_BLOCK
-    nblk = (N + blk - 1) // blk
-    b0 = (nblk * rank) // world
-    b1 = (nblk * (rank + 1)) // world
-    row0, row1 = b0 * blk, min(b1 * blk, N)
-    rows = row1 - row0
+    # N = 1: one GPU holds all of K; lower tiles are computed once and mirror-stored.
+    # N > 1: K is distributed by 512-row panels, 1-D block-cyclic (gaboflow_b200/dist.py): every rank generates the full
+    #        rows of its panels with no exchange (X is replicated), then the leading NC x NC block is factored by the
+    #        distributed right-looking Cholesky (diagonal-block broadcast + block-column all-gather over NCCL).
+    from gaboflow_b200.dist import (BlockCyclic, potrf_block_cyclic_, solve_lower_block_cyclic_, gp_loglik_block_cyclic)
+    PANEL = 512
+    lay = BlockCyclic(N, PANEL, world, rank)
+    rows = lay.local_rows
     K = torch.empty((rows, N), dtype=torch.float64, device=dev)
     ws = torch.empty(int(lib.gabo_points_gram_workspace_bytes(N, N, DIM)), dtype=torch.uint8, device=dev)
-    uplo = 'mirror' if world == 1 else 'full'
-    do_chol = (rank == 0 and rows >= NC)     # the leading NC block lives on rank 0 when its row block is tall enough
-    V = torch.empty((NC, 1), dtype=torch.float64, device=dev)
+    grow = lay.global_rows()
+    sel_fac = (grow < NC).to(dev)
+    y_rows = grow[grow < NC].to(dev)
+    V = torch.empty((int(y_rows.numel()) if world > 1 else NC, 1), dtype=torch.float64, device=dev)
+    ll_val_host = [None]
     ll_dev = torch.zeros((1,), dtype=torch.float64, device=dev)
 
     def barrier():
@@ -201,11 +205,18 @@ def run_ours(args):
             yd = yh.to(dev, non_blocking=True)
         if events is not None:
             events[0].record()
-        ops.points_gram(ops.SPHERE_GAUSSIAN, Xd, None, beta=BETA, variance=VARIANCE, out=K, row0=row0, row1=row1,
-                        uplo=uplo, workspace=ws)
+        if world == 1:
+            ops.points_gram(ops.SPHERE_GAUSSIAN, Xd, None, beta=BETA, variance=VARIANCE, out=K, uplo='mirror', workspace=ws)
+        else:
+            for pnl in lay.my_panels():
+                sl = lay.slot(pnl) * PANEL
+                r0 = pnl * PANEL
+                r1 = r0 + lay.panel_rows(pnl)
+                ops.points_gram(ops.SPHERE_GAUSSIAN, Xd, None, beta=BETA, variance=VARIANCE, out=K[sl: sl + (r1 - r0)],
+                                row0=r0, row1=r1, uplo='full', workspace=ws)
         if events is not None:
             events[1].record()
-        if do_chol:
+        if world == 1:
             A = K[:NC, :NC]                       # leading block, ld = N, factored in place (K is regenerated next step)
             ops.potrf_(A, SIGMA2, check=False)
             if events is not None:
@@ -213,12 +224,20 @@ def run_ours(args):
             V.copy_(yd[:NC])
             ops.trsm_(A, V)
             ll_dev = ops.gp_loglik(A, V)
-        elif events is not None:
-            events[2].record()
-        if events is not None:
-            events[3].record()
-        if from_host:
-            return float(ll_dev.item())          # device -> host read of the step's result
+            if events is not None:
+                events[3].record()
+            if from_host:
+                return float(ll_dev.item())      # device -> host read of the step's result
+        else:
+            potrf_block_cyclic_(K, lay, SIGMA2, n_factor=NC)
+            if events is not None:
+                events[2].record()
+            V.copy_(yd[y_rows])
+            solve_lower_block_cyclic_(K, V, lay, n_factor=NC)
+            ll_val_host[0] = gp_loglik_block_cyclic(K, V, lay, n_factor=NC)   # all-reduce + device -> host read
+            if events is not None:
+                events[3].record()
+            return ll_val_host[0]
         return None
 
     for _ in range(args.warmup):
@@ -241,7 +260,7 @@ def run_ours(args):
     gram_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     potrf_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
     solve_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
-    ll_val = float(ll_dev.item()) if do_chol else None
+    ll_val = float(ll_dev.item()) if world == 1 else ll_val_host[0]
 
     # ---- end to end from pinned host buffers through the public API ----
     for _ in range(min(args.warmup, 2)):
@@ -292,29 +311,33 @@ def run_ours(args):
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'sphere Gaussian Gram N={N} on S^50 (D={DIM}) + FP64 Cholesky of K+1e-2 I at N={NC} + solve + loglik',
                    'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2, 'seeds': [SEED_X, SEED_Y],
-                   'gram_mode': 'lower tiles computed once, mirror-stored (full dense K)' if sym else 'row blocks of the full dense K, one per rank',
+                   'gram_mode': 'lower tiles computed once, mirror-stored (full dense K)' if sym else
+                                f'full rows of the dense K in {PANEL}-row panels, 1-D block-cyclic over {world} ranks',
                    'l2': f'no flush: {rows * N * 8 / 1e9:.1f} GB of K per GPU >> 126 MB L2',
-                   'parallelism': 'single GPU' if world == 1 else f'Gram rows sharded over {world} ranks, no collective; Cholesky on rank 0'},
+                   'parallelism': 'single GPU' if world == 1 else
+                                  f'Gram: row panels block-cyclic over {world} ranks, no collective; Cholesky: right-looking over panels, '
+                                  f'diagonal-block broadcast + block-column all-gather over NCCL'},
         'phases_ms': {'gram': gram_ms, 'potrf': potrf_ms, 'solve_loglik': solve_ms},
         'cholesky': {'n': NC, 'seconds': potrf_s, 'tflops': potrf_tflops,
-                     'frac_fp64_tensor_peak': (potrf_tflops / FP64_PEAK_TFLOPS) if potrf_tflops else None},
+                     'frac_fp64_tensor_peak': (potrf_tflops / (FP64_PEAK_TFLOPS * world)) if potrf_tflops else None},
         'loglik': ll_val,
         'gpu_launches': launches_all,
         'clocks': clocks.summary(),
         'e2e': {'value': entries / (e2e_gram_ms * 1e-3), 'unit': 'entries/s',
                 'h2d_bytes_per_step': int(Xh.numel() * 8 + yh.numel() * 8), 'd2h_bytes_per_step': 8,
                 'ms_per_step': e2e_total_ms / args.steps,
-                'api': 'pinned host X,y -> device, ops.points_gram / potrf_ / trsm_ / gp_loglik (C-ABI), loglik.item()'},
+                'api': 'pinned host X,y -> device, ops.points_gram / potrf_ / trsm_ / gp_loglik (C-ABI; gaboflow_b200.dist for N>1), loglik read back'},
         'roofline': {'bound': 'tensor', 'kernel': 'gabo_potrf_f64 (95% in gemm_kernel<true,true>, DMMA.8x8x4)',
-                     'achieved': potrf_tflops, 'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s',
-                     'frac': (potrf_tflops / FP64_PEAK_TFLOPS) if potrf_tflops else None, 'traffic': None,
+                     'achieved': potrf_tflops, 'peak': FP64_PEAK_TFLOPS * world, 'unit': 'TFLOP/s',
+                     'frac': (potrf_tflops / (FP64_PEAK_TFLOPS * world)) if potrf_tflops else None,
+                     'traffic': POTRF_DRAM_TRAFFIC_BYTES if (world == 1 and NC == 32768) else None,
                      'flops_per_launch': NC ** 3 / 3,
                      'peak_source': 'FP64 tensor peak is not in MEASURED_PEAKS.json: measured on this pool with tools/fp64_probe.cu '
                                     '(profiles/r01_fp64_probe.txt, DMMA 37.2 TFLOP/s; cuBLAS DGEMM 36.2)'},
         'roofline_gram': {'bound': 'fp64', 'kernel': 'points_gram_kernel<52>', 'achieved': gram_flops / (gram_ms * 1e-3) * 1e-12,
-                          'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s',
-                          'frac': gram_flops / (gram_ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS,
-                          'hbm_write_gbs': rows * N * 8 / (gram_ms * 1e-3) * 1e-9, 'hbm_peak_gbs': hbm_peak, 'hbm_peak_source': hbm_src,
+                          'peak': FP64_PEAK_TFLOPS * world, 'unit': 'TFLOP/s',
+                          'frac': gram_flops / (gram_ms * 1e-3) * 1e-12 / (FP64_PEAK_TFLOPS * world),
+                          'hbm_write_gbs_per_gpu': rows * N * 8 / (gram_ms * 1e-3) * 1e-9, 'hbm_peak_gbs': hbm_peak, 'hbm_peak_source': hbm_src,
                           'flops_per_entry_declared': 2 * DIM + F_TR},
     }
     if world == 1 and not args.no_cpu_baseline:
