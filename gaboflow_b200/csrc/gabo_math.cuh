@@ -11,34 +11,43 @@
 
 namespace gabo {
 
+// Coefficients live in constant memory so that each DFMA takes its constant as a c[bank][offset] operand; as literals
+// they cost two extra UMOV per FMA (ncu: 37 % of the issued instructions of the first version were UMOV/IMAD moves).
+static __constant__ double kAsinC[12] = {
+    0x1.555555555554fp-3, 0x1.3333333336da5p-4, 0x1.6db6db684b6a1p-5, 0x1.f1c71f95269afp-6,
+    0x1.6e8b2b3b10be4p-6, 0x1.1c593c7b1d958p-6, 0x1.c87265d47ef49p-7, 0x1.8522ddffa6208p-7,
+    0x1.ff5fc4d14c735p-8, 0x1.06b9d26d10838p-6, -0x1.603991d6060e0p-7, 0x1.cd864394d2ff2p-6};
+static __constant__ double kExpC[12] = {
+    6755399441055744.0,        // [0] 1.5 * 2^52
+    0x1.71547652b82fep+5,      // [1] 32 / ln2
+    -0x1.62e42fefa0000p-6,     // [2] -ln2/32 hi (36 bits)
+    -0x1.cf79abc9e3b3ap-45,    // [3] -ln2/32 lo
+    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0,   // [4..9] Taylor coefficients of exp on |r| <= ln2/64
+    0x1.921fb54442d18p+0,      // [10] pi/2
+    0x1.921fb54442d18p+1};     // [11] pi
+
 __device__ __forceinline__ double asin_poly(double z) {
-    double p = 0x1.cd864394d2ff2p-6;
-    p = fma(p, z, -0x1.603991d6060e0p-7);
-    p = fma(p, z, 0x1.06b9d26d10838p-6);
-    p = fma(p, z, 0x1.ff5fc4d14c735p-8);
-    p = fma(p, z, 0x1.8522ddffa6208p-7);
-    p = fma(p, z, 0x1.c87265d47ef49p-7);
-    p = fma(p, z, 0x1.1c593c7b1d958p-6);
-    p = fma(p, z, 0x1.6e8b2b3b10be4p-6);
-    p = fma(p, z, 0x1.f1c71f95269afp-6);
-    p = fma(p, z, 0x1.6db6db684b6a1p-5);
-    p = fma(p, z, 0x1.3333333336da5p-4);
-    p = fma(p, z, 0x1.555555555554fp-3);
+    double p = kAsinC[11];
+#pragma unroll
+    for (int i = 10; i >= 0; --i) p = fma(p, z, kAsinC[i]);
     return p * z;
 }
 
-// acos for t already clamped to [-1, 1]
+// acos for t already clamped to [-1, 1].  The |t| > 0.5 path (needs a square root) is entered warp-uniformly so the
+// common case carries no divergence bookkeeping.
 __device__ __forceinline__ double acos_fast(double t) {
     const double a = fabs(t);
-    if (a <= 0.5) {
-        const double w = asin_poly(t * t);
-        return (0x1.921fb54442d18p+0 - t) - t * w;          // pi/2 - asin(t)
-    }
-    const double z = fma(-0.5, a, 0.5);
+    const bool big = a > 0.5;
+    const double z = big ? fma(-0.5, a, 0.5) : t * t;
     const double w = asin_poly(z);
-    const double s = sqrt(z);
-    const double r = fma(s, w, s);
-    return (t > 0.0) ? 2.0 * r : fma(-2.0, r, 0x1.921fb54442d18p+1);
+    double r = (kExpC[10] - t) - t * w;                     // pi/2 - asin(t), valid for |t| <= 0.5
+    if (__any_sync(0xffffffffu, big)) {
+        const double s = sqrt(z);
+        const double h = fma(s, w, s);                      // asin(sqrt((1-|t|)/2))
+        const double rb = (t > 0.0) ? 2.0 * h : fma(-2.0, h, kExpC[11]);
+        r = big ? rb : r;
+    }
+    return r;
 }
 
 // the 32-entry table 2^(j/32); kernels copy it to shared memory once (divergent constant-bank reads would serialise)
@@ -52,25 +61,93 @@ static __constant__ double kExp2Tab[32] = {
     0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
     0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
 
-// exp(x) for x <= 0, `tab` = shared-memory copy of kExp2Tab.  Falls back to libm below -700 (denormal range).
+// exp(x) for x <= 0, `tab` = shared-memory copy of kExp2Tab.  Falls back to libm below -700 (denormal range) or NaN,
+// warp-uniformly.
 __device__ __forceinline__ double exp_neg_fast(double x, const double* __restrict__ tab) {
-    if (!(x > -700.0)) return exp(x);                         // also NaN
-    const double MAGIC = 6755399441055744.0;                  // 1.5 * 2^52
-    const double tn = fma(x, 0x1.71547652b82fep+5, MAGIC);    // x * 32/ln2, rounded to integer in the low bits
+    const double tn = fma(x, kExpC[1], kExpC[0]);             // x * 32/ln2, rounded to integer in the low bits
     const int n = __double2loint(tn);
-    const double nf = tn - MAGIC;
-    double r = fma(nf, -0x1.62e42fefa0000p-6, x);             // ln2/32 split hi (36 bits) + lo
-    r = fma(nf, -0x1.cf79abc9e3b3ap-45, r);
-    double p = 1.0 / 720.0;
-    p = fma(p, r, 1.0 / 120.0);
-    p = fma(p, r, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    const double nf = tn - kExpC[0];
+    double r = fma(nf, kExpC[2], x);
+    r = fma(nf, kExpC[3], r);
+    double p = kExpC[4];
+#pragma unroll
+    for (int i = 5; i <= 9; ++i) p = fma(p, r, kExpC[i]);
+    p = fma(p, r, kExpC[9]);
     const double v = tab[n & 31] * p;
     const int m = n >> 5;                                     // arithmetic shift: floor division
-    return __hiloint2double(__double2hiint(v) + (m << 20), __double2loint(v));
+    double res = __hiloint2double(__double2hiint(v) + (m << 20), __double2loint(v));
+    const bool slow = !(x > -700.0);
+    if (__any_sync(0xffffffffu, slow)) {
+        if (slow) res = exp(x);
+    }
+    return res;
+}
+
+// ---- batched forms: N independent entries, straight-line (the compiler interleaves the N dependency chains), with ONE
+// warp vote per batch for the rare slow paths (a vote per entry is a scheduling barrier and serialises the chains).
+template <int N>
+__device__ __forceinline__ void acos_fast_n(const double (&t)[N], double (&out)[N]) {
+    double z[N], w[N];
+    bool anybig = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double a = fabs(t[i]);
+        const bool big = a > 0.5;
+        anybig = anybig || big;
+        z[i] = big ? fma(-0.5, a, 0.5) : t[i] * t[i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) w[i] = kAsinC[11];
+#pragma unroll
+    for (int c = 10; c >= 0; --c)
+#pragma unroll
+        for (int i = 0; i < N; ++i) w[i] = fma(w[i], z[i], kAsinC[c]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        w[i] *= z[i];
+        out[i] = (kExpC[10] - t[i]) - t[i] * w[i];           // pi/2 - asin(t), valid for |t| <= 0.5
+    }
+    if (__any_sync(0xffffffffu, anybig)) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (fabs(t[i]) > 0.5) {
+                const double s = sqrt(z[i]);
+                const double h = fma(s, w[i], s);
+                out[i] = (t[i] > 0.0) ? 2.0 * h : fma(-2.0, h, kExpC[11]);
+            }
+        }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void exp_neg_fast_n(const double (&x)[N], double (&out)[N], const double* __restrict__ tab) {
+    double r[N], p[N];
+    int n[N];
+    bool anyslow = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double tn = fma(x[i], kExpC[1], kExpC[0]);
+        n[i] = __double2loint(tn);
+        const double nf = tn - kExpC[0];
+        r[i] = fma(nf, kExpC[3], fma(nf, kExpC[2], x[i]));
+        p[i] = kExpC[4];
+        anyslow = anyslow || !(x[i] > -700.0);
+    }
+#pragma unroll
+    for (int c = 5; c <= 9; ++c)
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], kExpC[c]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        p[i] = fma(p[i], r[i], kExpC[9]);
+        const double v = tab[n[i] & 31] * p[i];
+        out[i] = __hiloint2double(__double2hiint(v) + ((n[i] >> 5) << 20), __double2loint(v));
+    }
+    if (__any_sync(0xffffffffu, anyslow)) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (!(x[i] > -700.0)) out[i] = exp(x[i]);
+    }
 }
 
 }  // namespace gabo

@@ -228,13 +228,133 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel(const GramPara
     }
 }
 
+// ---- single-chunk fast path (dim <= KLD, i.e. every configuration of BASELINE.json) -----------------------------------------
+// Same tiling, ring and stores as points_gram_kernel, but each warp walks its 32x32 block one 8-row strip at a time in a
+// ROLLED loop: 4 DMMA accumulators live at once instead of 16, so the epilogue needs no register rotation, indexes nothing
+// dynamically and has 8 independent entries in flight; the B fragments are re-read from shared memory per strip
+// (260 instead of 104 LDS per warp and tile, ~20 % of the shared-memory bandwidth).
+template <int KLD>
+__global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr uint32_t TILE_BYTES = BT * KLD * sizeof(double);
+    constexpr int TILE_DOUBLES = BT * KLD;
+    double* const smem_d = reinterpret_cast<double*>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar[NSTAGE];
+    __shared__ double exptab[32];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&full_bar[s], 1);
+        fence_mbar_init();
+    }
+    if (tid < 32) exptab[tid] = kExp2Tab[tid];
+    __syncthreads();
+
+    const int64_t my_tiles = (p.ntiles > (int64_t)blockIdx.x) ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+    auto issue = [&](int64_t tl) {
+        const int64_t t = (int64_t)blockIdx.x + tl * gridDim.x;
+        int64_t bi, bj;
+        tile_coords(p, t, bi, bj);
+        const int s = (int)(tl & 1);
+        mbar_arrive_expect_tx(&full_bar[s], 2 * TILE_BYTES);
+        tma_bulk_g2s(smem_d + 2 * s * TILE_DOUBLES, p.Ap + (p.tile_r0 + bi) * BT * KLD, TILE_BYTES, &full_bar[s]);
+        tma_bulk_g2s(smem_d + (2 * s + 1) * TILE_DOUBLES, p.Bp + bj * BT * KLD, TILE_BYTES, &full_bar[s]);
+    };
+    if (tid == 0 && my_tiles > 0) issue(0);
+
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+        const int s = (int)(tl & 1);
+        __syncthreads();   // every warp is done with stage s^1 (tile tl-1): refill it while this tile computes
+        if (tid == 0 && tl + 1 < my_tiles) issue(tl + 1);
+        const int64_t t = (int64_t)blockIdx.x + tl * gridDim.x;
+        int64_t bi, bj;
+        tile_coords(p, t, bi, bj);
+        const int64_t grow_tile = (p.tile_r0 + bi) * BT, gcol_tile = bj * BT;
+        const bool mirror = (p.uplo == GABO_SYMM_MIRROR) && (gcol_tile != grow_tile);
+        const bool diag_tile = p.symmetric && (gcol_tile == grow_tile);
+        mbar_wait(&full_bar[s], (uint32_t)((tl >> 1) & 1));
+
+        const double* b_base = smem_d + (2 * s + 1) * TILE_DOUBLES + (wn * 32 + g) * KLD + q;
+        const int64_t gcol0 = gcol_tile + wn * 32 + 2 * q;
+        double nb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nb[j] = 0.0;
+        if (p.kind == GABO_SQDIST_GAUSSIAN) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) { nb[2 * ni] = p.normB[gcol0 + ni * 8]; nb[2 * ni + 1] = p.normB[gcol0 + ni * 8 + 1]; }
+        }
+#pragma unroll 1
+        for (int mi = 0; mi < 4; ++mi) {
+            const double* a_ptr = smem_d + 2 * s * TILE_DOUBLES + (wm * 32 + mi * 8 + g) * KLD + q;
+            double c[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[j] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KLD / 4; ++ks) {
+                const double a = a_ptr[ks * 4];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(c[2 * ni], c[2 * ni + 1], a, b_base[ni * 8 * KLD + ks * 4]);
+            }
+            const int64_t grow = grow_tile + wm * 32 + mi * 8 + g;
+            double na = 0.0;
+            if (p.kind == GABO_SQDIST_GAUSSIAN) na = p.normA[grow];
+            double v[8], arg[8];
+            if (p.kind == GABO_SQDIST_GAUSSIAN) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) arg[j] = -p.beta * fmax(fma(-2.0, c[j], na + nb[j]), 0.0);
+            } else {
+                double tt[8], dd[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tt[j] = fmin(fmax(c[j], -1.0), 1.0);      // sphere_utils_tf.py:59
+                acos_fast_n<8>(tt, dd);                                                // sphere_utils_tf.py:60
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    arg[j] = -p.beta * ((p.kind == GABO_SPHERE_GAUSSIAN) ? dd[j] * dd[j] : dd[j]);   // kernels_sphere_tf.py:83-86, 199-202
+            }
+            exp_neg_fast_n<8>(arg, v, exptab);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= p.variance;                              // kernels_sphere_tf.py:88, 204
+            if (diag_tile) {   // K(X,X) diagonal is exactly `variance` (matches Kdiag, kernels_sphere_tf.py:105)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (gcol0 + (j >> 1) * 8 + (j & 1) == grow) v[j] = p.variance;
+            }
+            if (grow < p.row1) {
+                double* krow = p.K + (grow - p.row0) * p.ldk;
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const int64_t gcol = gcol0 + ni * 8;
+                    if (gcol + 1 < p.n2 && p.vec_ok) {
+                        st_cs_v2(krow + gcol, v[2 * ni], v[2 * ni + 1]);
+                    } else {
+                        if (gcol < p.n2) st_cs(krow + gcol, v[2 * ni]);
+                        if (gcol + 1 < p.n2) st_cs(krow + gcol + 1, v[2 * ni + 1]);
+                    }
+                    if (mirror) {   // K[col][row] = K[row][col]; 8 lanes of equal q write 64 contiguous bytes
+                        st_cs(p.K + gcol * p.ldk + grow, v[2 * ni]);
+                        st_cs(p.K + (gcol + 1) * p.ldk + grow, v[2 * ni + 1]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int KLD>
 int launch_points_gram(const GramParams& p, cudaStream_t stream) {
     constexpr size_t smem = (size_t)NSTAGE * 2 * BT * KLD * sizeof(double);
     GABO_CUDA_TRY(cudaFuncSetAttribute(points_gram_kernel<KLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GABO_CUDA_TRY(cudaFuncSetAttribute(points_gram_kernel_1c<KLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = p.ntiles < (int64_t)sm_count() ? p.ntiles : (int64_t)sm_count();
     if (grid <= 0) return 0;
-    points_gram_kernel<KLD><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
+    if (p.nchunks == 1) points_gram_kernel_1c<KLD><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
+    else points_gram_kernel<KLD><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
     GABO_LAUNCH_CHECK();
     return 0;
 }
