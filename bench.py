@@ -179,11 +179,21 @@ def run_ours(args):
     # N > 1: K is distributed by 512-row panels, 1-D block-cyclic (gaboflow_b200/dist.py): every rank generates the full
     #        rows of its panels with no exchange (X is replicated), then the leading NC x NC block is factored by the
     #        distributed right-looking Cholesky (diagonal-block broadcast + block-column all-gather over NCCL).
-    from gaboflow_b200.dist import (BlockCyclic, potrf_block_cyclic_, solve_lower_block_cyclic_, gp_loglik_block_cyclic)
+    from gaboflow_b200.dist import (BlockCyclic, PeerBuffers, gram_block_cyclic_mirrored, potrf_block_cyclic_,
+                                    solve_lower_block_cyclic_, gp_loglik_block_cyclic)
     PANEL = 512
     lay = BlockCyclic(N, PANEL, world, rank)
     rows = lay.local_rows
-    K = torch.empty((rows, N), dtype=torch.float64, device=dev)
+    # W = 2: symmetry is exploited across the two GPUs (each computes the lower tiles of its panels and stores the mirror
+    # tiles into the peer's HBM over NVLink).  W >= 4: every rank recomputes the full rows of its panels -- measured on
+    # B200, producing an entry on the FP64 pipe (~3 ps) is ~4x cheaper than moving it over NVLink (8 B at ~0.5 TB/s).
+    p2p_mirror = (world == 2 and N % PANEL == 0 and not args.no_p2p)
+    peers = None
+    if p2p_mirror:
+        peers = PeerBuffers(rows, N, dev)
+        K = peers.local
+    else:
+        K = torch.empty((rows, N), dtype=torch.float64, device=dev)
     ws = torch.empty(int(lib.gabo_points_gram_workspace_bytes(N, N, DIM)), dtype=torch.uint8, device=dev)
     grow = lay.global_rows()
     sel_fac = (grow < NC).to(dev)
@@ -207,6 +217,8 @@ def run_ours(args):
             events[0].record()
         if world == 1:
             ops.points_gram(ops.SPHERE_GAUSSIAN, Xd, None, beta=BETA, variance=VARIANCE, out=K, uplo='mirror', workspace=ws)
+        elif p2p_mirror:
+            gram_block_cyclic_mirrored(ops.SPHERE_GAUSSIAN, Xd, lay, peers, BETA, VARIANCE, workspace=ws, sync=True)
         else:
             for pnl in lay.my_panels():
                 sl = lay.slot(pnl) * PANEL
@@ -294,6 +306,9 @@ def run_ours(args):
     launches_all = int(reduce_max(float(launches)))
 
     if rank != 0:
+        if peers is not None:
+            del K
+            peers.close()
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -303,7 +318,7 @@ def run_ours(args):
     value = entries / (gram_ms * 1e-3)
     potrf_s = potrf_ms * 1e-3
     potrf_tflops = (NC ** 3 / 3) / potrf_s * 1e-12 if potrf_s > 0 else None
-    sym = (world == 1)
+    sym = (world == 1) or p2p_mirror
     gram_flops = entries * (2 * DIM + F_TR) * (0.5 if sym else 1.0)    # symmetric tiles are computed once and mirrored
     line = {
         'metric': 'sphere_gram_entries_per_s', 'value': value, 'unit': 'entries/s', 'n_gpus': world, 'steps': args.steps,
@@ -311,8 +326,10 @@ def run_ours(args):
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'sphere Gaussian Gram N={N} on S^50 (D={DIM}) + FP64 Cholesky of K+1e-2 I at N={NC} + solve + loglik',
                    'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2, 'seeds': [SEED_X, SEED_Y],
-                   'gram_mode': 'lower tiles computed once, mirror-stored (full dense K)' if sym else
-                                f'full rows of the dense K in {PANEL}-row panels, 1-D block-cyclic over {world} ranks',
+                   'gram_mode': 'lower tiles computed once, mirror-stored (full dense K)' if world == 1 else
+                                (f'{PANEL}-row panels block-cyclic over {world} ranks; lower tiles computed by the row owner, mirror tiles '
+                                 f'stored into the peer GPU over NVLink from inside the kernel' if p2p_mirror else
+                                 f'full rows of the dense K in {PANEL}-row panels, 1-D block-cyclic over {world} ranks'),
                    'l2': f'no flush: {rows * N * 8 / 1e9:.1f} GB of K per GPU >> 126 MB L2',
                    'parallelism': 'single GPU' if world == 1 else
                                   f'Gram: row panels block-cyclic over {world} ranks, no collective; Cholesky: right-looking over panels, '
@@ -344,6 +361,9 @@ def run_ours(args):
         line['cpu_baseline'] = cpu_reference_sample(N, n_chol_sample=min(args.ref_chol_n, NC), gram_rows=args.ref_gram_rows,
                                                     n_chol_metric=NC)
     print(json.dumps(line), flush=True)
+    if peers is not None:
+        del K
+        peers.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -360,6 +380,7 @@ def main():
     ap.add_argument('--ref-gram-rows', type=int, default=2048)
     ap.add_argument('--ref-chol-n', type=int, default=8192)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-p2p', action='store_true', help='N=2: full rows per rank instead of NVLink-mirrored tiles')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

@@ -1,5 +1,6 @@
 // Small C-ABI entry points that are not kernels of their own: version, device query, status text, Kdiag fill.
 #include <atomic>
+#include <cstring>
 #include "gabo_common.cuh"
 
 namespace gabo {
@@ -49,5 +50,55 @@ extern "C" int gabo_kdiag_const_f64(int64_t n, double variance, double* out, gab
     if (out == nullptr) return -3;
     gabo::fill_kernel<<<(unsigned)gabo::ceil_div64(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, variance);
     GABO_LAUNCH_CHECK();
+    return 0;
+}
+
+// Lets kernels on the current device dereference memory of `peer_device` (needed before gabo_points_gram_cyclic_f64 when the
+// peer buffers were opened through CUDA IPC under the exporter's device).  "Already enabled" is not an error.
+extern "C" int gabo_enable_peer_access(int peer_device) {
+    int dev = 0, can = 0;
+    GABO_CUDA_TRY(cudaGetDevice(&dev));
+    if (peer_device == dev) return 0;
+    GABO_CUDA_TRY(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) return -1;
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) return GABO_ERR_CUDA - (int)e;
+    return 0;
+}
+
+// ---- peer-shared buffers (multi-GPU mirrored Gram): plain cudaMalloc so that the allocation base can be exported with
+// CUDA IPC, and opened by the other ranks ON THEIR OWN DEVICE with lazy peer access, which is what makes kernel stores
+// from that device into this memory legal.
+extern "C" int gabo_shared_alloc(size_t bytes, void** out) {
+    if (out == nullptr) return -2;
+    *out = nullptr;
+    if (bytes == 0) return 0;
+    GABO_CUDA_TRY(cudaMalloc(out, bytes));
+    return 0;
+}
+extern "C" int gabo_shared_free(void* ptr) {
+    if (ptr != nullptr) GABO_CUDA_TRY(cudaFree(ptr));
+    return 0;
+}
+extern "C" int gabo_ipc_export(void* ptr, unsigned char* handle64) {
+    if (ptr == nullptr) return -1;
+    if (handle64 == nullptr) return -2;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    GABO_CUDA_TRY(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+extern "C" int gabo_ipc_open(const unsigned char* handle64, void** out) {
+    if (handle64 == nullptr) return -1;
+    if (out == nullptr) return -2;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    GABO_CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int gabo_ipc_close(void* ptr) {
+    if (ptr != nullptr) GABO_CUDA_TRY(cudaIpcCloseMemHandle(ptr));
     return 0;
 }

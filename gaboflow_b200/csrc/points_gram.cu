@@ -45,7 +45,32 @@ struct GramParams {
     double beta, variance;
     int64_t tile_r0;       // row0 / BT
     int64_t tiles_m, tiles_n, ntiles;
+    // block-cyclic multi-GPU mode (points_gram_kernel_1c<KLD, true>): row panels of CYC_PT tiles, panel P lives on rank
+    // P % cyc_world in local slot P / cyc_world; peer[r] = base of rank r's local [local_rows, ldk] buffer (peer[cyc_rank]
+    // is this GPU's own buffer, the others are NVLink peer mappings)
+    int cyc_world, cyc_rank;
+    double* peer[8];
 };
+
+constexpr int CYC_PT = 4;   // tiles per 512-row panel
+
+// u-th lower tile owned by this rank -> local row tile lt, global row tile gbi, column tile bj.
+// Tiles before local slot s: C(s) = 8 W s (s-1) + (16 rank + 10) s   (rows of global panel s W + rank own 4P+1 .. 4P+4 tiles).
+__device__ __forceinline__ void cyclic_tile_coords(const GramParams& p, int64_t u, int64_t& lt, int64_t& gbi, int64_t& bj) {
+    const double W = (double)p.cyc_world, b = 16.0 * p.cyc_rank + 10.0 - 8.0 * W;
+    int64_t s = (int64_t)floor((-b + sqrt(b * b + 32.0 * W * (double)u)) / (16.0 * W));
+    if (s < 0) s = 0;
+    auto C = [&](int64_t x) { return 8 * (int64_t)p.cyc_world * x * (x - 1) + (16 * (int64_t)p.cyc_rank + 10) * x; };
+    while (C(s) > u) --s;
+    while (C(s + 1) <= u) ++s;
+    int64_t rem = u - C(s);
+    const int64_t g0 = (s * p.cyc_world + p.cyc_rank) * CYC_PT;   // first global row tile of the panel
+    int rr = 0;
+    while (rem >= g0 + rr + 1) { rem -= g0 + rr + 1; ++rr; }
+    lt = s * CYC_PT + rr;
+    gbi = g0 + rr;
+    bj = rem;
+}
 
 // ---- packing -----------------------------------------------------------------------------------------
 template <int KLD, typename Tin>
@@ -233,7 +258,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel(const GramPara
 // ROLLED loop: 4 DMMA accumulators live at once instead of 16, so the epilogue needs no register rotation, indexes nothing
 // dynamically and has 8 independent entries in flight; the B fragments are re-read from shared memory per strip
 // (260 instead of 104 LDS per warp and tile, ~20 % of the shared-memory bandwidth).
-template <int KLD>
+template <int KLD, bool CYC>
 __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr uint32_t TILE_BYTES = BT * KLD * sizeof(double);
@@ -259,11 +284,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
 
     auto issue = [&](int64_t tl) {
         const int64_t t = (int64_t)blockIdx.x + tl * gridDim.x;
-        int64_t bi, bj;
-        tile_coords(p, t, bi, bj);
+        int64_t bi, bj, gbi;
+        if (CYC) cyclic_tile_coords(p, t, bi, gbi, bj);
+        else { tile_coords(p, t, bi, bj); gbi = p.tile_r0 + bi; }
         const int s = (int)(tl & 1);
         mbar_arrive_expect_tx(&full_bar[s], 2 * TILE_BYTES);
-        tma_bulk_g2s(smem_d + 2 * s * TILE_DOUBLES, p.Ap + (p.tile_r0 + bi) * BT * KLD, TILE_BYTES, &full_bar[s]);
+        tma_bulk_g2s(smem_d + 2 * s * TILE_DOUBLES, p.Ap + gbi * BT * KLD, TILE_BYTES, &full_bar[s]);
         tma_bulk_g2s(smem_d + (2 * s + 1) * TILE_DOUBLES, p.Bp + bj * BT * KLD, TILE_BYTES, &full_bar[s]);
     };
     if (tid == 0 && my_tiles > 0) issue(0);
@@ -273,11 +299,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
         __syncthreads();   // every warp is done with stage s^1 (tile tl-1): refill it while this tile computes
         if (tid == 0 && tl + 1 < my_tiles) issue(tl + 1);
         const int64_t t = (int64_t)blockIdx.x + tl * gridDim.x;
-        int64_t bi, bj;
-        tile_coords(p, t, bi, bj);
-        const int64_t grow_tile = (p.tile_r0 + bi) * BT, gcol_tile = bj * BT;
+        int64_t bi, bj, gbi;
+        if (CYC) cyclic_tile_coords(p, t, bi, gbi, bj);
+        else { tile_coords(p, t, bi, bj); gbi = p.tile_r0 + bi; }
+        const int64_t grow_tile = gbi * BT, gcol_tile = bj * BT;
         const bool mirror = (p.uplo == GABO_SYMM_MIRROR) && (gcol_tile != grow_tile);
         const bool diag_tile = p.symmetric && (gcol_tile == grow_tile);
+        // where the tile and its mirror image are stored: rows of K are local rows of this rank (CYC: local row tile bi),
+        // the mirror image belongs to the rank that owns global row panel bj / CYC_PT
+        const int64_t lrow_tile = CYC ? bi * BT : grow_tile - p.row0;
+        double* kmir_base = p.K;
+        if (CYC) {
+            const int64_t pj = bj / CYC_PT;
+            kmir_base = p.peer[pj % p.cyc_world] + ((pj / p.cyc_world) * CYC_PT + (bj % CYC_PT)) * BT * p.ldk;
+        } else {
+            kmir_base = p.K + gcol_tile * p.ldk;
+        }
         mbar_wait(&full_bar[s], (uint32_t)((tl >> 1) & 1));
 
         const double* b_base = smem_d + (2 * s + 1) * TILE_DOUBLES + (wn * 32 + g) * KLD + q;
@@ -326,7 +363,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
                     if (gcol0 + (j >> 1) * 8 + (j & 1) == grow) v[j] = p.variance;
             }
             if (grow < p.row1) {
-                double* krow = p.K + (grow - p.row0) * p.ldk;
+                double* krow = p.K + (lrow_tile + wm * 32 + mi * 8 + g) * p.ldk;
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) {
                     const int64_t gcol = gcol0 + ni * 8;
@@ -336,9 +373,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
                         if (gcol < p.n2) st_cs(krow + gcol, v[2 * ni]);
                         if (gcol + 1 < p.n2) st_cs(krow + gcol + 1, v[2 * ni + 1]);
                     }
-                    if (mirror) {   // K[col][row] = K[row][col]; 8 lanes of equal q write 64 contiguous bytes
-                        st_cs(p.K + gcol * p.ldk + grow, v[2 * ni]);
-                        st_cs(p.K + (gcol + 1) * p.ldk + grow, v[2 * ni + 1]);
+                    if (mirror) {   // K[col][row] = K[row][col]; 8 lanes of equal q write 64 contiguous bytes (own HBM or a peer's over NVLink)
+                        double* km = kmir_base + (int64_t)(wn * 32 + ni * 8 + 2 * q) * p.ldk + grow;
+                        st_cs(km, v[2 * ni]);
+                        st_cs(km + p.ldk, v[2 * ni + 1]);
                     }
                 }
             }
@@ -350,10 +388,12 @@ template <int KLD>
 int launch_points_gram(const GramParams& p, cudaStream_t stream) {
     constexpr size_t smem = (size_t)NSTAGE * 2 * BT * KLD * sizeof(double);
     GABO_CUDA_TRY(cudaFuncSetAttribute(points_gram_kernel<KLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GABO_CUDA_TRY(cudaFuncSetAttribute(points_gram_kernel_1c<KLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GABO_CUDA_TRY(cudaFuncSetAttribute(points_gram_kernel_1c<KLD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GABO_CUDA_TRY(cudaFuncSetAttribute(points_gram_kernel_1c<KLD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = p.ntiles < (int64_t)sm_count() ? p.ntiles : (int64_t)sm_count();
     if (grid <= 0) return 0;
-    if (p.nchunks == 1) points_gram_kernel_1c<KLD><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
+    if (p.cyc_world > 0) points_gram_kernel_1c<KLD, true><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
+    else if (p.nchunks == 1) points_gram_kernel_1c<KLD, false><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
     else points_gram_kernel<KLD><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
     GABO_LAUNCH_CHECK();
     return 0;
@@ -447,6 +487,8 @@ int points_gram_impl(int kind, const Tin* X, int64_t n1, int64_t ldx, const Tin*
     p.symmetric = symmetric ? 1 : 0;
     p.vec_ok = ((ldk % 2) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0) ? 1 : 0;
     p.beta = beta; p.variance = variance;
+    p.cyc_world = 0; p.cyc_rank = 0;
+    for (int r = 0; r < 8; ++r) p.peer[r] = nullptr;
     p.tile_r0 = row0 / BT;
     p.tiles_m = ceil_div64(row1 - row0, BT);
     p.tiles_n = ceil_div64(n2, BT);
@@ -471,4 +513,53 @@ extern "C" int gabo_points_gram_f64(int kind, const double* X, int64_t n1, int64
                                     gabo_stream_t stream) {
     return gabo::points_gram_impl<double>(kind, X, n1, ldx, X2, n2, ldx2, dim, beta, variance, K, ldk, row0, row1, uplo,
                                           workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// Multi-GPU symmetric Gram, 1-D block-cyclic over 512-row panels, symmetry exploited ACROSS GPUs: this rank computes the
+// lower tiles of the row panels it owns, stores them into its own buffer and stores each off-diagonal tile's mirror image
+// straight into the HBM of the rank that owns that row panel (peer mappings over NVLink / NVSwitch; no collective).
+// K_bases_host: `world` device pointers (host array): base of every rank's [local_rows, ldk] buffer as mapped in THIS process.
+// After the call + a stream sync + a barrier across ranks, every rank holds the full dense rows of its panels.
+extern "C" int gabo_points_gram_cyclic_f64(int kind, const double* X, int64_t n, int64_t ldx, int dim, double beta,
+                                           double variance, double* const* K_bases_host, int64_t ldk, int world, int rank,
+                                           void* workspace, size_t workspace_bytes, gabo_stream_t stream_) {
+    using namespace gabo;
+    if (kind < GABO_SPHERE_GAUSSIAN || kind > GABO_SQDIST_GAUSSIAN) return -1;
+    if (n < 0) return -3;
+    if (n == 0) return 0;
+    if (X == nullptr) return -2;
+    if (ldx < dim) return -4;
+    if (dim < 1 || dim > 52) return -5;               // single-chunk kernel only
+    if (K_bases_host == nullptr) return -8;
+    if (ldk < n) return -9;
+    if (world < 1 || world > 8) return -10;
+    if (rank < 0 || rank >= world) return -11;
+    if (n % (BT * CYC_PT) != 0) return -3;            // whole 512-row panels only
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PackPlan pl = make_plan(n, n, dim);
+    const size_t need = pl.bytesA + pl.bytesNorm1;
+    if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return -12;
+    if (workspace_bytes < need) return -13;
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    double* Ap = reinterpret_cast<double*>(ws);
+    double* nA = reinterpret_cast<double*>(ws + pl.bytesA);
+    const bool want_norm = (kind == GABO_SQDIST_GAUSSIAN);
+    int rc = pack_dispatch<double>(pl.kld, X, n, ldx, dim, Ap, pl.n1_pad, pl.nchunks, want_norm ? nA : nullptr, stream);
+    if (rc) return rc;
+    const int64_t npanels = n / (BT * CYC_PT);
+    const int64_t nslots = (npanels > rank) ? (npanels - 1 - rank) / world + 1 : 0;
+    GramParams p;
+    p.Ap = Ap; p.Bp = Ap; p.normA = want_norm ? nA : nullptr; p.normB = p.normA;
+    p.K = K_bases_host[rank]; p.ldk = ldk; p.n1_pad = pl.n1_pad; p.n2_pad = pl.n2_pad;
+    p.row0 = 0; p.row1 = n; p.n2 = n; p.nchunks = 1; p.kind = kind; p.uplo = GABO_SYMM_MIRROR; p.symmetric = 1;
+    p.vec_ok = ((ldk % 2) == 0 && (reinterpret_cast<uintptr_t>(p.K) & 15) == 0) ? 1 : 0;
+    p.beta = beta; p.variance = variance;
+    p.tile_r0 = 0; p.tiles_m = nslots * CYC_PT; p.tiles_n = n / BT;
+    p.cyc_world = world; p.cyc_rank = rank;
+    for (int r = 0; r < 8; ++r) p.peer[r] = (r < world) ? K_bases_host[r] : nullptr;
+    p.ntiles = 8 * (int64_t)world * nslots * (nslots - 1) + (16 * (int64_t)rank + 10) * nslots;
+    if (p.K == nullptr) return -8;
+    if (pl.kld == 4) return launch_points_gram<4>(p, stream);
+    if (pl.kld == 20) return launch_points_gram<20>(p, stream);
+    return launch_points_gram<52>(p, stream);
 }

@@ -221,3 +221,77 @@ def gp_loglik_block_cyclic(A_loc: torch.Tensor, V_loc: torch.Tensor, layout: Blo
     if W > 1:
         dist.all_reduce(acc, group=group)
     return float(acc.item())
+
+
+# ---- peer-memory plumbing for the NVLink-mirrored Gram -----------------------------------------------------------------
+class _RawCudaArray:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can view it without copying."""
+
+    def __init__(self, ptr, shape, typestr='<f8'):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False), 'version': 2}
+
+
+class PeerBuffers:
+    """One [rows, cols] FP64 buffer per rank, allocated with cudaMalloc through the C-ABI, exported with CUDA IPC and opened
+    by every other rank of the node on its own device with lazy peer access.  `local` is this rank's buffer as a torch
+    tensor (no copy); `ptrs[r]` is the device pointer of rank r's buffer in THIS process."""
+
+    def __init__(self, rows: int, cols: int, device, group=None):
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        self._L = L
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = torch.device(device)
+        self._opened = []
+        with torch.cuda.device(self.device):
+            p = C.c_void_p()
+            _lib.check('gabo_shared_alloc', L.gabo_shared_alloc(max(rows * cols * 8, 8), C.byref(p)))
+            self._base = p.value
+            self.local = torch.as_tensor(_RawCudaArray(self._base, (rows, cols)), device=self.device)
+            self.ptrs = [None] * self.world
+            self.ptrs[self.rank] = self._base
+            if self.world > 1:
+                hbuf = C.create_string_buffer(64)
+                _lib.check('gabo_ipc_export', L.gabo_ipc_export(self._base, hbuf))
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(hbuf.raw), group=group)
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        continue
+                    q = C.c_void_p()
+                    _lib.check('gabo_ipc_open', L.gabo_ipc_open(h, C.byref(q)))
+                    self.ptrs[r] = q.value
+                    self._opened.append(q.value)
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=group)
+
+    def close(self, group=None):
+        """Unmap the peers' buffers, then free the local one (collective: every rank must have unmapped first)."""
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for q in self._opened:
+                self._L.gabo_ipc_close(q)
+            self._opened = []
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=group)
+            self.local = None
+            if self._base:
+                self._L.gabo_shared_free(self._base)
+                self._base = None
+
+
+def gram_block_cyclic_mirrored(kind: int, X: torch.Tensor, layout: BlockCyclic, peers: PeerBuffers, beta: float,
+                               variance: float, workspace=None, group=None, sync: bool = True) -> torch.Tensor:
+    """Symmetric Gram K(X,X) into the block-cyclic row panels of all ranks: each rank computes the lower tiles of its own
+    panels once and writes their mirror images into the owning peers' memory from inside the kernel."""
+    from . import ops
+    if layout.nb != 512:
+        raise ValueError('the mirrored Gram uses 512-row panels')
+    ops.points_gram_cyclic(kind, X, peers.ptrs, int(peers.local.stride(0)), layout.world, layout.rank, beta, variance, workspace)
+    if sync:
+        torch.cuda.synchronize(X.device)
+        if layout.world > 1:
+            dist.barrier(group=group)      # remote mirror stores of every rank have landed
+    return peers.local

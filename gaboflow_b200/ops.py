@@ -302,3 +302,21 @@ def solve_update_(Y: torch.Tensor, Lp: torch.Tensor, X: torch.Tensor) -> torch.T
     st = _lib.lib().gabo_solve_update_f64(m, k, nrhs, Lp.data_ptr(), _ldm(Lp), X.data_ptr(), _ldm(X), Y.data_ptr(), _ldm(Y), _stream())
     _lib.check('gabo_solve_update_f64', st)
     return Y
+
+
+def points_gram_cyclic(kind: int, X: torch.Tensor, bases, ldk: int, world: int, rank: int, beta: float = 1.0,
+                       variance: float = 1.0, workspace: Optional[torch.Tensor] = None) -> None:
+    """Block-cyclic symmetric Gram with peer-memory mirror stores (gabo_points_gram_cyclic_f64).  `bases`: list of `world`
+    device pointers (ints), entry r = base of rank r's local buffer as mapped in this process."""
+    import ctypes as C
+    L = _lib.lib()
+    X = _rowmajor2d(_req(X, 'X'))
+    n, dim = int(X.shape[0]), int(X.shape[1])
+    nbytes = int(L.gabo_points_gram_workspace_bytes(n, n, dim))
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=X.device)
+    arr = (C.c_void_p * world)(*[C.c_void_p(int(b)) for b in bases])
+    st = L.gabo_points_gram_cyclic_f64(int(kind), X.data_ptr(), n, _ld(X), dim, float(beta), float(variance),
+                                       C.cast(arr, C.c_void_p), int(ldk), int(world), int(rank),
+                                       workspace.data_ptr(), workspace.numel(), _stream())
+    _lib.check('gabo_points_gram_cyclic_f64', st)

@@ -154,7 +154,28 @@ int gabo_gemm_nt_sub_f64(int64_t m, int64_t n, int64_t k, const double* A, int64
  * The host side (gaboflow_b200/dist.py) broadcasts the factored diagonal block and all-gathers the panel over NCCL;
  * these calls do the local work of each rank.
  * gabo_trsm_right_f64: A[m, nb] <- A * L^-T, L lower nb x nb (panel rows owned by this rank). */
+/* Enables loads/stores from kernels on the current device to memory of `peer_device` (cudaDeviceEnablePeerAccess);
+ * returns -1 if the two devices have no peer path. */
+int gabo_enable_peer_access(int peer_device);
+/* Peer-shared buffers for gabo_points_gram_cyclic_f64: cudaMalloc'd on the current device (gabo_shared_alloc/free),
+ * exported as a 64-byte CUDA IPC handle (gabo_ipc_export) and opened by the other ranks of the node on THEIR device
+ * with lazy peer access (gabo_ipc_open / gabo_ipc_close), so that kernels there may store into it over NVLink. */
+int gabo_shared_alloc(size_t bytes, void** out);
+int gabo_shared_free(void* ptr);
+int gabo_ipc_export(void* ptr, unsigned char* handle64);
+int gabo_ipc_open(const unsigned char* handle64, void** out);
+int gabo_ipc_close(void* ptr);
 size_t gabo_trsm_right_workspace_bytes(int64_t nb);
+/* gabo_points_gram_cyclic_f64: symmetric Gram K(X,X) distributed by 512-row panels, 1-D block-cyclic (panel P on rank
+ *   P % world, local slot P / world), with the symmetry exploited ACROSS GPUs: this rank computes only the lower tiles
+ *   of its own row panels and stores every off-diagonal tile's mirror image directly into the HBM of the rank owning
+ *   that row panel (peer-mapped pointers over NVLink/NVSwitch; the transfer overlaps the tile math, no collective).
+ *   K_bases_host: HOST array of `world` device pointers, entry r = base of rank r's [local_rows, ldk] buffer as mapped
+ *   in this process (entry `rank` is the local buffer; the others come from cudaIpcOpenMemHandle).  n must be a multiple
+ *   of 512, dim <= 52.  Callers synchronise the stream and barrier across ranks before reading their rows. */
+int gabo_points_gram_cyclic_f64(int kind, const double* X, int64_t n, int64_t ldx, int dim, double beta, double variance,
+                                double* const* K_bases_host, int64_t ldk, int world, int rank,
+                                void* workspace, size_t workspace_bytes, gabo_stream_t stream);
 int gabo_trsm_right_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, double* A, int64_t lda,
                         void* workspace, size_t workspace_bytes, gabo_stream_t stream);
 /* gabo_syrk_cyclic_f64: C[m,n] -= A[m,k] B[n,k]^T restricted to GLOBAL col <= GLOBAL row, where local row r of C is

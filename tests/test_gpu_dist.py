@@ -67,3 +67,24 @@ def test_block_cyclic_driver_world1(cuda):
     ll = gp_loglik_block_cyclic(A, V, lay, n_factor=1024)
     ref = orc.gp_loglik(orc.sphere_gaussian_K(X[:1024], beta=2.0), y[:1024], 1e-2)
     assert abs(ll / ref - 1) < 1e-8
+
+
+@pytest.mark.parametrize('world', [1, 2, 3])
+def test_cyclic_mirrored_gram_single_process(cuda, world):
+    """gabo_points_gram_cyclic_f64 with all `world` ranks emulated on one GPU (every 'peer' buffer is local memory):
+    same kernel and addressing as the NVLink run, launched once per rank."""
+    from gaboflow_b200 import ops
+    from gaboflow_b200.dist import BlockCyclic
+    from oracle import gabo_oracle as orc
+    n = 512 * 5
+    X = torch.from_numpy(orc.synth_sphere(n, 51, seed=8)).cuda()
+    lays = [BlockCyclic(n, 512, world, r) for r in range(world)]
+    bufs = [torch.full((l.local_rows, n), float('nan'), dtype=torch.float64, device='cuda') for l in lays]
+    ptrs = [b.data_ptr() for b in bufs]
+    for r in range(world):
+        ops.points_gram_cyclic(ops.SPHERE_GAUSSIAN, X, ptrs, n, world, r, beta=2.0, variance=1.0)
+    torch.cuda.synchronize()
+    full = ops.points_gram(ops.SPHERE_GAUSSIAN, X, None, beta=2.0, uplo='mirror')
+    for r in range(world):
+        rows = lays[r].global_rows().cuda()
+        assert torch.equal(bufs[r], full[rows])
