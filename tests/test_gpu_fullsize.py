@@ -60,9 +60,9 @@ def test_cholesky_n32768_properties(cuda):
     for _ in range(6):
         bi, bj = sorted(rng.integers(0, N // 512, 2).tolist(), reverse=True)
         i0, j0 = bi * 512, bj * 512
-        Li = torch.tril(L[i0:i0 + 512, :i0 + 512])
-        Lj = torch.tril(L[j0:j0 + 512, :j0 + 512])
-        prod = Li[:, :j0 + 512] @ Lj.t()
+        Li = torch.tril(L[i0:i0 + 512, :j0 + 512], diagonal=i0)      # rows of L, masked at the GLOBAL diagonal
+        Lj = torch.tril(L[j0:j0 + 512, :j0 + 512], diagonal=j0)
+        prod = Li @ Lj.t()
         ref = K[i0:i0 + 512, j0:j0 + 512].clone()
         if bi == bj:
             ref.diagonal().add_(1e-2)
