@@ -117,63 +117,70 @@ __device__ __forceinline__ int warp_chol16_inv(double (&a)[BS], double (&w)[BS],
     return bad;
 }
 
-constexpr int DLD = 20;   // leading dimension of the 16-wide scratch blocks (4 mod 16)
-constexpr size_t POTF2V2_SMEM = (size_t)(NB_IN * WLD + NB_IN * DLD + NB_IN * DLD) * sizeof(double);   // 176,128
+constexpr int DLD = 20;   // leading dimension of every 16-wide block in shared memory (4 mod 16: conflict-free fragments)
+constexpr int BLKD = BS * DLD;                         // doubles per 16x16 block
+constexpr int NLOWBLK = NBLK * (NBLK + 1) / 2;         // 36 lower blocks
+// Footprint kept under 135 KB and 128 registers so that this CTA can run beside one resident trailing-update CTA
+// (92 KB, 31k registers): that is what lets the look-ahead panel overlap the big update (gabo_potrf_f64).
+constexpr size_t POTF2V2_SMEM = (size_t)(NLOWBLK * BLKD + NB_IN * DLD + NB_IN * DLD) * sizeof(double);   // 133,120
+
+__device__ __forceinline__ int lowblk(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * BLKD; }   // bj <= bi
 
 // ---- diagonal block: L11 = chol(A11 + sigma2 I) in place; Winv = inv(L11) (dense [128][128], zero above) ---------------
 // Blocked by 16 inside one CTA (8 warps): warp 0 factors and inverts each 16x16 diagonal block in registers; the panel
 // below it (x inv^T), the trailing update and the assembly of the 128x128 inverse run on DMMA from shared memory.
-__global__ void __launch_bounds__(256, 1) potf2_inv_kernel(double* __restrict__ A, int64_t lda, int jb, double sigma2,
+// Shared memory holds only the 36 lower 16x16 blocks (block (bi,bj) at lowblk(bi,bj), rows of 20 doubles).
+__global__ void __launch_bounds__(256, 2) potf2_inv_kernel(double* __restrict__ A, int64_t lda, int jb, double sigma2,
                                                            double* __restrict__ Winv, int32_t* __restrict__ info,
                                                            int info_base) {
     extern __shared__ __align__(16) double sm_potf2[];
-    double* S = sm_potf2;                      // [128][132] the block (lower part); its strictly-lower blocks become the inverse
-    double* Dv = sm_potf2 + NB_IN * WLD;       // [8][16][20] inverses of the diagonal 16x16 blocks, row-major
+    double* S = sm_potf2;                      // lower blocks of the matrix; strictly-lower blocks become the inverse
+    double* Dv = sm_potf2 + NLOWBLK * BLKD;    // [128][20] inverses of the diagonal 16x16 blocks, row-major
     double* Y = Dv + NB_IN * DLD;              // [112][20] scratch of the inverse assembly
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
     for (int e = tid; e < NB_IN * NB_IN; e += 256) {
         const int r = e >> 7, c = e & 127;
+        if ((c >> 4) > (r >> 4)) continue;     // block above the diagonal: not stored
         double v = 0.0;
         if (r < jb && c <= r) v = A[(int64_t)r * lda + c];
         if (r == c) v = (r < jb) ? v + sigma2 : 1.0;   // identity padding keeps the inverse well defined
-        S[r * WLD + c] = v;
+        S[lowblk(r >> 4, c >> 4) + (r & 15) * DLD + (c & 15)] = v;
     }
     __syncthreads();
 #pragma unroll 1
     for (int kb = 0; kb < NBLK; ++kb) {
-        const int o = kb * BS;
+        double* Dk = S + lowblk(kb, kb);
         if (warp == 0) {
             double a[BS], w[BS];
             const int ln = lane & (BS - 1);
 #pragma unroll
-            for (int k = 0; k < BS; ++k) a[k] = (k <= ln) ? S[(o + ln) * WLD + o + k] : 0.0;
+            for (int k = 0; k < BS; ++k) a[k] = (k <= ln) ? Dk[ln * DLD + k] : 0.0;
             const int bad = warp_chol16_inv(a, w, lane);
-            if (bad != 0 && o + bad <= jb && lane == 0) atomicCAS(info, 0, info_base + o + bad);
+            if (bad != 0 && kb * BS + bad <= jb && lane == 0) atomicCAS(info, 0, info_base + kb * BS + bad);
             if (lane < BS) {
 #pragma unroll
                 for (int k = 0; k < BS; ++k) {
-                    if (k <= lane) S[(o + lane) * WLD + o + k] = a[k];
-                    Dv[(o + k) * DLD + lane] = w[k];            // W[k][lane]
+                    if (k <= lane) Dk[lane * DLD + k] = a[k];
+                    Dv[(kb * BS + k) * DLD + lane] = w[k];            // W[k][lane]
                 }
             }
         }
         __syncthreads();
-        // panel: rows below, 8-row strips; X = A_strip * W_kk^T.  A strip reads only its own rows: no cross-warp hazard.
-        const int nstrips = (NB_IN - o - BS) / 8;
+        // panel: 8-row strips of the blocks below; X = A_strip * W_kk^T.  A strip reads only its own rows.
+        const int nstrips = (NBLK - 1 - kb) * 2;
         for (int st = warp; st < nstrips; st += 8) {
-            const double* Ar = S + (o + BS + st * 8 + g) * WLD + o + q;
+            double* Ar = S + lowblk(kb + 1 + (st >> 1), kb) + ((st & 1) * 8 + g) * DLD;
             double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
             for (int ks = 0; ks < BS / 4; ++ks) {
-                const double av = Ar[ks * 4];
+                const double av = Ar[ks * 4 + q];
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) dmma884(c[ni][0], c[ni][1], av, Dv[(o + ni * 8 + g) * DLD + ks * 4 + q]);
+                for (int ni = 0; ni < 2; ++ni) dmma884(c[ni][0], c[ni][1], av, Dv[(kb * BS + ni * 8 + g) * DLD + ks * 4 + q]);
             }
             __syncwarp();
-            double* Xr = S + (o + BS + st * 8 + g) * WLD + o + 2 * q;
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni) { Xr[ni * 8] = c[ni][0]; Xr[ni * 8 + 1] = c[ni][1]; }
+            for (int ni = 0; ni < 2; ++ni) { Ar[ni * 8 + 2 * q] = c[ni][0]; Ar[ni * 8 + 2 * q + 1] = c[ni][1]; }
         }
         __syncthreads();
         // trailing update of the lower part: S[i][j] -= sum_k S[i][o+k] S[j][o+k]; 8x8 tiles dealt round-robin to warps
@@ -183,12 +190,13 @@ __global__ void __launch_bounds__(256, 1) potf2_inv_kernel(double* __restrict__ 
             while (st * (st + 1) / 2 > t) --st;
             while ((st + 1) * (st + 2) / 2 <= t) ++st;
             const int ct = t - st * (st + 1) / 2;
-            const double* Ar = S + (o + BS + st * 8 + g) * WLD + o + q;
-            const double* Br = S + (o + BS + ct * 8 + g) * WLD + o + q;
+            const int bi = kb + 1 + (st >> 1), bj = kb + 1 + (ct >> 1);
+            const double* Ar = S + lowblk(bi, kb) + ((st & 1) * 8 + g) * DLD + q;
+            const double* Br = S + lowblk(bj, kb) + ((ct & 1) * 8 + g) * DLD + q;
             double u0 = 0.0, u1 = 0.0;
 #pragma unroll
             for (int ks = 0; ks < BS / 4; ++ks) dmma884(u0, u1, Ar[ks * 4], Br[ks * 4]);
-            double* Cr = S + (o + BS + st * 8 + g) * WLD + o + BS + ct * 8 + 2 * q;
+            double* Cr = S + lowblk(bi, bj) + ((st & 1) * 8 + g) * DLD + (ct & 1) * 8 + 2 * q;
             Cr[0] -= u0;
             Cr[1] -= u1;
         }
@@ -197,56 +205,64 @@ __global__ void __launch_bounds__(256, 1) potf2_inv_kernel(double* __restrict__ 
     // the factor goes back to global memory before its off-diagonal blocks are overwritten by the inverse
     for (int e = tid; e < jb * jb; e += 256) {
         const int r = e / jb, c = e - r * jb;
-        if (c <= r) A[(int64_t)r * lda + c] = S[r * WLD + c];
+        if (c <= r) A[(int64_t)r * lda + c] = S[lowblk(r >> 4, c >> 4) + (r & 15) * DLD + (c & 15)];
     }
     __syncthreads();
-    // inverse, block columns right to left: W[j+1:, j] = -W[j+1:, j+1:] * (L[j+1:, j] * W_jj).  Column j of S still holds L,
+    // inverse, block columns right to left: W[j+1:, j] = -W[j+1:, j+1:] * (L[j+1:, j] * W_jj).  Block column j still holds L,
     // everything to its right already holds W, so both products have no sequential block dependency.
 #pragma unroll 1
     for (int j = NBLK - 2; j >= 0; --j) {
-        const int o = j * BS, r1 = o + BS, nstr = (NB_IN - r1) / 8;
-        // Y = L[r1:, o:o+16] * W_jj   (W_jj read as [k][n])
+        const int nstr = (NBLK - 1 - j) * 2;
+        // Y = L[j+1:, j] * W_jj   (W_jj read as [k][n])
         for (int st = warp; st < nstr; st += 8) {
-            const double* Ar = S + (r1 + st * 8 + g) * WLD + o + q;
+            const double* Ar = S + lowblk(j + 1 + (st >> 1), j) + ((st & 1) * 8 + g) * DLD + q;
             double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
             for (int ks = 0; ks < BS / 4; ++ks) {
                 const double av = Ar[ks * 4];
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) dmma884(c[ni][0], c[ni][1], av, Dv[(o + ks * 4 + q) * DLD + ni * 8 + g]);
+                for (int ni = 0; ni < 2; ++ni) dmma884(c[ni][0], c[ni][1], av, Dv[(j * BS + ks * 4 + q) * DLD + ni * 8 + g]);
             }
             double* Yr = Y + (st * 8 + g) * DLD + 2 * q;
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni) { Yr[ni * 8] = c[ni][0]; Yr[ni * 8 + 1] = c[ni][1]; }
         }
         __syncthreads();
-        // W[r1 + r, o + c] = -sum_{k <= r} Wt[r][k] Y[k][c];  Wt = inverse of the trailing block (diagonal blocks from Dv)
+        // W[j+1+.., j] = -sum_{k <= r} Wt[r][k] Y[k][:];  Wt = inverse of the trailing block (diagonal blocks from Dv)
         for (int st = warp; st < nstr; st += 8) {
-            const int rr = st * 8;                      // first row of the strip inside the trailing block
+            const int bi = j + 1 + (st >> 1), rl = (st & 1) * 8 + g;     // block row, row inside the block
             double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-            const int kdiag = (rr / BS) * BS;           // start of the diagonal block this strip belongs to
-            for (int k0 = 0; k0 < kdiag; k0 += 4) {     // strictly-lower part: from S
-                const double av = S[(r1 + rr + g) * WLD + r1 + k0 + q];
+            for (int bk = j + 1; bk < bi; ++bk) {                        // strictly-lower blocks: from S
+                const double* Wr = S + lowblk(bi, bk) + rl * DLD + q;
+                const double* Yk = Y + ((bk - j - 1) * BS + q) * DLD + g;
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) dmma884(c[ni][0], c[ni][1], av, Y[(k0 + q) * DLD + ni * 8 + g]);
+                for (int ks = 0; ks < BS / 4; ++ks) {
+                    const double av = Wr[ks * 4];
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni) dmma884(c[ni][0], c[ni][1], av, Yk[ks * 4 * DLD + ni * 8]);
+                }
             }
+            {                                                             // diagonal block: from Dv (zero above the diagonal)
+                const double* Wr = Dv + (bi * BS + rl) * DLD + q;
+                const double* Yk = Y + ((bi - j - 1) * BS + q) * DLD + g;
 #pragma unroll
-            for (int ks = 0; ks < BS / 4; ++ks) {       // diagonal block: from Dv (zero above the diagonal)
-                const double av = Dv[(r1 + rr + g) * DLD + ks * 4 + q];
+                for (int ks = 0; ks < BS / 4; ++ks) {
+                    const double av = Wr[ks * 4];
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) dmma884(c[ni][0], c[ni][1], av, Y[(kdiag + ks * 4 + q) * DLD + ni * 8 + g]);
+                    for (int ni = 0; ni < 2; ++ni) dmma884(c[ni][0], c[ni][1], av, Yk[ks * 4 * DLD + ni * 8]);
+                }
             }
-            double* Wr = S + (r1 + rr + g) * WLD + o + 2 * q;
+            double* Wo = S + lowblk(bi, j) + rl * DLD + 2 * q;
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni) { Wr[ni * 8] = -c[ni][0]; Wr[ni * 8 + 1] = -c[ni][1]; }
+            for (int ni = 0; ni < 2; ++ni) { Wo[ni * 8] = -c[ni][0]; Wo[ni * 8 + 1] = -c[ni][1]; }
         }
         __syncthreads();
     }
     for (int e = tid; e < NB_IN * NB_IN; e += 256) {
         const int r = e >> 7, c = e & 127;
         double v = 0.0;
-        if ((r / BS) == (c / BS)) v = Dv[r * DLD + (c & (BS - 1))];   // diagonal blocks (zero above the diagonal already)
-        else if (c < r) v = S[r * WLD + c];
+        if ((r >> 4) == (c >> 4)) v = Dv[r * DLD + (c & 15)];   // diagonal blocks (zero above the diagonal already)
+        else if (c < r) v = S[lowblk(r >> 4, c >> 4) + (r & 15) * DLD + (c & 15)];
         Winv[e] = v;
     }
 }
@@ -516,9 +532,41 @@ using namespace gabo;
 
 // ----------------------------------------------------------------------------------------------------------------------
 extern "C" size_t gabo_potrf_workspace_bytes(int64_t n) {
-    (void)n;
-    return align256((size_t)NB_IN * NB_IN * sizeof(double));
+    if (n < 0) n = 0;
+    // inverse of the current 128x128 diagonal block + the [n, 128] staging buffer of the panel product
+    return align256((size_t)NB_IN * NB_IN * sizeof(double)) + align256((size_t)n * NB_IN * sizeof(double));
 }
+
+namespace {
+
+// Factor block column [k1, k2) of the lower triangle for all rows k1 .. n-1 (inner blocking nb = 128), on `stream`.
+// Every kernel here fits beside one resident trailing-update CTA, so the panel can run concurrently with the update.
+int potrf_panel(int64_t n, double* A, int64_t lda, int64_t k1, int64_t k2, double sigma2, int32_t* info, double* Winv,
+                double* T, cudaStream_t stream) {
+    int rc;
+    for (int64_t kk = k1; kk < k2; kk += NB_IN) {
+        const int jb = (int)((k2 - kk) < NB_IN ? (k2 - kk) : NB_IN);
+        potf2_inv_kernel<<<1, 256, POTF2V2_SMEM, stream>>>(A + kk * lda + kk, lda, jb, sigma2, Winv, info, (int)kk);
+        GABO_LAUNCH_CHECK();
+        const int64_t mrest = n - (kk + jb);
+        if (mrest <= 0) continue;
+        double* A21 = A + (kk + jb) * lda + kk;
+        // L21 = A21 * inv(L11)^T as a DMMA product into the staging buffer, then back in place
+        rc = launch_gemm(true, true, mrest, jb, jb, 1.0, A21, lda, Winv, NB_IN, true, T, NB_IN, false, stream);
+        if (rc) return rc;
+        GABO_CUDA_TRY(cudaMemcpy2DAsync(A21, (size_t)lda * sizeof(double), T, (size_t)NB_IN * sizeof(double),
+                                        (size_t)jb * sizeof(double), (size_t)mrest, cudaMemcpyDeviceToDevice, stream));
+        const int64_t ncols = k2 - (kk + jb);   // panel-internal update of the remaining columns of the block column
+        if (ncols > 0) {
+            rc = launch_gemm(true, true, mrest, ncols, jb, -1.0, A21, lda, A21, lda, false, A + (kk + jb) * lda + (kk + jb),
+                             lda, true, stream);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+}  // namespace
 
 extern "C" int gabo_potrf_f64(int64_t n, double* A, int64_t lda, double sigma2, int32_t* info, void* workspace,
                               size_t workspace_bytes, gabo_stream_t stream_) {
@@ -532,40 +580,57 @@ extern "C" int gabo_potrf_f64(int64_t n, double* A, int64_t lda, double sigma2, 
     if (n > 2000000000LL) return -1;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     double* Winv = static_cast<double*>(workspace);
+    double* T = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + align256((size_t)NB_IN * NB_IN * sizeof(double)));
     int rc;
     if ((rc = set_smem(potf2_inv_kernel, POTF2V2_SMEM))) return rc;
-    if ((rc = set_smem(panel_trsm_kernel, PANEL_SMEM))) return rc;
     GABO_CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int32_t), stream));
+    if (n <= NB_OUT) return potrf_panel(n, A, lda, 0, n, sigma2, info, Winv, T, stream);
 
-    for (int64_t k0 = 0; k0 < n; k0 += NB_OUT) {
-        const int64_t kend = (k0 + NB_OUT < n) ? k0 + NB_OUT : n;   // end of this outer block column
-        for (int64_t kk = k0; kk < kend; kk += NB_IN) {
-            const int jb = (int)((kend - kk) < NB_IN ? (kend - kk) : NB_IN);
-            double* Akk = A + kk * lda + kk;
-            potf2_inv_kernel<<<1, 256, POTF2V2_SMEM, stream>>>(Akk, lda, jb, sigma2, Winv, info, (int)kk);
-            GABO_LAUNCH_CHECK();
-            const int64_t mrest = n - (kk + jb);
-            if (mrest <= 0) continue;
-            double* A21 = A + (kk + jb) * lda + kk;
-            panel_trsm_kernel<<<(unsigned)ceil_div64(mrest, CH), 256, PANEL_SMEM, stream>>>(A21, lda, mrest, jb, Winv);
-            GABO_LAUNCH_CHECK();
-            // panel-internal update: columns kk+jb .. kend of all rows below, lower part (k = jb)
-            const int64_t ncols = kend - (kk + jb);
-            if (ncols > 0) {
-                rc = launch_gemm(true, true, mrest, ncols, jb, -1.0, A21, lda, A21, lda, false,
-                                 A + (kk + jb) * lda + (kk + jb), lda, true, stream);
-                if (rc) return rc;
-            }
-        }
-        // trailing update with the whole outer block column (k = kend - k0)
-        const int64_t mtrail = n - kend;
-        if (mtrail > 0) {
-            const double* L21 = A + kend * lda + k0;
-            rc = launch_gemm(true, true, mtrail, mtrail, kend - k0, -1.0, L21, lda, L21, lda, false,
-                             A + kend * lda + kend, lda, true, stream);
-            if (rc) return rc;
+    // Right-looking with one block column of look-ahead.  Main stream: the big trailing updates.  Auxiliary high-priority
+    // stream: the factorisation of the NEXT block column, started as soon as that column alone has been updated (U1), so it
+    // runs while the rest of the trailing matrix is updated (U2).  The streams and events live only for this call.
+    int least = 0, greatest = 0;
+    GABO_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    cudaStream_t aux;
+    cudaEvent_t e_main, e_aux;
+    GABO_CUDA_TRY(cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, greatest));
+    GABO_CUDA_TRY(cudaEventCreateWithFlags(&e_main, cudaEventDisableTiming));
+    GABO_CUDA_TRY(cudaEventCreateWithFlags(&e_aux, cudaEventDisableTiming));
+    auto cleanup = [&]() { cudaEventDestroy(e_main); cudaEventDestroy(e_aux); cudaStreamDestroy(aux); };
+#define GABO_TRY_CLEAN(expr)                                           \
+    do {                                                               \
+        cudaError_t e__ = (expr);                                      \
+        if (e__ != cudaSuccess) { cleanup(); return GABO_ERR_CUDA - (int)e__; } \
+    } while (0)
+
+    GABO_TRY_CLEAN(cudaEventRecord(e_main, stream));
+    GABO_TRY_CLEAN(cudaStreamWaitEvent(aux, e_main, 0));
+    rc = potrf_panel(n, A, lda, 0, NB_OUT, sigma2, info, Winv, T, aux);
+    if (rc) { cleanup(); return rc; }
+    GABO_TRY_CLEAN(cudaEventRecord(e_aux, aux));
+    for (int64_t k0 = 0; k0 + NB_OUT < n; k0 += NB_OUT) {
+        const int64_t k1 = k0 + NB_OUT;
+        const int64_t k2 = (k1 + NB_OUT < n) ? k1 + NB_OUT : n;
+        const double* L21 = A + k1 * lda + k0;                      // rows k1.., the factored block column [k0, k1)
+        GABO_TRY_CLEAN(cudaStreamWaitEvent(stream, e_aux, 0));      // block column [k0, k1) is factored
+        // U1: next block column only
+        rc = launch_gemm(true, true, n - k1, k2 - k1, NB_OUT, -1.0, L21, lda, L21, lda, false, A + k1 * lda + k1, lda, true, stream);
+        if (rc) { cleanup(); return rc; }
+        GABO_TRY_CLEAN(cudaEventRecord(e_main, stream));
+        GABO_TRY_CLEAN(cudaStreamWaitEvent(aux, e_main, 0));
+        rc = potrf_panel(n, A, lda, k1, k2, sigma2, info, Winv, T, aux);
+        if (rc) { cleanup(); return rc; }
+        GABO_TRY_CLEAN(cudaEventRecord(e_aux, aux));
+        // U2: everything to the right of the next block column
+        if (k2 < n) {
+            const double* L31 = A + k2 * lda + k0;
+            rc = launch_gemm(true, true, n - k2, n - k2, NB_OUT, -1.0, L31, lda, L31, lda, false, A + k2 * lda + k2, lda, true, stream);
+            if (rc) { cleanup(); return rc; }
         }
     }
+    GABO_TRY_CLEAN(cudaStreamWaitEvent(stream, e_aux, 0));
+#undef GABO_TRY_CLEAN
+    cleanup();
     return 0;
 }
 
