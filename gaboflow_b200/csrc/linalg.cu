@@ -391,6 +391,77 @@ __global__ void __launch_bounds__(256, 1) diag_apply_kernel(double* __restrict__
     }
 }
 
+// ---- solve step for <= 4 right-hand sides: B_k (jb x NRHS, in place) <- W B_k or W^T B_k, one CTA, W read once from L2 ----
+template <int NRHS, bool TRANS>
+__global__ void __launch_bounds__(256) diag_apply_gemv_kernel(double* __restrict__ B, int64_t ldb, int jb,
+                                                              const double* __restrict__ Winv) {
+    __shared__ double sb[NB_IN][NRHS];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NB_IN * NRHS; e += 256) {
+        const int k = e / NRHS, c = e - k * NRHS;
+        sb[k][c] = (k < jb) ? B[(int64_t)k * ldb + c] : 0.0;
+    }
+    __syncthreads();
+    if (!TRANS) {
+        // x_r = sum_{k <= r} W[r][k] b_k.  Warp w owns rows w, w+8, ...; all 16 x 4 loads of a lane are issued before
+        // the first use (memory-level parallelism: the kernel is L2-latency bound otherwise).
+        const int warp = tid >> 5, lane = tid & 31;
+        double w[16][4];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int r = warp + 8 * i;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = lane + 32 * j;
+                w[i][j] = (r < jb && k <= r) ? Winv[r * NB_IN + k] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int r = warp + 8 * i;
+            double acc[NRHS];
+#pragma unroll
+            for (int c = 0; c < NRHS; ++c) {
+                acc[c] = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[c] = fma(w[i][j], sb[lane + 32 * j][c], acc[c]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+            }
+            if (lane == 0 && r < jb) {
+#pragma unroll
+                for (int c = 0; c < NRHS; ++c) B[(int64_t)r * ldb + c] = acc[c];
+            }
+        }
+    } else {
+        // x_i = sum_{k >= i} W[k][i] b_k.  Thread = (i, half): 64 k's each, coalesced across i; halves combined in smem.
+        __shared__ double part[NB_IN][NRHS];
+        const int i = tid & 127, half = tid >> 7;
+        double w[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            const int k = half * 64 + j;
+            w[j] = (k < jb && k >= i) ? Winv[k * NB_IN + i] : 0.0;
+        }
+        double acc[NRHS];
+#pragma unroll
+        for (int c = 0; c < NRHS; ++c) {
+            acc[c] = 0.0;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) acc[c] = fma(w[j], sb[half * 64 + j][c], acc[c]);
+        }
+        if (half == 1) {
+#pragma unroll
+            for (int c = 0; c < NRHS; ++c) part[i][c] = acc[c];
+        }
+        __syncthreads();
+        if (half == 0 && i < jb) {
+#pragma unroll
+            for (int c = 0; c < NRHS; ++c) B[(int64_t)i * ldb + c] = acc[c] + part[i][c];
+        }
+    }
+}
+
 // ---- solve step for <= 4 right-hand sides: B[r, :] -= sum_k Lp[r][k] X[k, :], HBM-bound, one warp per row ---------------
 //  TRANS == false: Lp element (r,k) at Lp[r*ldl + k]   (panel below the diagonal block)
 //  TRANS == true : element (r,k) = L[k][r] at Lp[k*ldl + r] (row block left of the diagonal block, read transposed)
@@ -677,8 +748,24 @@ extern "C" int gabo_trsm_f64(int trans, int64_t n, int64_t nrhs, const double* L
         const int jb = (int)((n - k0) < NB_IN ? (n - k0) : NB_IN);
         double* Bk = B + k0 * ldb;
         const double* Wk = Wall + kb * NB_IN * NB_IN;
-        if (!trans) diag_apply_kernel<false><<<rhs_chunks, 256, DIAGAPPLY_SMEM, stream>>>(Bk, ldb, nrhs, jb, Wk);
-        else diag_apply_kernel<true><<<rhs_chunks, 256, DIAGAPPLY_SMEM, stream>>>(Bk, ldb, nrhs, jb, Wk);
+        if (nrhs <= 4) {
+#define GABO_DAG(NR)                                                                                         \
+    do {                                                                                                     \
+        if (!trans) diag_apply_gemv_kernel<NR, false><<<1, 256, 0, stream>>>(Bk, ldb, jb, Wk);               \
+        else diag_apply_gemv_kernel<NR, true><<<1, 256, 0, stream>>>(Bk, ldb, jb, Wk);                       \
+    } while (0)
+            switch (nrhs) {
+                case 1: GABO_DAG(1); break;
+                case 2: GABO_DAG(2); break;
+                case 3: GABO_DAG(3); break;
+                default: GABO_DAG(4); break;
+            }
+#undef GABO_DAG
+        } else if (!trans) {
+            diag_apply_kernel<false><<<rhs_chunks, 256, DIAGAPPLY_SMEM, stream>>>(Bk, ldb, nrhs, jb, Wk);
+        } else {
+            diag_apply_kernel<true><<<rhs_chunks, 256, DIAGAPPLY_SMEM, stream>>>(Bk, ldb, nrhs, jb, Wk);
+        }
         GABO_LAUNCH_CHECK();
         // rows still to be updated: below the block (forward) or above it (backward)
         const int64_t m = trans ? k0 : n - (k0 + jb);
