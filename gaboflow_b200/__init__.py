@@ -6,5 +6,6 @@ from .kernel_utils import (SphereGaussianKernel, SphereLaplaceKernel, SpdSteinGa
                            SpdAffineInvariantGaussianKernel, SpdAffineInvariantLaplaceKernel,
                            SpdFrobeniusGaussianKernel, SpdLogEuclideanGaussianKernel)
 from .gpr import GPR, Gaussian, Zero, Constant
+from .acquisition import ExpectedImprovement
 
 __version__ = '0.1.0'

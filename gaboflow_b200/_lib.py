@@ -30,6 +30,7 @@ SIGNATURES = {
     'gabo_logdet_f64': (i32, [i64, vp, i64, vp, vp]),
     'gabo_gp_loglik_f64': (i32, [i64, i64, vp, i64, vp, i64, vp, vp]),
     'gabo_gp_predict_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, f64, vp, vp, vp]),
+    'gabo_expected_improvement_f64': (i32, [i64, vp, vp, f64, vp, vp]),
     'gabo_gemm_nt_sub_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, i32, vp]),
     'gabo_points_gram_cyclic_f64': (i32, [i32, vp, i64, i64, i32, f64, f64, vp, i64, i32, i32, vp, sz, vp]),
     'gabo_enable_peer_access': (i32, [i32]),

@@ -1,0 +1,31 @@
+"""Expected Improvement on the B200 posterior: the slice of GPflowOpt's ``ExpectedImprovement`` [third party] that the
+reference's optimisers consume (``examples/bo_sphere/benchmark_examples/bo_sphere_ackley_manifold.py:145``;
+``BoManifolds/BO_utils/manifold_optimization.py:250-271,427`` call ``acquisition.evaluate`` on candidate points).
+Gradients with respect to the candidates are not available yet."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .param import to_device
+
+
+class ExpectedImprovement:
+    def __init__(self, model):
+        self.model = model
+        self.fmin = None
+        self.setup()
+
+    def setup(self):
+        """fmin = min of the posterior mean at the training inputs (GPflowOpt ``ExpectedImprovement._setup``)."""
+        mean, _ = self.model.build_predict(self.model.X, full_cov=False)
+        self.fmin = float(mean.min().item())
+        return self.fmin
+
+    def build_acquisition(self, Xcand) -> torch.Tensor:
+        mean, var = self.model.build_predict(to_device(Xcand), full_cov=False)
+        return ops.expected_improvement(mean, var, self.fmin)
+
+    def evaluate(self, Xcand):
+        """NumPy in, NumPy out: EI at the candidate points, shape [M, 1]."""
+        return self.build_acquisition(Xcand).cpu().numpy()

@@ -927,3 +927,36 @@ extern "C" int gabo_solve_update_f64(int64_t m, int64_t k, int64_t nrhs, const d
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     return launch_gemm(true, false, m, nrhs, k, -1.0, Lp, ldl, X, ldx, false, Y, ldy, false, stream);
 }
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Expected Improvement (GPflowOpt ExpectedImprovement.build_acquisition [third party], consumed by the reference at
+// BO_utils/manifold_optimization.py:250-271,427): EI = (fmin - mu) Phi(z) + var * N(fmin; mu, sqrt(var)),
+// var floored at 1e-6, z = (fmin - mu) / sqrt(var).  Elementwise over the M candidates.
+namespace gabo {
+namespace {
+__global__ void ei_kernel(int64_t M, const double* __restrict__ mean, const double* __restrict__ var, double fmin,
+                          double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const double v = fmax(var[i], 1e-6);
+    const double sd = sqrt(v);
+    const double diff = fmin - mean[i];
+    const double z = diff / sd;
+    const double cdf = 0.5 * erfc(-z * 0.70710678118654752440);
+    const double pdf = exp(-0.5 * z * z) * 0.39894228040143267794 / sd;   // N(fmin; mu, sd)
+    out[i] = diff * cdf + v * pdf;
+}
+}  // namespace
+}  // namespace gabo
+
+extern "C" int gabo_expected_improvement_f64(int64_t M, const double* mean, const double* var, double fmin, double* out,
+                                             gabo_stream_t stream) {
+    if (M < 0) return -1;
+    if (M == 0) return 0;
+    if (mean == nullptr) return -2;
+    if (var == nullptr) return -3;
+    if (out == nullptr) return -5;
+    gabo::ei_kernel<<<(unsigned)gabo::ceil_div64(M, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(M, mean, var, fmin, out);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}

@@ -320,3 +320,14 @@ def points_gram_cyclic(kind: int, X: torch.Tensor, bases, ldk: int, world: int, 
                                        C.cast(arr, C.c_void_p), int(ldk), int(world), int(rank),
                                        workspace.data_ptr(), workspace.numel(), _stream())
     _lib.check('gabo_points_gram_cyclic_f64', st)
+
+
+def expected_improvement(mean: torch.Tensor, var: torch.Tensor, fmin: float) -> torch.Tensor:
+    """EI over the candidates (gabo_expected_improvement_f64); mean / var are [M] or [M,1] device tensors."""
+    _req(mean, 'mean'); _req(var, 'var')
+    m = mean.reshape(-1).contiguous()
+    v = var.reshape(-1).contiguous()
+    out = torch.empty_like(m)
+    st = _lib.lib().gabo_expected_improvement_f64(int(m.numel()), m.data_ptr(), v.data_ptr(), float(fmin), out.data_ptr(), _stream())
+    _lib.check('gabo_expected_improvement_f64', st)
+    return out.reshape(mean.shape)

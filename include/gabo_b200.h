@@ -150,6 +150,12 @@ int gabo_gemm_nt_sub_f64(int64_t m, int64_t n, int64_t k, const double* A, int64
                          const double* B, int64_t ldb, double* C, int64_t ldc, int lower,
                          gabo_stream_t stream);
 
+/* Expected Improvement over M candidates from the posterior mean / variance (GPflowOpt ExpectedImprovement
+ * [third party]; consumed by the reference at BO_utils/manifold_optimization.py:250-271,427):
+ *   out = (fmin - mean) Phi(z) + var N(fmin; mean, sqrt(var)), var floored at 1e-6, z = (fmin - mean)/sqrt(var). */
+int gabo_expected_improvement_f64(int64_t M, const double* mean, const double* var, double fmin, double* out,
+                                  gabo_stream_t stream);
+
 /* ---- Building blocks of the multi-GPU factorisation (1-D block-cyclic by row panels) --------
  * The host side (gaboflow_b200/dist.py) broadcasts the factored diagonal block and all-gathers the panel over NCCL;
  * these calls do the local work of each rank.

@@ -132,3 +132,21 @@ def test_gp_pipeline_synthetic_sphere(cuda, n):
     mo, vo = orc.gp_predict(Kor, orc.sphere_gaussian_K(X, Xs, beta=2.0), np.ones(300), y, 1e-2)
     assert np.max(np.abs(mean - mo)) / np.max(np.abs(mo)) < 1e-8
     assert np.max(np.abs(var - vo) / np.abs(vo)) < 1e-8
+
+
+def test_expected_improvement_vs_oracle(cuda, golden):
+    """a12 of SURVEY section 8(a): EI from the posterior, against the oracle's restatement of GPflowOpt's formula."""
+    from gaboflow_b200 import GPR, SphereGaussianKernel, ExpectedImprovement
+    g = golden['sphere_s2']
+    k = SphereGaussianKernel(input_dim=3, active_dims=range(3), beta_min=7.0, beta=10.0, variance=1.)
+    m = GPR(g['x_man'], g['y_train'], kern=k)
+    acq = ExpectedImprovement(m)
+    Kor = orc.sphere_gaussian_K(g['x_man'], beta=17.0)
+    m_tr, _ = orc.gp_predict(Kor, Kor, np.ones(20), g['y_train'], 1.0)
+    assert abs(acq.fmin - m_tr.min()) < 1e-10
+    cand = orc.synth_sphere(100, 3, seed=12)          # the reference scores 100 anchor candidates (manifold_optimization.py:402-431)
+    mo, vo = orc.gp_predict(Kor, orc.sphere_gaussian_K(g['x_man'], cand, beta=17.0), np.ones(100), g['y_train'], 1.0)
+    ref = orc.expected_improvement(mo, vo, m_tr.min())
+    got = acq.evaluate(cand)
+    assert got.shape == (100, 1)
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-12)) < 1e-8
