@@ -33,7 +33,7 @@ SEED_X, SEED_Y = 20240, 20241
 BETA, VARIANCE, SIGMA2 = 2.0, 1.0, 1e-2
 DIM = 51
 FP64_PEAK_TFLOPS = 37.2                # measured on this pool: tools/fp64_probe.cu -> profiles/r01_fp64_probe.txt (DMMA.8x8x4)
-POTRF_DRAM_TRAFFIC_BYTES = None        # dram read+write of one potrf at N=32768 from the ncu capture in profiles/ (filled when captured)
+GEMM_DRAM_TRAFFIC_BYTES = 9.40e9        # ncu: dram__bytes_read 5.286 GB + write 4.115 GB for the m=32256, k=512 trailing update
 F_TR = 100                             # declared transcendental flops per sphere Gram entry
 
 
@@ -165,7 +165,12 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            opts = None
+        dist.init_process_group('nccl', device_id=dev, pg_options=opts)
     lib = _lib.lib()
 
     N, NC = args.n_gram, min(args.n_chol, args.n_gram)
@@ -241,7 +246,7 @@ def run_ours(args):
             if from_host:
                 return float(ll_dev.item())      # device -> host read of the step's result
         else:
-            potrf_block_cyclic_(K, lay, SIGMA2, n_factor=NC)
+            potrf_block_cyclic_(K, lay, SIGMA2, n_factor=NC, lookahead=os.environ.get('GABO_DIST_LOOKAHEAD', '0') == '1')
             if events is not None:
                 events[2].record()
             V.copy_(yd[y_rows])
@@ -258,6 +263,8 @@ def run_ours(args):
 
     # ---- device-resident timing: K steps, per-phase events, max over ranks ----
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    if world == 1:
+        lib.gabo_profile_trailing_updates(1)     # CUDA events around every big trailing-update launch (dominant kernel)
     launches0 = lib.gabo_launch_count()
     with ClockSampler(index=local_rank) as clocks:
         barrier()
@@ -268,6 +275,16 @@ def run_ours(args):
         t_end.record()
         barrier()
     launches = lib.gabo_launch_count() - launches0
+    kern = None
+    if world == 1:
+        import ctypes as C
+        kn, kms, kfl, kmx, kmxf = C.c_int64(), C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        lib.gabo_profile_trailing_read(C.byref(kn), C.byref(kms), C.byref(kfl), C.byref(kmx), C.byref(kmxf))
+        lib.gabo_profile_trailing_updates(0)
+        if kn.value > 0 and kms.value > 0:
+            kern = {'launches': kn.value, 'total_ms': kms.value, 'tflops_avg': kfl.value / kms.value * 1e-9,
+                    'largest_ms': kmx.value, 'largest_tflops': kmxf.value / kmx.value * 1e-9 if kmx.value > 0 else None,
+                    'flops_per_launch_avg': kfl.value / kn.value, 'ms_per_launch_avg': kms.value / kn.value}
     total_ms = t_start.elapsed_time(t_end)
     gram_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     potrf_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
@@ -344,11 +361,21 @@ def run_ours(args):
                 'h2d_bytes_per_step': int(Xh.numel() * 8 + yh.numel() * 8), 'd2h_bytes_per_step': 8,
                 'ms_per_step': e2e_total_ms / args.steps,
                 'api': 'pinned host X,y -> device, ops.points_gram / potrf_ / trsm_ / gp_loglik (C-ABI; gaboflow_b200.dist for N>1), loglik read back'},
-        'roofline': {'bound': 'tensor', 'kernel': 'gabo_potrf_f64 (95% in gemm_kernel<true,true>, DMMA.8x8x4)',
-                     'achieved': potrf_tflops, 'peak': FP64_PEAK_TFLOPS * world, 'unit': 'TFLOP/s',
-                     'frac': (potrf_tflops / (FP64_PEAK_TFLOPS * world)) if potrf_tflops else None,
-                     'traffic': POTRF_DRAM_TRAFFIC_BYTES if (world == 1 and NC == 32768) else None,
-                     'flops_per_launch': NC ** 3 / 3,
+        'roofline': {'bound': 'tensor',
+                     'kernel': 'gemm_kernel<true,true> (DMMA.8x8x4): the k=512 trailing updates inside gabo_potrf_f64, '
+                               + ('%.0f%% of the step' % (100.0 * kern['total_ms'] / args.steps / (total_ms / args.steps)) if kern else 'dominant kernel'),
+                     'achieved': kern['tflops_avg'] if kern else potrf_tflops,
+                     'peak': FP64_PEAK_TFLOPS * world, 'unit': 'TFLOP/s',
+                     'frac': ((kern['tflops_avg'] if kern else potrf_tflops) / (FP64_PEAK_TFLOPS * world)) if (kern or potrf_tflops) else None,
+                     'traffic': GEMM_DRAM_TRAFFIC_BYTES if kern else None,
+                     'traffic_note': 'dram read+write of ONE launch at m=32256, k=512 (the largest): ncu --set full, '
+                                     'profiles/r01_gemm_bench_shape_ncu.txt; algorithmic bytes of that launch 8.49e9',
+                     'flops_per_launch': kern['flops_per_launch_avg'] if kern else NC ** 3 / 3,
+                     'ms_per_launch': kern['ms_per_launch_avg'] if kern else None,
+                     'launches_timed': kern['launches'] if kern else None,
+                     'largest_launch': {'ms': kern['largest_ms'], 'tflops': kern['largest_tflops']} if kern else None,
+                     'how': 'CUDA events recorded by the library around every such launch on its stream during the timed steps '
+                            '(gabo_profile_trailing_updates); flops = 2*128*64*512 per lower tile',
                      'peak_source': 'FP64 tensor peak is not in MEASURED_PEAKS.json: measured on this pool with tools/fp64_probe.cu '
                                     '(profiles/r01_fp64_probe.txt, DMMA 37.2 TFLOP/s; cuBLAS DGEMM 36.2)'},
         'roofline_gram': {'bound': 'fp64', 'kernel': 'points_gram_kernel<52>', 'achieved': gram_flops / (gram_ms * 1e-3) * 1e-12,

@@ -31,6 +31,8 @@ SIGNATURES = {
     'gabo_gp_loglik_f64': (i32, [i64, i64, vp, i64, vp, i64, vp, vp]),
     'gabo_gp_predict_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, f64, vp, vp, vp]),
     'gabo_expected_improvement_f64': (i32, [i64, vp, vp, f64, vp, vp]),
+    'gabo_profile_trailing_updates': (i32, [i32]),
+    'gabo_profile_trailing_read': (i32, [C.POINTER(i64), C.POINTER(f64), C.POINTER(f64), C.POINTER(f64), C.POINTER(f64)]),
     'gabo_gemm_nt_sub_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, i32, vp]),
     'gabo_points_gram_cyclic_f64': (i32, [i32, vp, i64, i64, i32, f64, f64, vp, i64, i32, i32, vp, sz, vp]),
     'gabo_enable_peer_access': (i32, [i32]),
@@ -39,8 +41,10 @@ SIGNATURES = {
     'gabo_ipc_export': (i32, [vp, C.c_char_p]),
     'gabo_ipc_open': (i32, [C.c_char_p, C.POINTER(vp)]),
     'gabo_ipc_close': (i32, [vp]),
-    'gabo_trsm_right_workspace_bytes': (sz, [i64]),
+    'gabo_trsm_right_workspace_bytes': (sz, [i64, i64]),
     'gabo_trsm_right_f64': (i32, [i64, i64, vp, i64, vp, i64, vp, sz, vp]),
+    'gabo_potrf_diag_f64': (i32, [i64, vp, i64, f64, vp, vp, vp, sz, vp]),
+    'gabo_trsm_right_winv_f64': (i32, [i64, i64, vp, i64, vp, vp, i64, vp, sz, vp]),
     'gabo_syrk_cyclic_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, i32, vp]),
     'gabo_solve_update_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]),
 }

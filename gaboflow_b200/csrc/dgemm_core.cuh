@@ -6,8 +6,8 @@
 //
 // CTA tile 128x64, 8 warps (4x2), 32x32 outputs per warp in registers (64 accumulator registers), two CTAs per SM so
 // that one CTA's prologue / C read-modify-write epilogue / barrier skew is covered by the other CTA's DMMA stream
-// (one 16-warp CTA per SM left the pipe idle 24% of the time: profiles/r01_gemm_v3_summary.txt).  BK = 16 per stage,
-// 3-stage cp.async (LDGSTS) ring.  Operand tiles sit in shared memory with a leading dimension = 4 (mod 16) doubles,
+// (one 16-warp CTA per SM left the pipe idle 24% of the time: profiles/r01_gemm_v3_summary.txt).  BK = 32 per stage,
+// 2-stage cp.async (LDGSTS) ring (110 KB per CTA).  Operand tiles sit in shared memory with a leading dimension = 4 (mod 16) doubles,
 // which makes every fragment load of the m8n8k4 layout bank-conflict free for both operand orientations.
 #pragma once
 #include "gabo_common.cuh"
@@ -17,13 +17,14 @@ namespace gabo {
 constexpr int GTM = 128;         // CTA tile rows
 constexpr int GTN = 64;          // CTA tile columns
 constexpr int GT = GTM;          // row granularity used by callers
-constexpr int GBK = 16;          // k per stage
-constexpr int GSTAGES = 3;
+constexpr int GBK = 32;          // k per stage
+constexpr int GSTAGES = 2;
 constexpr int GTHREADS = 256;
 constexpr int GWN = GTN / 32;    // warps along n (2); warps along m = 4
-constexpr int LDK_MAJ = GBK + 4;     // 20: K-major tile [rows][20]
-constexpr int LDM_MAJ = GTM + 4;     // 132: M-major A tile [16][132]
-constexpr int LDN_MAJ = GTN + 4;     // 68:  N-major B tile [16][68]
+constexpr int GEMM_GROUP_M = 16; // tile rows per rasterisation group
+constexpr int LDK_MAJ = GBK + 4;     // 36: K-major tile [rows][36]
+constexpr int LDM_MAJ = GTM + 4;     // 132: M-major A tile [32][132]
+constexpr int LDN_MAJ = GTN + 4;     // 68:  N-major B tile [32][68]
 constexpr int TILE_A_DOUBLES = (GTM * LDK_MAJ > GBK * LDM_MAJ) ? GTM * LDK_MAJ : GBK * LDM_MAJ;   // 2560
 constexpr int TILE_B_DOUBLES = (GTN * LDK_MAJ > GBK * LDN_MAJ) ? GTN * LDK_MAJ : GBK * LDN_MAJ;   // 1280
 constexpr int STAGE_DOUBLES = TILE_A_DOUBLES + TILE_B_DOUBLES;
@@ -40,6 +41,7 @@ struct GemmParams {
     int64_t row_base, col_base;
     int cyc_nb, cyc_world, cyc_rank;
     int vecA, vecB, vecC;   // 16-byte access allowed (even leading dimension, 16 B aligned base)
+    int tiles_m, tiles_n;   // tile grid; CTAs are rasterised in groups of GEMM_GROUP_M tile rows (see gemm_kernel)
     double alpha;    // C <- C + alpha * op(A) op(B)   (alpha = -1 for the updates; +1 with beta0 for products)
     int beta0;       // 1: C <- alpha * op(A) op(B)  (C not read)
 };
@@ -197,7 +199,15 @@ __device__ __forceinline__ void gemm_tile_epilogue(const GemmParams& p, int64_t 
 template <bool A_KMAJ, bool B_KMAJ>
 __global__ void __launch_bounds__(GTHREADS, 2) gemm_kernel(const GemmParams p) {
     extern __shared__ __align__(16) double gemm_smem[];
-    const int64_t bi = blockIdx.y, bj = blockIdx.x;
+    // Grouped rasterisation: consecutive CTAs walk DOWN a group of GEMM_GROUP_M tile rows before moving to the next tile
+    // column, so the CTAs in flight share a few B tiles and GEMM_GROUP_M A tiles through L2.  With the plain row-major
+    // order the k = 512 panel of the N = 32768 update (132 MB > L2) was re-streamed from HBM for every tile row:
+    // 15.5 GB of DRAM reads against 4.3 GB algorithmic (profiles/r01_gemm_bench_shape_ncu.txt).
+    const int64_t t = blockIdx.x;
+    const int64_t per_group = (int64_t)GEMM_GROUP_M * p.tiles_n;
+    const int64_t grp = t / per_group, rem = t - grp * per_group;
+    const int64_t bj = rem / GEMM_GROUP_M, bi = grp * GEMM_GROUP_M + (rem - bj * GEMM_GROUP_M);
+    if (bi >= p.tiles_m) return;
     const int64_t row0 = bi * GTM, col0 = bj * GTN;
     if (p.lower) {   // tile strictly above the diagonal (global coordinates of its last row / first column)
         const int64_t last = (row0 + GTM - 1 < p.m) ? row0 + GTM - 1 : p.m - 1;

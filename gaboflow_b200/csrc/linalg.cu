@@ -17,6 +17,7 @@
 // Triangular solves use the same trick: the 128x128 diagonal blocks of L are inverted once (one CTA each, all in
 // parallel), after which forward/backward substitution is a chain of DMMA products (or of HBM-bound GEMV updates when
 // there are at most 4 right-hand sides).
+#include <vector>
 #include "dgemm_core.cuh"
 
 namespace gabo {
@@ -33,7 +34,10 @@ int launch_gemm(bool a_kmaj, bool b_kmaj, int64_t m, int64_t n, int64_t k, doubl
     p.lower = lower ? 1 : 0;
     p.vecA = aligned16(A, lda) ? 1 : 0; p.vecB = aligned16(B, ldb) ? 1 : 0; p.vecC = aligned16(C, ldc) ? 1 : 0;
     p.alpha = alpha; p.beta0 = beta0 ? 1 : 0;
-    dim3 grid((unsigned)ceil_div64(n, GTN), (unsigned)ceil_div64(m, GTM));
+    p.tiles_m = (int)ceil_div64(m, GTM);
+    p.tiles_n = (int)ceil_div64(n, GTN);
+    const int64_t groups = ceil_div64(p.tiles_m, GEMM_GROUP_M);
+    dim3 grid((unsigned)(groups * GEMM_GROUP_M * p.tiles_n));
     const int smem = (int)GEMM_SMEM_BYTES;
 #define GABO_GEMM_LAUNCH(AK, BK_)                                                                                   \
     do {                                                                                                            \
@@ -48,6 +52,15 @@ int launch_gemm(bool a_kmaj, bool b_kmaj, int64_t m, int64_t n, int64_t k, doubl
     GABO_LAUNCH_CHECK();
     return 0;
 }
+
+// ---- optional in-situ timing of the dominant kernel (the U2 trailing updates inside gabo_potrf_f64) --------------------
+// Diagnostic only, off by default: when enabled, every U2 launch is bracketed by CUDA events on its own stream, so that
+// bench.py can report the kernel's average duration inside the timed region without a profiler.
+namespace prof {
+struct Rec { cudaEvent_t e0, e1; double flops; };
+static bool g_enabled = false;
+static std::vector<Rec> g_recs;
+}  // namespace prof
 
 namespace {
 
@@ -612,11 +625,13 @@ namespace {
 
 // Factor block column [k1, k2) of the lower triangle for all rows k1 .. n-1 (inner blocking nb = 128), on `stream`.
 // Every kernel here fits beside one resident trailing-update CTA, so the panel can run concurrently with the update.
-int potrf_panel(int64_t n, double* A, int64_t lda, int64_t k1, int64_t k2, double sigma2, int32_t* info, double* Winv,
-                double* T, cudaStream_t stream) {
+int potrf_panel(int64_t n, double* A, int64_t lda, int64_t k1, int64_t k2, double sigma2, int32_t* info, double* Winv0,
+                double* T, cudaStream_t stream, double* Winv_all = nullptr) {
     int rc;
     for (int64_t kk = k1; kk < k2; kk += NB_IN) {
         const int jb = (int)((k2 - kk) < NB_IN ? (k2 - kk) : NB_IN);
+        // inverse of this diagonal block: shared scratch, or kept per block when the caller wants them all
+        double* Winv = Winv_all ? Winv_all + ((kk - k1) / NB_IN) * NB_IN * NB_IN : Winv0;
         potf2_inv_kernel<<<1, 256, POTF2V2_SMEM, stream>>>(A + kk * lda + kk, lda, jb, sigma2, Winv, info, (int)kk);
         GABO_LAUNCH_CHECK();
         const int64_t mrest = n - (kk + jb);
@@ -695,8 +710,21 @@ extern "C" int gabo_potrf_f64(int64_t n, double* A, int64_t lda, double sigma2, 
         // U2: everything to the right of the next block column
         if (k2 < n) {
             const double* L31 = A + k2 * lda + k0;
+            prof::Rec rec{};
+            if (prof::g_enabled) {
+                cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
+                cudaEventRecord(rec.e0, stream);
+            }
             rc = launch_gemm(true, true, n - k2, n - k2, NB_OUT, -1.0, L31, lda, L31, lda, false, A + k2 * lda + k2, lda, true, stream);
             if (rc) { cleanup(); return rc; }
+            if (prof::g_enabled) {
+                cudaEventRecord(rec.e1, stream);
+                const int64_t m2 = n - k2, tm = ceil_div64(m2, GTM), tn = ceil_div64(m2, GTN);
+                int64_t tiles = 0;   // 128 x 64 tiles on or below the diagonal
+                for (int64_t bi = 0; bi < tm; ++bi) { const int64_t c = (bi * GTM + GTM - 1) / GTN + 1; tiles += c < tn ? c : tn; }
+                rec.flops = 2.0 * (double)tiles * GTM * GTN * NB_OUT;
+                prof::g_recs.push_back(rec);
+            }
         }
     }
     GABO_TRY_CLEAN(cudaStreamWaitEvent(stream, e_aux, 0));
@@ -852,10 +880,53 @@ extern "C" int gabo_gemm_nt_sub_f64(int64_t m, int64_t n, int64_t k, const doubl
 // Building blocks of the multi-GPU (1-D block-cyclic by row panels) factorisation; see gaboflow_b200/dist.py.
 
 // A[m, nb] <- A * L^-T with L lower nb x nb (the panel step of a right-looking Cholesky for rows that live on this rank).
-extern "C" size_t gabo_trsm_right_workspace_bytes(int64_t nb) { return gabo_trsm_workspace_bytes(nb, 1); }
+extern "C" size_t gabo_trsm_right_workspace_bytes(int64_t m, int64_t nb) {
+    if (m < 0) m = 0;
+    // inverses of the 128x128 diagonal blocks of L + the [m, 128] staging buffer of each block-column product
+    return gabo_trsm_workspace_bytes(nb, 1) + align256((size_t)m * NB_IN * sizeof(double));
+}
+
+static int trsm_right_impl(int64_t m, int64_t nb, const double* L, int64_t ldl, const double* Winv_all, double* A,
+                           int64_t lda, void* workspace, size_t workspace_bytes, gabo_stream_t stream_);
 
 extern "C" int gabo_trsm_right_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, double* A, int64_t lda,
                                    void* workspace, size_t workspace_bytes, gabo_stream_t stream_) {
+    return trsm_right_impl(m, nb, L, ldl, nullptr, A, lda, workspace, workspace_bytes, stream_);
+}
+
+// Same, with the inverses of the 128x128 diagonal blocks of L supplied by the caller (as written by gabo_potrf_diag_f64 and
+// broadcast with the factor): no inversion kernel on the critical path of the panel.
+extern "C" int gabo_trsm_right_winv_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, const double* Winv_all,
+                                        double* A, int64_t lda, void* workspace, size_t workspace_bytes,
+                                        gabo_stream_t stream_) {
+    if (Winv_all == nullptr) return -5;
+    const int rc = trsm_right_impl(m, nb, L, ldl, Winv_all, A, lda, workspace, workspace_bytes, stream_);
+    return (rc <= -5 && rc > GABO_ERR_CUDA) ? rc - 1 : rc;   // argument numbering shifts by one after Winv_all
+}
+
+// Factor one diagonal block (nb <= 512) in place and also return the inverses of its 128x128 diagonal blocks
+// (Winv_all: [ceil(nb/128)][128][128]); the owner rank of a panel calls this, then broadcasts factor + inverses.
+extern "C" int gabo_potrf_diag_f64(int64_t nb, double* A, int64_t lda, double sigma2, int32_t* info, double* Winv_all,
+                                   void* workspace, size_t workspace_bytes, gabo_stream_t stream_) {
+    if (nb < 0 || nb > NB_OUT) return -1;
+    if (nb == 0) return 0;
+    if (A == nullptr) return -2;
+    if (lda < nb) return -3;
+    if (info == nullptr) return -5;
+    if (Winv_all == nullptr) return -6;
+    if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return -7;
+    if (workspace_bytes < gabo_potrf_workspace_bytes(nb)) return -8;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    double* Winv = static_cast<double*>(workspace);
+    double* T = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + align256((size_t)NB_IN * NB_IN * sizeof(double)));
+    int rc;
+    if ((rc = set_smem(potf2_inv_kernel, POTF2V2_SMEM))) return rc;
+    GABO_CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int32_t), stream));
+    return potrf_panel(nb, A, lda, 0, nb, sigma2, info, Winv, T, stream, Winv_all);
+}
+
+static int trsm_right_impl(int64_t m, int64_t nb, const double* L, int64_t ldl, const double* Winv_all, double* A,
+                           int64_t lda, void* workspace, size_t workspace_bytes, gabo_stream_t stream_) {
     if (m < 0) return -1;
     if (nb < 0) return -2;
     if (m == 0 || nb == 0) return 0;
@@ -864,15 +935,19 @@ extern "C" int gabo_trsm_right_f64(int64_t m, int64_t nb, const double* L, int64
     if (A == nullptr) return -5;
     if (lda < nb) return -6;
     if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return -7;
-    if (workspace_bytes < gabo_trsm_right_workspace_bytes(nb)) return -8;
+    if (workspace_bytes < gabo_trsm_right_workspace_bytes(m, nb)) return -8;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     double* Wall = static_cast<double*>(workspace);
+    double* T = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + gabo_trsm_workspace_bytes(nb, 1));
     const int64_t nblk = ceil_div64(nb, NB_IN);
     int rc;
-    if ((rc = set_smem(trtri_blocks_kernel, POTF2_SMEM))) return rc;
-    if ((rc = set_smem(panel_trsm_kernel, PANEL_SMEM))) return rc;
-    trtri_blocks_kernel<<<(unsigned)nblk, 512, POTF2_SMEM, stream>>>(L, ldl, nb, Wall);
-    GABO_LAUNCH_CHECK();
+    const double* Winvs = Winv_all;
+    if (Winvs == nullptr) {
+        if ((rc = set_smem(trtri_blocks_kernel, POTF2_SMEM))) return rc;
+        trtri_blocks_kernel<<<(unsigned)nblk, 512, POTF2_SMEM, stream>>>(L, ldl, nb, Wall);
+        GABO_LAUNCH_CHECK();
+        Winvs = Wall;
+    }
     for (int64_t b = 0; b < nblk; ++b) {
         const int64_t j0 = b * NB_IN;
         const int jb = (int)((nb - j0) < NB_IN ? (nb - j0) : NB_IN);
@@ -880,8 +955,12 @@ extern "C" int gabo_trsm_right_f64(int64_t m, int64_t nb, const double* L, int64
             rc = launch_gemm(true, true, m, jb, j0, -1.0, A, lda, L + j0 * ldl, ldl, false, A + j0, lda, false, stream);
             if (rc) return rc;
         }
-        panel_trsm_kernel<<<(unsigned)ceil_div64(m, CH), 256, PANEL_SMEM, stream>>>(A + j0, lda, m, jb, Wall + b * NB_IN * NB_IN);
-        GABO_LAUNCH_CHECK();
+        // A[:, j0:j0+jb] <- A[:, j0:j0+jb] * inv(L_bb)^T through the staging buffer (GEMM-core footprint: it can run
+        // beside a resident trailing-update CTA, which the look-ahead of the distributed factorisation relies on)
+        rc = launch_gemm(true, true, m, jb, jb, 1.0, A + j0, lda, Winvs + b * NB_IN * NB_IN, NB_IN, true, T, NB_IN, false, stream);
+        if (rc) return rc;
+        GABO_CUDA_TRY(cudaMemcpy2DAsync(A + j0, (size_t)lda * sizeof(double), T, (size_t)NB_IN * sizeof(double),
+                                        (size_t)jb * sizeof(double), (size_t)m, cudaMemcpyDeviceToDevice, stream));
     }
     return 0;
 }
@@ -958,5 +1037,32 @@ extern "C" int gabo_expected_improvement_f64(int64_t M, const double* mean, cons
     if (out == nullptr) return -5;
     gabo::ei_kernel<<<(unsigned)gabo::ceil_div64(M, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(M, mean, var, fmin, out);
     GABO_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- profiling hook (see namespace prof above) ---------------------------------------------------------------------
+extern "C" int gabo_profile_trailing_updates(int enable) {
+    for (auto& r : gabo::prof::g_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    gabo::prof::g_recs.clear();
+    gabo::prof::g_enabled = (enable != 0);
+    return 0;
+}
+// Sums over the recorded U2 launches since the hook was enabled (synchronises on their events): number of launches,
+// total device milliseconds, total algorithmic flops (2 * 128 * 64 * 512 per lower tile), duration of the longest one.
+extern "C" int gabo_profile_trailing_read(int64_t* launches, double* total_ms, double* total_flops, double* max_ms,
+                                          double* max_flops) {
+    int64_t n = 0; double ms = 0.0, fl = 0.0, mx = 0.0, mxf = 0.0;
+    for (auto& r : gabo::prof::g_recs) {
+        GABO_CUDA_TRY(cudaEventSynchronize(r.e1));
+        float t = 0.f;
+        GABO_CUDA_TRY(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ++n; ms += t; fl += r.flops;
+        if (t > mx) { mx = t; mxf = r.flops; }
+    }
+    if (launches) *launches = n;
+    if (total_ms) *total_ms = ms;
+    if (total_flops) *total_flops = fl;
+    if (max_ms) *max_ms = mx;
+    if (max_flops) *max_flops = mxf;
     return 0;
 }

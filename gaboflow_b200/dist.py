@@ -74,9 +74,14 @@ class CudaLocalOps:
         return ops.potrf_(A, sigma2, check=False)
 
     @staticmethod
-    def trsm_right_(A, L):
+    def potrf_diag_(A, sigma2, winv_all):
         from . import ops
-        return ops.trsm_right_(A, L)
+        return ops.potrf_diag_(A, sigma2, winv_all)
+
+    @staticmethod
+    def trsm_right_(A, L, winv_all=None):
+        from . import ops
+        return ops.trsm_right_(A, L, winv_all)
 
     @staticmethod
     def syrk_cyclic_(C, A, B, row_base, col_base, nb, world, rank):
@@ -117,61 +122,125 @@ def gram_block_cyclic(gram_rows, layout: BlockCyclic, out: Optional[torch.Tensor
 
 
 def potrf_block_cyclic_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: float, n_factor: Optional[int] = None,
-                        local=CudaLocalOps, group=None) -> int:
+                        local=CudaLocalOps, group=None, lookahead: bool = False) -> int:
     """In-place distributed Cholesky of the leading n_factor x n_factor block (default: everything) of the symmetric
     matrix whose lower triangle is stored block-cyclically in A_loc [local_rows, >= n_factor].  Returns LAPACK-style info
-    (0, or the order of the first non-positive-definite leading minor), identical on every rank."""
+    (0, or the order of the first non-positive-definite leading minor), identical on every rank.
+
+    Right-looking over panels; the trailing update is split into U1 (next block column) and U2 (the rest).  With
+    ``lookahead=True`` the next panel's factorisation / broadcast / row solve / all-gather run on a high-priority side
+    stream while the main stream runs U2.  Measured on 2 x B200 this does NOT pay yet (258 ms without, 266-288 ms with):
+    NCCL's collective CTAs need a whole SM's registers and starve behind the 2-CTA/SM update kernel, so the default is
+    off; the fix is copy-engine transfers through the CUDA-IPC peer buffers.  On CPU tensors (gloo tests)
+    the same steps run in order."""
     W, rank, nb = layout.world, layout.rank, layout.nb
     n = layout.n if n_factor is None else n_factor
     if n % nb != 0 and n != layout.n:
         raise ValueError('n_factor must be a multiple of the panel size')
     npan = (n + nb - 1) // nb
     dev = A_loc.device
-    Lkk = torch.empty((nb, nb), dtype=A_loc.dtype, device=dev)
-    first_bad = torch.full((1,), 2 ** 62, dtype=torch.int64, device=dev)
-    # local rows that belong to the factored block: panels p < npan
+    dt = A_loc.dtype
+    nwb = (nb + 127) // 128
+    use_streams = bool(A_loc.is_cuda and lookahead and npan > 1)
+    main = torch.cuda.current_stream(dev) if A_loc.is_cuda else None
+    side = torch.cuda.Stream(device=dev, priority=-1) if use_streams else main
     my = [p for p in layout.my_panels() if p < npan]
     rows_f = sum(min(nb, n - p * nb) for p in my)
-    for kp in range(npan):
+    maxslots = (npan + W - 1) // W
+    # double-buffered communication buffers (panel k+1 is produced while panel k is still being consumed)
+    bc = [torch.empty((nb * nb + nwb * 128 * 128,), dtype=dt, device=dev) for _ in range(2)]   # factor + block inverses
+    send = [torch.zeros((maxslots * nb, nb), dtype=dt, device=dev) for _ in range(2)] if W > 1 else None
+    recv = [torch.empty((W, maxslots * nb, nb), dtype=dt, device=dev) for _ in range(2)] if W > 1 else None
+    first_bad = torch.full((1,), 2 ** 62, dtype=torch.int64, device=dev)
+
+    class _Ctx:
+        def __init__(self, stream):
+            self.stream = stream
+
+        def __enter__(self):
+            if A_loc.is_cuda:
+                self.cm = torch.cuda.stream(self.stream)
+                self.cm.__enter__()
+
+        def __exit__(self, *a):
+            if A_loc.is_cuda:
+                self.cm.__exit__(*a)
+
+    def panel(kp):
+        """Factor block column kp for all rows (runs on the side stream).  Returns the gathered block column below the
+        diagonal block in global row order (or a local view when W == 1), the first local row below, the local row count."""
+        nonlocal first_bad
+        b = kp % 2
         k0 = kp * nb
         kb = min(nb, n - k0)
         k1 = k0 + kb
         owner = layout.owner(kp)
+        Lkk = bc[b][: nb * nb].view(nb, nb)
+        Wv = bc[b][nb * nb:].view(nwb, 128, 128)
         if rank == owner:
-            s = layout.slot(kp)
-            blk = A_loc[s * nb: s * nb + kb, k0:k1]
-            info = local.potrf_(blk, sigma2)
+            sl = layout.slot(kp)
+            blk = A_loc[sl * nb: sl * nb + kb, k0:k1]
+            info = local.potrf_diag_(blk, sigma2, Wv)
             bad = info.to(torch.int64)
             first_bad = torch.minimum(first_bad, torch.where(bad > 0, bad + k0, torch.full_like(bad, 2 ** 62)))
             Lkk[:kb, :kb].copy_(blk)
         if W > 1:
-            dist.broadcast(Lkk, src=owner, group=group)
+            dist.broadcast(bc[b], src=owner, group=group)
         if k1 >= n:
-            break
+            return None, rows_f, 0
         s0 = layout.slots_after(kp)
         lr0 = s0 * nb
         m = rows_f - lr0
         if m > 0:
-            local.trsm_right_(A_loc[lr0:rows_f, k0:k1], Lkk[:kb, :kb])
-        # all-gather the block column below the diagonal block, in global row order
-        nbelow = npan - (kp + 1)                      # panels below
-        maxslots = (nbelow + W - 1) // W
-        if W > 1:
-            send = torch.zeros((maxslots * nb, kb), dtype=A_loc.dtype, device=dev)
-            if m > 0:
-                send[:m].copy_(A_loc[lr0:rows_f, k0:k1])
-            recv = torch.empty((W, maxslots * nb, kb), dtype=A_loc.dtype, device=dev)
-            dist.all_gather_into_tensor(recv.view(-1, kb), send, group=group)
-            # panel kp+1+t sits on rank (kp+1+t) % W, relative slot t // W
-            shift = (kp + 1) % W
-            order = [(shift + i) % W for i in range(W)]
-            P = recv[order].view(W, maxslots, nb, kb).permute(1, 0, 2, 3).reshape(-1, kb)[: n - k1]
-            if not P.is_contiguous():
-                P = P.contiguous()
-        else:
-            P = A_loc[lr0:rows_f, k0:k1]
+            local.trsm_right_(A_loc[lr0:rows_f, k0:k1], Lkk[:kb, :kb], Wv)
+        if W == 1:
+            return A_loc[lr0:rows_f, k0:k1], lr0, m
+        nbelow = npan - (kp + 1)
+        ms = (nbelow + W - 1) // W
+        snd = send[b][: ms * nb, :kb]
         if m > 0:
-            local.syrk_cyclic_(A_loc[lr0:rows_f, k1:n], A_loc[lr0:rows_f, k0:k1], P, s0 * W * nb, k1, nb, W, rank)
+            snd[:m].copy_(A_loc[lr0:rows_f, k0:k1])
+        if m < ms * nb:
+            snd[m:].zero_()
+        rcv = recv[b].view(-1)[: W * ms * nb * kb].view(W, ms * nb, kb)
+        dist.all_gather_into_tensor(rcv.view(-1, kb), snd.contiguous() if not snd.is_contiguous() else snd, group=group)
+        # panel kp+1+t sits on rank (kp+1+t) % W, relative slot t // W
+        shift = (kp + 1) % W
+        order = [(shift + i) % W for i in range(W)]
+        P = rcv[order].view(W, ms, nb, kb).permute(1, 0, 2, 3).reshape(-1, kb)[: n - k1]
+        return P.contiguous(), lr0, m
+
+    ev_panel = torch.cuda.Event() if use_streams else None
+    ev_u1 = torch.cuda.Event() if use_streams else None
+    if use_streams:
+        side.wait_stream(main)
+    with _Ctx(side):
+        cur = panel(0)
+        if use_streams:
+            ev_panel.record(side)
+    for kp in range(npan - 1):
+        k0 = kp * nb
+        k1 = k0 + nb
+        k2 = min(k1 + nb, n)
+        P, lr0, m = cur
+        if use_streams:
+            main.wait_event(ev_panel)           # block column kp factored, solved and gathered
+        # U1: the next block column only (lower part, mask in global coordinates)
+        if m > 0:
+            local.syrk_cyclic_(A_loc[lr0:rows_f, k1:k2], A_loc[lr0:rows_f, k0:k1], P[: k2 - k1], (lr0 // nb) * W * nb, k1, nb, W, rank)
+        if use_streams:
+            ev_u1.record(main)
+            side.wait_event(ev_u1)
+        with _Ctx(side):
+            nxt = panel(kp + 1)
+            if use_streams:
+                ev_panel.record(side)
+        # U2: everything to the right of the next block column
+        if m > 0 and k2 < n:
+            local.syrk_cyclic_(A_loc[lr0:rows_f, k2:n], A_loc[lr0:rows_f, k0:k1], P[k2 - k1:], (lr0 // nb) * W * nb, k2, nb, W, rank)
+        cur = nxt
+    if use_streams:
+        main.wait_stream(side)
     if W > 1:
         dist.all_reduce(first_bad, op=dist.ReduceOp.MIN, group=group)
     fb = int(first_bad.item())

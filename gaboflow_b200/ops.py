@@ -173,7 +173,7 @@ def potrf_(A: torch.Tensor, sigma2: float = 0.0, check: bool = True) -> torch.Te
     n = int(A.shape[0])
     L = _lib.lib()
     nbytes = int(L.gabo_potrf_workspace_bytes(n))
-    key = (A.device.index, 'potrf')
+    key = (A.device.index, 'potrf', torch.cuda.current_stream().cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=A.device)
@@ -198,7 +198,7 @@ def trsm_(L_: torch.Tensor, B: torch.Tensor, trans: bool = False) -> torch.Tenso
         raise ValueError('B must be a row-major [n, nrhs] tensor')
     Lh = _lib.lib()
     nbytes = int(Lh.gabo_trsm_workspace_bytes(n, int(B.shape[1])))
-    key = (L_.device.index, 'trsm')
+    key = (L_.device.index, 'trsm', torch.cuda.current_stream().cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=L_.device)
@@ -262,21 +262,45 @@ def _ldm(t: torch.Tensor) -> int:
     return max(int(t.stride(0)), int(t.shape[1])) if t.shape[0] > 1 else max(int(t.shape[1]), int(t.stride(0)))
 
 
-def trsm_right_(A: torch.Tensor, L_: torch.Tensor) -> torch.Tensor:
-    """A[m, nb] <- A L^-T in place (L lower nb x nb)."""
+def potrf_diag_(A: torch.Tensor, sigma2: float, winv_all: torch.Tensor) -> torch.Tensor:
+    """Factor one diagonal block (nb <= 512) in place and write the inverses of its 128 x 128 diagonal blocks into
+    winv_all [ceil(nb/128), 128, 128].  Returns the device info word."""
+    _req(A, 'A'); _req(winv_all, 'winv_all')
+    nb = int(A.shape[0])
+    Lh = _lib.lib()
+    nbytes = int(Lh.gabo_potrf_workspace_bytes(nb))
+    key = (A.device.index, 'potrf_diag', torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=A.device)
+        _ws_cache[key] = ws
+    info = torch.zeros((1,), dtype=torch.int32, device=A.device)
+    st = Lh.gabo_potrf_diag_f64(nb, A.data_ptr(), _ldm(A), float(sigma2), info.data_ptr(), winv_all.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _stream())
+    _lib.check('gabo_potrf_diag_f64', st)
+    return info
+
+
+def trsm_right_(A: torch.Tensor, L_: torch.Tensor, winv_all: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A[m, nb] <- A L^-T in place (L lower nb x nb); winv_all = inverses of L's 128 x 128 diagonal blocks if known."""
     _req(A, 'A'); _req(L_, 'L')
     m, nb = int(A.shape[0]), int(A.shape[1])
     if m == 0 or nb == 0:
         return A
     Lh = _lib.lib()
-    nbytes = int(Lh.gabo_trsm_right_workspace_bytes(nb))
-    key = (A.device.index, 'trsm_right')
+    nbytes = int(Lh.gabo_trsm_right_workspace_bytes(m, nb))
+    key = (A.device.index, 'trsm_right', torch.cuda.current_stream().cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=A.device)
         _ws_cache[key] = ws
-    st = Lh.gabo_trsm_right_f64(m, nb, L_.data_ptr(), _ldm(L_), A.data_ptr(), _ldm(A), ws.data_ptr(), ws.numel(), _stream())
-    _lib.check('gabo_trsm_right_f64', st)
+    if winv_all is not None:
+        st = Lh.gabo_trsm_right_winv_f64(m, nb, L_.data_ptr(), _ldm(L_), winv_all.data_ptr(), A.data_ptr(), _ldm(A),
+                                         ws.data_ptr(), ws.numel(), _stream())
+        _lib.check('gabo_trsm_right_winv_f64', st)
+    else:
+        st = Lh.gabo_trsm_right_f64(m, nb, L_.data_ptr(), _ldm(L_), A.data_ptr(), _ldm(A), ws.data_ptr(), ws.numel(), _stream())
+        _lib.check('gabo_trsm_right_f64', st)
     return A
 
 

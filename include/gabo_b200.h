@@ -156,6 +156,12 @@ int gabo_gemm_nt_sub_f64(int64_t m, int64_t n, int64_t k, const double* A, int64
 int gabo_expected_improvement_f64(int64_t M, const double* mean, const double* var, double fmin, double* out,
                                   gabo_stream_t stream);
 
+/* Diagnostic: in-situ timing of the dominant kernel.  gabo_profile_trailing_updates(1) makes gabo_potrf_f64 bracket each big
+ * trailing-update launch (gemm_kernel, k = 512) with CUDA events on its stream; gabo_profile_trailing_read sums them
+ * (launch count, device ms, algorithmic flops, and the longest launch); (0) switches it off and drops the records. */
+int gabo_profile_trailing_updates(int enable);
+int gabo_profile_trailing_read(int64_t* launches, double* total_ms, double* total_flops, double* max_ms, double* max_flops);
+
 /* ---- Building blocks of the multi-GPU factorisation (1-D block-cyclic by row panels) --------
  * The host side (gaboflow_b200/dist.py) broadcasts the factored diagonal block and all-gathers the panel over NCCL;
  * these calls do the local work of each rank.
@@ -171,7 +177,7 @@ int gabo_shared_free(void* ptr);
 int gabo_ipc_export(void* ptr, unsigned char* handle64);
 int gabo_ipc_open(const unsigned char* handle64, void** out);
 int gabo_ipc_close(void* ptr);
-size_t gabo_trsm_right_workspace_bytes(int64_t nb);
+size_t gabo_trsm_right_workspace_bytes(int64_t m, int64_t nb);
 /* gabo_points_gram_cyclic_f64: symmetric Gram K(X,X) distributed by 512-row panels, 1-D block-cyclic (panel P on rank
  *   P % world, local slot P / world), with the symmetry exploited ACROSS GPUs: this rank computes only the lower tiles
  *   of its own row panels and stores every off-diagonal tile's mirror image directly into the HBM of the rank owning
@@ -184,6 +190,13 @@ int gabo_points_gram_cyclic_f64(int kind, const double* X, int64_t n, int64_t ld
                                 void* workspace, size_t workspace_bytes, gabo_stream_t stream);
 int gabo_trsm_right_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, double* A, int64_t lda,
                         void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+/* gabo_potrf_diag_f64: factor one diagonal block (nb <= 512) in place AND return the inverses of its 128 x 128 diagonal
+ *   blocks, Winv_all [ceil(nb/128)][128][128]; the owner of a panel broadcasts factor + inverses, so that
+ * gabo_trsm_right_winv_f64 (same as gabo_trsm_right_f64 with the inverses supplied) has no inversion on its path. */
+int gabo_potrf_diag_f64(int64_t nb, double* A, int64_t lda, double sigma2, int32_t* info, double* Winv_all,
+                        void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+int gabo_trsm_right_winv_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, const double* Winv_all,
+                             double* A, int64_t lda, void* workspace, size_t workspace_bytes, gabo_stream_t stream);
 /* gabo_syrk_cyclic_f64: C[m,n] -= A[m,k] B[n,k]^T restricted to GLOBAL col <= GLOBAL row, where local row r of C is
  *   global row row_base + ((r / cyc_nb) * cyc_world + cyc_rank) * cyc_nb + r % cyc_nb (cyc_nb == 0: row_base + r) and
  *   local column c is global column col_base + c. */

@@ -25,7 +25,11 @@ class TorchCpuLocalOps:
         return info.to(torch.int32).reshape(1)
 
     @staticmethod
-    def trsm_right_(A, L):
+    def potrf_diag_(A, sigma2, winv_all):
+        return TorchCpuLocalOps.potrf_(A, sigma2)
+
+    @staticmethod
+    def trsm_right_(A, L, winv_all=None):
         A.copy_(torch.linalg.solve_triangular(torch.tril(L), A.T.contiguous(), upper=False).T)
         return A
 
