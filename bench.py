@@ -93,11 +93,15 @@ class ClockSampler:
 def cpu_reference_sample(n_gram, n_chol_sample=8192, gram_rows=2048, n_chol_metric=32768):
     """The reference math on the host cores (NumPy/OpenBLAS oracle port), bounded sample of the bench workload."""
     from oracle import gabo_oracle as orc   # the ONE place bench.py executes oracle/: the CPU baseline
+    # all the host threads the BLAS can use (torchrun exports OMP_NUM_THREADS=1, which would make this arm single-threaded)
+    want = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_info, threadpool_limits
+        _limit = threadpool_limits(limits=want)
         cores = max([p.get('num_threads', 1) for p in threadpool_info()] + [1])
     except Exception:
-        cores = os.cpu_count() or 1
+        _limit = None
+        cores = 1
     X = synth_sphere(n_gram, DIM, SEED_X)
     rows = min(gram_rows, n_gram)
     t0 = time.perf_counter()

@@ -1,0 +1,104 @@
+"""GPU: edge cases of the boundary -- strided views, leading dimensions, FP32 variants, Kdiag of every kernel class,
+constant mean, factor on a sub-view (what bench.py does with the leading block of a larger Gram)."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+import torch
+
+from oracle import gabo_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_strided_inputs_and_outputs(cuda):
+    from gaboflow_b200 import ops
+    X = orc.synth_sphere(300, 51, seed=1)
+    X2 = orc.synth_sphere(200, 51, seed=2)
+    big = torch.zeros((300, 64), dtype=torch.float64, device='cuda')
+    big[:, :51] = torch.from_numpy(X).cuda()
+    big2 = torch.zeros((200, 70), dtype=torch.float64, device='cuda')
+    big2[:, 3:54] = torch.from_numpy(X2).cuda()
+    out_big = torch.full((300, 333), -7.0, dtype=torch.float64, device='cuda')
+    ops.points_gram(ops.SPHERE_GAUSSIAN, big[:, :51], big2[:, 3:54], beta=2.0, out=out_big[:, 5:205])   # odd offset: scalar stores
+    ref = orc.sphere_gaussian_K(X, X2, beta=2.0)
+    got = out_big.cpu().numpy()
+    assert np.max(np.abs(got[:, 5:205] / ref - 1)) < 1e-12
+    assert np.all(got[:, :5] == -7.0) and np.all(got[:, 205:] == -7.0)
+
+
+def test_fp32_variants(cuda):
+    from gaboflow_b200 import ops
+    X = orc.synth_sphere(257, 51, seed=3).astype(np.float32)
+    Xd = torch.from_numpy(X).cuda()
+    Kl = ops.points_gram(ops.SPHERE_LAPLACE, Xd, None, beta=2.0, variance=0.5, uplo='lower').cpu().numpy()
+    ref = orc.sphere_laplace_K(X.astype(np.float64), beta=2.0, variance=0.5)
+    low = np.tril(np.ones_like(ref, dtype=bool), -1)
+    assert np.max(np.abs(Kl[low] / ref[low] - 1)) < 1e-5
+    F = np.random.default_rng(4).standard_normal((190, 21)).astype(np.float32)
+    Ks = ops.points_gram(ops.SQDIST_GAUSSIAN, torch.from_numpy(F).cuda(), None, beta=0.05).cpu().numpy()
+    d2 = ((F[:, None, :].astype(np.float64) - F[None, :, :]) ** 2).sum(-1)
+    assert np.max(np.abs(Ks - np.exp(-0.05 * d2))) < 2e-5
+    assert np.all(np.diag(Ks) == 1.0)
+
+
+def test_kdiag_every_kernel(cuda):
+    from gaboflow_b200 import (SphereGaussianKernel, SphereLaplaceKernel, SpdSteinGaussianKernel,
+                               SpdAffineInvariantGaussianKernel, SpdAffineInvariantLaplaceKernel,
+                               SpdFrobeniusGaussianKernel, SpdLogEuclideanGaussianKernel)
+    Xs = orc.synth_sphere(33, 3, seed=5)
+    for k in (SphereGaussianKernel(3, range(3), beta_min=6.5, variance=1.7), SphereLaplaceKernel(3, range(3), variance=1.7)):
+        assert np.array_equal(k.compute_Kdiag(Xs), np.full(33, 1.7))
+    Xm = orc.synth_spd_mandel(33, 3, seed=6)
+    for cls in (SpdAffineInvariantLaplaceKernel, SpdFrobeniusGaussianKernel, SpdLogEuclideanGaussianKernel):
+        assert np.array_equal(cls(6, range(6), variance=0.3).compute_Kdiag(Xm), np.full(33, 0.3))
+    assert np.array_equal(SpdAffineInvariantGaussianKernel(6, range(6), beta_min=0.5, variance=0.3).compute_Kdiag(Xm), np.full(33, 0.3))
+    ks = SpdSteinGaussianKernel(6, range(6), beta=1.5, variance=0.3)
+    assert np.max(np.abs(ks.compute_Kdiag(Xm) / np.diag(orc.spd_stein_K(Xm, beta=1.5, variance=0.3)) - 1)) < 1e-12
+    assert np.max(np.abs(ks.compute_Kdiag(Xm) / np.diag(ks.compute_K_symm(Xm)) - 1)) < 1e-12
+
+
+def test_gpr_constant_mean_and_two_outputs(cuda):
+    from gaboflow_b200 import GPR, SphereGaussianKernel, Constant
+    n = 400
+    X = orc.synth_sphere(n, 5, seed=7)
+    Y = np.random.default_rng(8).standard_normal((n, 2)) + 3.0
+    Xs = orc.synth_sphere(50, 5, seed=9)
+    k = SphereGaussianKernel(5, range(5), beta_min=1.0, beta=1.0, variance=1.2)
+    m = GPR(X, Y, kern=k, mean_function=Constant(3.0))
+    m.likelihood.variance = 0.1
+    K = orc.sphere_gaussian_K(X, beta=2.0, variance=1.2)
+    assert abs(m.compute_log_likelihood() / orc.gp_loglik(K, Y, 0.1, mean=3.0) - 1) < 1e-8
+    mean, var = m.predict_f(Xs)
+    mo, vo = orc.gp_predict(K, orc.sphere_gaussian_K(X, Xs, beta=2.0, variance=1.2), np.full(50, 1.2), Y, 0.1, mean=3.0)
+    assert mean.shape == (50, 2) and var.shape == (50, 2)
+    assert np.max(np.abs(mean - mo) / np.abs(mo)) < 1e-8
+    assert np.max(np.abs(var - vo) / np.abs(vo)) < 1e-8
+    ym, yv = m.predict_y(Xs)
+    assert np.allclose(yv, var + 0.1, rtol=1e-12)
+
+
+def test_potrf_on_leading_subview(cuda):
+    from gaboflow_b200 import ops
+    n, nc = 1500, 1024
+    G = np.random.default_rng(10).standard_normal((n, 700))
+    A = G @ G.T / 700 + np.eye(n)
+    d = torch.from_numpy(A).cuda()
+    keep = d.clone()
+    ops.potrf_(d[:nc, :nc], 0.5)
+    ref = sla.cholesky(A[:nc, :nc] + 0.5 * np.eye(nc), lower=True)
+    assert np.max(np.abs(np.tril(d[:nc, :nc].cpu().numpy()) - ref)) < 1e-12
+    assert torch.equal(d[nc:], keep[nc:]) and torch.equal(d[:nc, nc:], keep[:nc, nc:])
+
+
+def test_empty_and_tiny(cuda):
+    from gaboflow_b200 import ops, SpdAffineInvariantGaussianKernel
+    e = ops.spd_prep(torch.zeros((0, 6), dtype=torch.float64, device='cuda'), 3)
+    assert e.n == 0
+    k = SpdAffineInvariantGaussianKernel(3, range(3), beta_min=0.5)
+    one = orc.synth_spd_mandel(1, 2, seed=11)
+    assert k.compute_K_symm(one).tolist() == [[1.0]]
+    L = torch.tensor([[2.0]], dtype=torch.float64, device='cuda')
+    b = torch.tensor([[4.0]], dtype=torch.float64, device='cuda')
+    ops.potrf_(L, 0.0)
+    ops.trsm_(L, b)
+    assert abs(float(L.item()) - np.sqrt(2.0)) < 1e-15 and abs(float(b.item()) - 4.0 / np.sqrt(2.0)) < 1e-15
