@@ -117,7 +117,50 @@ class GPR(Parameterized):
         m, v = self.build_predict(Xnew, full_cov=False)
         return m.cpu().numpy(), (v + float(self.likelihood.variance)).cpu().numpy()
 
-    def optimize(self, *args, **kwargs):
-        raise NotImplementedError(
-            'hyper-parameter optimisation needs the analytic gradients of the path (SURVEY.md section 8f-1); '
-            'set parameters explicitly (kern.update_beta, kern.variance = ..., likelihood.variance = ...)')
+    # ---- hyper-parameter fitting ---------------------------------------------------------------------------
+    def _free_params(self):
+        ps = [(f'kern.{k}', v) for k, v in sorted(self.kern.params().items()) if not getattr(v, 'fixed', False)]
+        if not getattr(self.likelihood.variance, 'fixed', False):
+            ps.append(('likelihood.variance', self.likelihood.variance))
+        if isinstance(self.mean_function, Constant) and not getattr(self.mean_function.c, 'fixed', False):
+            ps.append(('mean_function.c', self.mean_function.c))
+        return ps
+
+    def optimize(self, method='L-BFGS-B', maxiter=1000, **kwargs):
+        """Maximise the log marginal likelihood over the free hyper-parameters, as ``GPR.optimize()`` of GPflow 0.5 does
+        with SciPy L-BFGS-B in the unconstrained (softplus) space (reference call sites: ``sphere_kernels.py:133``,
+        ``spd_kernels.py:155-187``).  Every objective evaluation runs on the GPU (Gram -> Cholesky -> solve -> log-lik);
+        gradients are finite differences until the analytic ones exist, which is affordable because
+        the models of the reference have 2-4 hyper-parameters.  Returns the SciPy result."""
+        from scipy.optimize import minimize
+        ps = self._free_params()
+        if not ps:
+            return None
+
+        def to_free(p):                      # inverse softplus for 'positive' Params (GPflow transforms.positive)
+            v = float(p)
+            if p.transform == 'positive':
+                v = max(v, 1e-12)
+                return v + np.log(-np.expm1(-v)) if v < 30 else v
+            return v
+
+        def from_free(p, x):
+            if p.transform == 'positive':
+                return float(np.logaddexp(0.0, x))
+            return float(x)
+
+        def set_all(x):
+            for (_, p), xi in zip(ps, x):
+                p.assign(from_free(p, xi))
+
+        def objective(x):
+            set_all(x)
+            try:
+                return -self.compute_log_likelihood()
+            except np.linalg.LinAlgError:     # non-PD Gram (e.g. beta below the PD threshold): reject the step
+                return 1e25
+
+        x0 = np.array([to_free(p) for _, p in ps], dtype=np.float64)
+        res = minimize(objective, x0, method=method, options={'maxiter': maxiter}, **kwargs)
+        set_all(res.x)
+        return res

@@ -150,3 +150,24 @@ def test_expected_improvement_vs_oracle(cuda, golden):
     got = acq.evaluate(cand)
     assert got.shape == (100, 1)
     assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-12)) < 1e-8
+
+
+def test_gpr_optimize_improves_and_matches_cpu_optimum(cuda, golden):
+    """m.optimize() (sphere_kernels.py:133): same optimum as L-BFGS-B over the oracle's log-likelihood."""
+    from scipy.optimize import minimize
+    from gaboflow_b200 import GPR, SphereGaussianKernel
+    g = golden['sphere_s2']
+    k = SphereGaussianKernel(input_dim=3, active_dims=range(3), beta_min=7.0, beta=10.0, variance=1.)
+    m = GPR(g['x_man'], g['y_train'], kern=k)
+    ll0 = m.compute_log_likelihood()
+    res = m.optimize()
+    ll1 = m.compute_log_likelihood()
+    assert ll1 > ll0 + 1.0 and abs(ll1 + res.fun) < 1e-9
+    assert float(k.beta_shifted) > 0 and float(k.variance) > 0 and float(m.likelihood.variance) > 0
+
+    sp = lambda x: np.logaddexp(0.0, x)
+    def nll(x):
+        return -orc.gp_loglik(orc.sphere_gaussian_K(g['x_man'], beta=sp(x[0]) + 7.0, variance=sp(x[1])), g['y_train'], sp(x[2]))
+    inv = lambda v: v + np.log(-np.expm1(-v))
+    ref = minimize(nll, [inv(10.0), inv(1.0), inv(1.0)], method='L-BFGS-B')
+    assert abs(ll1 - (-ref.fun)) < 1e-3 * abs(ref.fun)
