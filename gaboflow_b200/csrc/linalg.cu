@@ -18,7 +18,9 @@
 // parallel), after which forward/backward substitution is a chain of DMMA products (or of HBM-bound GEMV updates when
 // there are at most 4 right-hand sides).
 #include <vector>
+#include <cstdlib>
 #include "dgemm_core.cuh"
+#include "dgemm_tma.cuh"
 
 namespace gabo {
 
@@ -44,7 +46,14 @@ int launch_gemm(bool a_kmaj, bool b_kmaj, int64_t m, int64_t n, int64_t k, doubl
         GABO_CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
         gemm_kernel<AK, BK_><<<grid, GTHREADS, smem, stream>>>(p);                                                  \
     } while (0)
-    if (a_kmaj && b_kmaj) GABO_GEMM_LAUNCH(true, true);
+    if (a_kmaj && b_kmaj) {
+        static const bool use_tma = []() { const char* e = std::getenv("GABO_GEMM_TMA"); return !(e && e[0] == '0'); }();
+        if (use_tma) {   // hot case: TMA-fed, mbarrier-pipelined kernel; falls through when the operands do not qualify
+            const int rc = launch_gemm_nt_tma(p, grid, stream);
+            if (rc != GABO_TMA_NA) return rc;
+        }
+        GABO_GEMM_LAUNCH(true, true);
+    }
     else if (a_kmaj && !b_kmaj) GABO_GEMM_LAUNCH(true, false);
     else if (!a_kmaj && !b_kmaj) GABO_GEMM_LAUNCH(false, false);
     else GABO_GEMM_LAUNCH(false, true);
