@@ -33,7 +33,7 @@ SEED_X, SEED_Y = 20240, 20241
 BETA, VARIANCE, SIGMA2 = 2.0, 1.0, 1e-2
 DIM = 51
 FP64_PEAK_TFLOPS = 37.2                # measured on this pool: tools/fp64_probe.cu -> profiles/r01_fp64_probe.txt (DMMA.8x8x4)
-GEMM_DRAM_TRAFFIC_BYTES = 9.40e9        # ncu: dram__bytes_read 5.286 GB + write 4.115 GB for the m=32256, k=512 trailing update
+GEMM_DRAM_TRAFFIC_BYTES = 9.41e9        # ncu: dram__bytes_read 5.285 GB + write 4.128 GB for the m=32256, k=512 trailing update
 F_TR = 100                             # declared transcendental flops per sphere Gram entry
 
 
@@ -366,14 +366,14 @@ def run_ours(args):
                 'ms_per_step': e2e_total_ms / args.steps,
                 'api': 'pinned host X,y -> device, ops.points_gram / potrf_ / trsm_ / gp_loglik (C-ABI; gaboflow_b200.dist for N>1), loglik read back'},
         'roofline': {'bound': 'tensor',
-                     'kernel': 'gemm_kernel<true,true> (DMMA.8x8x4): the k=512 trailing updates inside gabo_potrf_f64, '
+                     'kernel': 'gemm_nt_tma_kernel (DMMA.8x8x4 fed by UTMALDG): the k=512 trailing updates inside gabo_potrf_f64, '
                                + ('%.0f%% of the step' % (100.0 * kern['total_ms'] / args.steps / (total_ms / args.steps)) if kern else 'dominant kernel'),
                      'achieved': kern['tflops_avg'] if kern else potrf_tflops,
                      'peak': FP64_PEAK_TFLOPS * world, 'unit': 'TFLOP/s',
                      'frac': ((kern['tflops_avg'] if kern else potrf_tflops) / (FP64_PEAK_TFLOPS * world)) if (kern or potrf_tflops) else None,
                      'traffic': GEMM_DRAM_TRAFFIC_BYTES if kern else None,
                      'traffic_note': 'dram read+write of ONE launch at m=32256, k=512 (the largest): ncu --set full, '
-                                     'profiles/r01_gemm_bench_shape_ncu.txt; algorithmic bytes of that launch 8.49e9',
+                                     'profiles/r01_gemm_tma_ncu.txt; algorithmic bytes of that launch 8.49e9',
                      'flops_per_launch': kern['flops_per_launch_avg'] if kern else NC ** 3 / 3,
                      'ms_per_launch': kern['ms_per_launch_avg'] if kern else None,
                      'launches_timed': kern['launches'] if kern else None,
