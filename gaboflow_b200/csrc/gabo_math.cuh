@@ -85,42 +85,44 @@ __device__ __forceinline__ double exp_neg_fast(double x, const double* __restric
 
 // ---- batched forms: N independent entries, straight-line (the compiler interleaves the N dependency chains), with ONE
 // warp vote per batch for the rare slow paths (a vote per entry is a scheduling barrier and serialises the chains).
+// Range tests are done on the high 32 bits with INTEGER compares: an FP64 compare (DSETP) or min/max occupies the same
+// FP64 pipe as the DFMAs and the DMMAs, and that pipe is what bounds the Gram kernel.
+__device__ __forceinline__ int hi_abs(double x) { return __double2hiint(x) & 0x7fffffff; }
+
+// acos(clamp(t, -1, 1)) for N values (the clamp of sphere_utils_tf.py:59 is part of the big-|t| slow path).
 template <int N>
-__device__ __forceinline__ void acos_fast_n(const double (&t)[N], double (&out)[N]) {
-    double z[N], w[N];
+__device__ __forceinline__ void acos_clamped_fast_n(const double (&t)[N], double (&out)[N]) {
+    double w[N];
     bool anybig = false;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const double a = fabs(t[i]);
-        const bool big = a > 0.5;
-        anybig = anybig || big;
-        z[i] = big ? fma(-0.5, a, 0.5) : t[i] * t[i];
-    }
+    for (int i = 0; i < N; ++i) anybig = anybig || (hi_abs(t[i]) > 0x3fe00000);     // |t| > 0.5 (or NaN)
 #pragma unroll
     for (int i = 0; i < N; ++i) w[i] = kAsinC[11];
 #pragma unroll
     for (int c = 10; c >= 0; --c)
 #pragma unroll
-        for (int i = 0; i < N; ++i) w[i] = fma(w[i], z[i], kAsinC[c]);
+        for (int i = 0; i < N; ++i) w[i] = fma(w[i], t[i] * t[i], kAsinC[c]);
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        w[i] *= z[i];
-        out[i] = (kExpC[10] - t[i]) - t[i] * w[i];           // pi/2 - asin(t), valid for |t| <= 0.5
-    }
+    for (int i = 0; i < N; ++i) out[i] = (kExpC[10] - t[i]) - t[i] * (w[i] * (t[i] * t[i]));   // pi/2 - asin(t), |t| <= 0.5
     if (__any_sync(0xffffffffu, anybig)) {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            if (fabs(t[i]) > 0.5) {
-                const double s = sqrt(z[i]);
-                const double h = fma(s, w[i], s);
-                out[i] = (t[i] > 0.0) ? 2.0 * h : fma(-2.0, h, kExpC[11]);
+            if (hi_abs(t[i]) > 0x3fe00000) {      // per-lane slow path: NO warp-level primitive may appear in here
+                const double tc = fmin(fmax(t[i], -1.0), 1.0);                 // sphere_utils_tf.py:59
+                const double z = fma(-0.5, fabs(tc), 0.5);
+                const double s = sqrt(z);
+                const double h = fma(s, asin_poly(z), s);                       // asin(sqrt((1-|t|)/2))
+                const double rb = (tc > 0.0) ? 2.0 * h : fma(-2.0, h, kExpC[11]);
+                out[i] = (t[i] == t[i]) ? rb : t[i];
             }
         }
     }
 }
 
+// exp(x) * scale for x <= 0; `tab` = shared-memory table 2^(j/32) ALREADY multiplied by `scale`.
 template <int N>
-__device__ __forceinline__ void exp_neg_fast_n(const double (&x)[N], double (&out)[N], const double* __restrict__ tab) {
+__device__ __forceinline__ void exp_neg_scaled_fast_n(const double (&x)[N], double (&out)[N], const double* __restrict__ tab,
+                                                      double scale) {
     double r[N], p[N];
     int n[N];
     bool anyslow = false;
@@ -131,7 +133,7 @@ __device__ __forceinline__ void exp_neg_fast_n(const double (&x)[N], double (&ou
         const double nf = tn - kExpC[0];
         r[i] = fma(nf, kExpC[3], fma(nf, kExpC[2], x[i]));
         p[i] = kExpC[4];
-        anyslow = anyslow || !(x[i] > -700.0);
+        anyslow = anyslow || (hi_abs(x[i]) >= 0x4085e000);      // |x| >= 700 (or NaN / inf)
     }
 #pragma unroll
     for (int c = 5; c <= 9; ++c)
@@ -146,8 +148,16 @@ __device__ __forceinline__ void exp_neg_fast_n(const double (&x)[N], double (&ou
     if (__any_sync(0xffffffffu, anyslow)) {
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            if (!(x[i] > -700.0)) out[i] = exp(x[i]);
+            if (hi_abs(x[i]) >= 0x4085e000) out[i] = scale * exp(x[i]);
     }
+}
+
+template <int N>
+__device__ __forceinline__ void acos_fast_n(const double (&t)[N], double (&out)[N]) { acos_clamped_fast_n<N>(t, out); }
+
+template <int N>
+__device__ __forceinline__ void exp_neg_fast_n(const double (&x)[N], double (&out)[N], const double* __restrict__ tab) {
+    exp_neg_scaled_fast_n<N>(x, out, tab, 1.0);
 }
 
 }  // namespace gabo

@@ -277,7 +277,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
     }
-    if (tid < 32) exptab[tid] = kExp2Tab[tid];
+    // kernel parameters used in the hot loop, once into registers (they were re-read with LDC inside the loop)
+    const double nbeta = -p.beta, variance = p.variance;
+    const int kind = p.kind;
+    const int64_t n2 = p.n2, ldk = p.ldk, row1 = p.row1;
+    const bool vec_ok = p.vec_ok != 0;
+    double* const Kbase = p.K;
+    if (tid < 32) exptab[tid] = kExp2Tab[tid] * variance;   // variance folded into the exp table: one DMUL less per entry
     __syncthreads();
 
     const int64_t my_tiles = (p.ntiles > (int64_t)blockIdx.x) ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
@@ -342,41 +348,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
             double na = 0.0;
             if (p.kind == GABO_SQDIST_GAUSSIAN) na = p.normA[grow];
             double v[8], arg[8];
-            if (p.kind == GABO_SQDIST_GAUSSIAN) {
+            if (kind == GABO_SQDIST_GAUSSIAN) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) arg[j] = -p.beta * fmax(fma(-2.0, c[j], na + nb[j]), 0.0);
+                for (int j = 0; j < 8; ++j) arg[j] = nbeta * fmax(fma(-2.0, c[j], na + nb[j]), 0.0);
             } else {
-                double tt[8], dd[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) tt[j] = fmin(fmax(c[j], -1.0), 1.0);      // sphere_utils_tf.py:59
-                acos_fast_n<8>(tt, dd);                                                // sphere_utils_tf.py:60
+                double dd[8];
+                acos_clamped_fast_n<8>(c, dd);                                         // sphere_utils_tf.py:59-60
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    arg[j] = -p.beta * ((p.kind == GABO_SPHERE_GAUSSIAN) ? dd[j] * dd[j] : dd[j]);   // kernels_sphere_tf.py:83-86, 199-202
+                    arg[j] = (kind == GABO_SPHERE_GAUSSIAN) ? (nbeta * dd[j]) * dd[j] : nbeta * dd[j];   // kernels_sphere_tf.py:83-86, 199-202
             }
-            exp_neg_fast_n<8>(arg, v, exptab);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] *= p.variance;                              // kernels_sphere_tf.py:88, 204
+            exp_neg_scaled_fast_n<8>(arg, v, exptab, variance);                        // kernels_sphere_tf.py:88, 204
             if (diag_tile) {   // K(X,X) diagonal is exactly `variance` (matches Kdiag, kernels_sphere_tf.py:105)
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (gcol0 + (j >> 1) * 8 + (j & 1) == grow) v[j] = p.variance;
+                    if (gcol0 + (j >> 1) * 8 + (j & 1) == grow) v[j] = variance;
             }
-            if (grow < p.row1) {
-                double* krow = p.K + (lrow_tile + wm * 32 + mi * 8 + g) * p.ldk;
+            if (grow < row1) {
+                double* krow = Kbase + (lrow_tile + wm * 32 + mi * 8 + g) * ldk;
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) {
                     const int64_t gcol = gcol0 + ni * 8;
-                    if (gcol + 1 < p.n2 && p.vec_ok) {
+                    if (gcol + 1 < n2 && vec_ok) {
                         st_cs_v2(krow + gcol, v[2 * ni], v[2 * ni + 1]);
                     } else {
-                        if (gcol < p.n2) st_cs(krow + gcol, v[2 * ni]);
-                        if (gcol + 1 < p.n2) st_cs(krow + gcol + 1, v[2 * ni + 1]);
+                        if (gcol < n2) st_cs(krow + gcol, v[2 * ni]);
+                        if (gcol + 1 < n2) st_cs(krow + gcol + 1, v[2 * ni + 1]);
                     }
                     if (mirror) {   // K[col][row] = K[row][col]; 8 lanes of equal q write 64 contiguous bytes (own HBM or a peer's over NVLink)
-                        double* km = kmir_base + (int64_t)(wn * 32 + ni * 8 + 2 * q) * p.ldk + grow;
+                        double* km = kmir_base + (int64_t)(wn * 32 + ni * 8 + 2 * q) * ldk + grow;
                         st_cs(km, v[2 * ni]);
-                        st_cs(km + p.ldk, v[2 * ni + 1]);
+                        st_cs(km + ldk, v[2 * ni + 1]);
                     }
                 }
             }
