@@ -123,7 +123,15 @@ __device__ __forceinline__ void tridiag_ql_eigvals(double (&A)[D][D], double (&d
     d[D - 1] = A[D - 1][D - 1];
     e[D - 1] = 0.0;
 
-    const double EPS = 2e-15;   // neglected coupling: |delta lambda| <= EPS * 2 lambda, far inside the 1e-12 budget
+    // Convergence tests on the exponents with INTEGER arithmetic (an FP64 compare occupies the FP64 pipe that bounds this
+    // kernel): e is negligible against its neighbours when exponent(e) + 49 <= exponent(max(|d_i|, |d_i+1|)), i.e.
+    // |e| < 2^-48 * max(...) ~ 3.6e-15 * max: neglected coupling far inside the 1e-12 budget.  (hi word >> 20 = exponent.)
+    auto negligible = [](double ee, double da, double db) {
+        const int he = __double2hiint(ee) & 0x7fffffff;
+        const int ha = __double2hiint(da) & 0x7fffffff, hb = __double2hiint(db) & 0x7fffffff;
+        const int hm = ha > hb ? ha : hb;
+        return he + (49 << 20) <= hm;
+    };
 #pragma unroll
     for (int l = 0; l < D - 1; ++l) {
         for (int iter = 0; iter < 40; ++iter) {
@@ -131,7 +139,7 @@ __device__ __forceinline__ void tridiag_ql_eigvals(double (&A)[D][D], double (&d
             int m = D - 1;
 #pragma unroll
             for (int mm = D - 2; mm >= l; --mm)
-                if (fabs(e[mm]) <= EPS * (fabs(d[mm]) + fabs(d[mm + 1]))) m = mm;
+                if (negligible(e[mm], d[mm], d[mm + 1])) m = mm;
             if (m == l) break;
             double dm = d[D - 1];
 #pragma unroll
@@ -149,7 +157,7 @@ __device__ __forceinline__ void tridiag_ql_eigvals(double (&A)[D][D], double (&d
                 if (i < m && !aborted) {
                     const double f = s * e[i], b = c * e[i];
                     const double h2 = fma(f, f, g * g);
-                    if (h2 == 0.0) {
+                    if (((__double2hiint(h2) & 0x7fffffff) | __double2loint(h2)) == 0) {
                         d[i + 1] -= p;
                         aborted = true;
                     } else {
