@@ -382,7 +382,7 @@ def run_ours(args):
                             '(gabo_profile_trailing_updates); flops = 2*128*64*512 per lower tile',
                      'peak_source': 'FP64 tensor peak is not in MEASURED_PEAKS.json: measured on this pool with tools/fp64_probe.cu '
                                     '(profiles/r01_fp64_probe.txt, DMMA 37.2 TFLOP/s; cuBLAS DGEMM 36.2)'},
-        'roofline_gram': {'bound': 'fp64', 'kernel': 'points_gram_kernel<52>', 'achieved': gram_flops / (gram_ms * 1e-3) * 1e-12,
+        'roofline_gram': {'bound': 'fp64', 'kernel': 'points_gram_kernel_1c<52> (DMMA inner products + fused acos/exp epilogue)', 'achieved': gram_flops / (gram_ms * 1e-3) * 1e-12,
                           'peak': FP64_PEAK_TFLOPS * world, 'unit': 'TFLOP/s',
                           'frac': gram_flops / (gram_ms * 1e-3) * 1e-12 / (FP64_PEAK_TFLOPS * world),
                           'hbm_write_gbs_per_gpu': rows * N * 8 / (gram_ms * 1e-3) * 1e-9, 'hbm_peak_gbs': hbm_peak, 'hbm_peak_source': hbm_src,
