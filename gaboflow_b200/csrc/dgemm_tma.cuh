@@ -18,14 +18,14 @@ namespace gabo {
 
 constexpr int GABO_TMA_NA = -999;
 constexpr int TBK = 16;                 // k per stage
-constexpr int TSTAGES = 4;
+constexpr int TSTAGES = 3;
 constexpr int TBOX = TBK / 4;           // boxes of 4 k per operand and stage
 constexpr int T_CONSUMERS = 8;          // consumer warps
 constexpr int T_THREADS = (T_CONSUMERS + 1) * 32;
 constexpr int T_A_DOUBLES = GTM * TBK;  // 2048
 constexpr int T_B_DOUBLES = GTN * TBK;  // 1024
 constexpr int T_STAGE_DOUBLES = T_A_DOUBLES + T_B_DOUBLES;
-constexpr size_t T_SMEM_BYTES = (size_t)TSTAGES * T_STAGE_DOUBLES * sizeof(double) + 128;   // 98,432
+constexpr size_t T_SMEM_BYTES = (size_t)TSTAGES * T_STAGE_DOUBLES * sizeof(double) + 128;   // 73,856: small enough that potf2 (133 KB) fits beside one resident CTA
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(

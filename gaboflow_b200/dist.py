@@ -128,11 +128,11 @@ def potrf_block_cyclic_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: float,
     (0, or the order of the first non-positive-definite leading minor), identical on every rank.
 
     Right-looking over panels; the trailing update is split into U1 (next block column) and U2 (the rest).  With
-    ``lookahead=True`` the next panel's factorisation / broadcast / row solve / all-gather run on a high-priority side
-    stream while the main stream runs U2.  Measured on 2 x B200 this does NOT pay yet (258 ms without, 266-288 ms with):
-    NCCL's collective CTAs need a whole SM's registers and starve behind the 2-CTA/SM update kernel, so the default is
-    off; the fix is copy-engine transfers through the CUDA-IPC peer buffers.  On CPU tensors (gloo tests)
-    the same steps run in order."""
+    ``lookahead=True`` the compute-only parts of the next panel (diagonal factorisation on the owner, row solve on every
+    rank) run on a high-priority side stream under the two halves of U2, and the two collectives are issued on the main
+    stream between / after those halves.  (A first version that also ran the collectives on the side stream was slower
+    than no look-ahead: NCCL's CTAs need a whole SM's registers and starve behind the 2-CTA/SM update kernel.)  On CPU
+    tensors (gloo tests) the same steps run in order."""
     W, rank, nb = layout.world, layout.rank, layout.nb
     n = layout.n if n_factor is None else n_factor
     if n % nb != 0 and n != layout.n:
@@ -166,79 +166,119 @@ def potrf_block_cyclic_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: float,
             if A_loc.is_cuda:
                 self.cm.__exit__(*a)
 
-    def panel(kp):
-        """Factor block column kp for all rows (runs on the side stream).  Returns the gathered block column below the
-        diagonal block in global row order (or a local view when W == 1), the first local row below, the local row count."""
+    # ---- the panel of block column kp in three pieces -------------------------------------------------------------
+    #   diag(kp)    owner factors the diagonal block (+ inverses of its 128-blocks)        compute only
+    #   bcast(kp)   NCCL broadcast of factor + inverses                                     collective
+    #   solve(kp)   every rank solves its rows of the block column, packs the send buffer   compute only
+    #   gather(kp)  NCCL all-gather + reorder into global row order                         collective
+    # With look-ahead the compute-only pieces run on a high-priority side stream while the main stream updates the trailing
+    # matrix; the collectives are issued on the MAIN stream between the two halves of that update: NCCL's CTAs need a
+    # whole SM's registers and starve behind the 2-CTA/SM update kernel when issued concurrently (measured).
+    def diag(kp):
         nonlocal first_bad
         b = kp % 2
         k0 = kp * nb
         kb = min(nb, n - k0)
-        k1 = k0 + kb
-        owner = layout.owner(kp)
-        Lkk = bc[b][: nb * nb].view(nb, nb)
-        Wv = bc[b][nb * nb:].view(nwb, 128, 128)
-        if rank == owner:
+        if rank == layout.owner(kp):
+            Lkk = bc[b][: nb * nb].view(nb, nb)
+            Wv = bc[b][nb * nb:].view(nwb, 128, 128)
             sl = layout.slot(kp)
-            blk = A_loc[sl * nb: sl * nb + kb, k0:k1]
+            blk = A_loc[sl * nb: sl * nb + kb, k0:k0 + kb]
             info = local.potrf_diag_(blk, sigma2, Wv)
             bad = info.to(torch.int64)
             first_bad = torch.minimum(first_bad, torch.where(bad > 0, bad + k0, torch.full_like(bad, 2 ** 62)))
             Lkk[:kb, :kb].copy_(blk)
+
+    def bcast(kp):
         if W > 1:
-            dist.broadcast(bc[b], src=owner, group=group)
+            dist.broadcast(bc[kp % 2], src=layout.owner(kp), group=group)
+
+    def solve(kp):
+        b = kp % 2
+        k0 = kp * nb
+        kb = min(nb, n - k0)
+        k1 = k0 + kb
         if k1 >= n:
-            return None, rows_f, 0
-        s0 = layout.slots_after(kp)
-        lr0 = s0 * nb
+            return
+        Lkk = bc[b][: nb * nb].view(nb, nb)
+        Wv = bc[b][nb * nb:].view(nwb, 128, 128)
+        lr0 = layout.slots_after(kp) * nb
         m = rows_f - lr0
         if m > 0:
             local.trsm_right_(A_loc[lr0:rows_f, k0:k1], Lkk[:kb, :kb], Wv)
+        if W > 1:
+            ms = (npan - (kp + 1) + W - 1) // W
+            snd = send[b][: ms * nb, :kb]
+            if m > 0:
+                snd[:m].copy_(A_loc[lr0:rows_f, k0:k1])
+            if m < ms * nb:
+                snd[m:].zero_()
+
+    def gather(kp):
+        """Returns (P, lr0, m): the block column below the diagonal block in global row order, the first local row below
+        it and the number of local rows below it."""
+        b = kp % 2
+        k0 = kp * nb
+        kb = min(nb, n - k0)
+        k1 = k0 + kb
+        if k1 >= n:
+            return None, rows_f, 0
+        lr0 = layout.slots_after(kp) * nb
+        m = rows_f - lr0
         if W == 1:
             return A_loc[lr0:rows_f, k0:k1], lr0, m
-        nbelow = npan - (kp + 1)
-        ms = (nbelow + W - 1) // W
+        ms = (npan - (kp + 1) + W - 1) // W
         snd = send[b][: ms * nb, :kb]
-        if m > 0:
-            snd[:m].copy_(A_loc[lr0:rows_f, k0:k1])
-        if m < ms * nb:
-            snd[m:].zero_()
         rcv = recv[b].view(-1)[: W * ms * nb * kb].view(W, ms * nb, kb)
-        dist.all_gather_into_tensor(rcv.view(-1, kb), snd.contiguous() if not snd.is_contiguous() else snd, group=group)
-        # panel kp+1+t sits on rank (kp+1+t) % W, relative slot t // W
-        shift = (kp + 1) % W
+        dist.all_gather_into_tensor(rcv.view(-1, kb), snd if snd.is_contiguous() else snd.contiguous(), group=group)
+        shift = (kp + 1) % W                      # panel kp+1+t sits on rank (kp+1+t) % W, relative slot t // W
         order = [(shift + i) % W for i in range(W)]
         P = rcv[order].view(W, ms, nb, kb).permute(1, 0, 2, 3).reshape(-1, kb)[: n - k1]
         return P.contiguous(), lr0, m
 
-    ev_panel = torch.cuda.Event() if use_streams else None
-    ev_u1 = torch.cuda.Event() if use_streams else None
-    if use_streams:
-        side.wait_stream(main)
-    with _Ctx(side):
-        cur = panel(0)
-        if use_streams:
-            ev_panel.record(side)
+    ev = [torch.cuda.Event() for _ in range(4)] if use_streams else None
+    diag(0)
+    bcast(0)
+    solve(0)
+    cur = gather(0)
     for kp in range(npan - 1):
         k0 = kp * nb
         k1 = k0 + nb
         k2 = min(k1 + nb, n)
         P, lr0, m = cur
-        if use_streams:
-            main.wait_event(ev_panel)           # block column kp factored, solved and gathered
+        rb, cb = (lr0 // nb) * W * nb, None
         # U1: the next block column only (lower part, mask in global coordinates)
         if m > 0:
-            local.syrk_cyclic_(A_loc[lr0:rows_f, k1:k2], A_loc[lr0:rows_f, k0:k1], P[: k2 - k1], (lr0 // nb) * W * nb, k1, nb, W, rank)
-        if use_streams:
-            ev_u1.record(main)
-            side.wait_event(ev_u1)
+            local.syrk_cyclic_(A_loc[lr0:rows_f, k1:k2], A_loc[lr0:rows_f, k0:k1], P[: k2 - k1], rb, k1, nb, W, rank)
+        # U2 on rows [lr0, rows_f) x columns [k2, n), in two halves when look-ahead is on
+        def update(r_lo, r_hi):
+            if r_hi > r_lo and k2 < n:
+                local.syrk_cyclic_(A_loc[r_lo:r_hi, k2:n], A_loc[r_lo:r_hi, k0:k1], P[k2 - k1:],
+                                   (r_lo // nb) * W * nb, k2, nb, W, rank)
+        if not use_streams:
+            update(lr0, rows_f)
+            diag(kp + 1); bcast(kp + 1); solve(kp + 1)
+            cur = gather(kp + 1)
+            continue
+        # split point: about a third of the local rows (whole panels), enough to cover the diagonal factorisation
+        nslots = (rows_f - lr0 + nb - 1) // nb
+        mid = lr0 + min(rows_f - lr0, max(1, nslots // 3) * nb)
+        ev[0].record(main)
+        side.wait_event(ev[0])
         with _Ctx(side):
-            nxt = panel(kp + 1)
-            if use_streams:
-                ev_panel.record(side)
-        # U2: everything to the right of the next block column
-        if m > 0 and k2 < n:
-            local.syrk_cyclic_(A_loc[lr0:rows_f, k2:n], A_loc[lr0:rows_f, k0:k1], P[k2 - k1:], (lr0 // nb) * W * nb, k2, nb, W, rank)
-        cur = nxt
+            diag(kp + 1)
+            ev[1].record(side)
+        update(lr0, mid)                           # U2a   || diag(kp+1)
+        main.wait_event(ev[1])
+        bcast(kp + 1)                              # collective on the main stream: the SMs are free between U2a and U2b
+        ev[2].record(main)
+        side.wait_event(ev[2])
+        with _Ctx(side):
+            solve(kp + 1)
+            ev[3].record(side)
+        update(mid, rows_f)                        # U2b   || solve(kp+1)
+        main.wait_event(ev[3])
+        cur = gather(kp + 1)                       # collective on the main stream after U2b
     if use_streams:
         main.wait_stream(side)
     if W > 1:
