@@ -250,11 +250,12 @@ def run_ours(args):
             if from_host:
                 return float(ll_dev.item())      # device -> host read of the step's result
         else:
-            potrf_block_cyclic_(K, lay, SIGMA2, n_factor=NC, lookahead=os.environ.get('GABO_DIST_LOOKAHEAD', '0') == '1')
+            winv = {}
+            potrf_block_cyclic_(K, lay, SIGMA2, n_factor=NC, lookahead=os.environ.get('GABO_DIST_LOOKAHEAD', '0') == '1', winv_store=winv)
             if events is not None:
                 events[2].record()
             V.copy_(yd[y_rows])
-            solve_lower_block_cyclic_(K, V, lay, n_factor=NC)
+            solve_lower_block_cyclic_(K, V, lay, n_factor=NC, winv_store=winv)
             ll_val_host[0] = gp_loglik_block_cyclic(K, V, lay, n_factor=NC)   # all-reduce + device -> host read
             if events is not None:
                 events[3].record()

@@ -27,6 +27,7 @@ SIGNATURES = {
     'gabo_potrf_f64': (i32, [i64, vp, i64, f64, vp, vp, sz, vp]),
     'gabo_trsm_workspace_bytes': (sz, [i64, i64]),
     'gabo_trsm_f64': (i32, [i32, i64, i64, vp, i64, vp, i64, vp, sz, vp]),
+    'gabo_trsm_winv_f64': (i32, [i32, i64, i64, vp, i64, vp, vp, i64, vp]),
     'gabo_logdet_f64': (i32, [i64, vp, i64, vp, vp]),
     'gabo_gp_loglik_f64': (i32, [i64, i64, vp, i64, vp, i64, vp, vp]),
     'gabo_gp_predict_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, f64, vp, vp, vp]),

@@ -758,8 +758,25 @@ static int gemv_dispatch(bool trans, const double* Lp, int64_t ldl, int64_t m, i
     return 0;
 }
 
+static int trsm_impl(int trans, int64_t n, int64_t nrhs, const double* L, int64_t ldl, const double* Winv_pre, double* B,
+                     int64_t ldb, void* workspace, size_t workspace_bytes, gabo_stream_t stream_);
+
 extern "C" int gabo_trsm_f64(int trans, int64_t n, int64_t nrhs, const double* L, int64_t ldl, double* B, int64_t ldb,
                              void* workspace, size_t workspace_bytes, gabo_stream_t stream_) {
+    return trsm_impl(trans, n, nrhs, L, ldl, nullptr, B, ldb, workspace, workspace_bytes, stream_);
+}
+
+// Same, with the inverses of the 128x128 diagonal blocks of L supplied (Winv_all [ceil(n/128)][128][128], as written by
+// gabo_potrf_diag_f64): no inversion kernel and no workspace.
+extern "C" int gabo_trsm_winv_f64(int trans, int64_t n, int64_t nrhs, const double* L, int64_t ldl, const double* Winv_all,
+                                  double* B, int64_t ldb, gabo_stream_t stream_) {
+    if (Winv_all == nullptr) return -6;
+    const int rc = trsm_impl(trans, n, nrhs, L, ldl, Winv_all, B, ldb, nullptr, 0, stream_);
+    return (rc <= -6 && rc > GABO_ERR_CUDA) ? rc - 1 : rc;
+}
+
+static int trsm_impl(int trans, int64_t n, int64_t nrhs, const double* L, int64_t ldl, const double* Winv_pre, double* B,
+                     int64_t ldb, void* workspace, size_t workspace_bytes, gabo_stream_t stream_) {
     if (n < 0) return -2;
     if (nrhs < 0) return -3;
     if (n == 0 || nrhs == 0) return 0;
@@ -767,17 +784,22 @@ extern "C" int gabo_trsm_f64(int trans, int64_t n, int64_t nrhs, const double* L
     if (ldl < n) return -5;
     if (B == nullptr) return -6;
     if (ldb < nrhs) return -7;
-    if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return -8;
-    if (workspace_bytes < gabo_trsm_workspace_bytes(n, nrhs)) return -9;
+    if (Winv_pre == nullptr) {
+        if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return -8;
+        if (workspace_bytes < gabo_trsm_workspace_bytes(n, nrhs)) return -9;
+    }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    double* Wall = static_cast<double*>(workspace);
+    const double* Wall = Winv_pre;
     const int64_t nblk = ceil_div64(n, NB_IN);
     int rc;
-    if ((rc = set_smem(trtri_blocks_kernel, POTF2_SMEM))) return rc;
     if ((rc = set_smem(diag_apply_kernel<false>, DIAGAPPLY_SMEM))) return rc;
     if ((rc = set_smem(diag_apply_kernel<true>, DIAGAPPLY_SMEM))) return rc;
-    trtri_blocks_kernel<<<(unsigned)nblk, 512, POTF2_SMEM, stream>>>(L, ldl, n, Wall);
-    GABO_LAUNCH_CHECK();
+    if (Winv_pre == nullptr) {
+        if ((rc = set_smem(trtri_blocks_kernel, POTF2_SMEM))) return rc;
+        trtri_blocks_kernel<<<(unsigned)nblk, 512, POTF2_SMEM, stream>>>(L, ldl, n, static_cast<double*>(workspace));
+        GABO_LAUNCH_CHECK();
+        Wall = static_cast<const double*>(workspace);
+    }
     const unsigned rhs_chunks = (unsigned)ceil_div64(nrhs, CH);
     for (int64_t b = 0; b < nblk; ++b) {
         const int64_t kb = trans ? (nblk - 1 - b) : b;

@@ -89,9 +89,9 @@ class CudaLocalOps:
         return ops.syrk_cyclic_(C, A, B, row_base, col_base, nb, world, rank)
 
     @staticmethod
-    def trsm_left_(L, B):
+    def trsm_left_(L, B, winv_all=None):
         from . import ops
-        return ops.trsm_(L, B, trans=False)
+        return ops.trsm_(L, B, trans=False, winv_all=winv_all)
 
     @staticmethod
     def solve_update_(Y, Lp, X):
@@ -122,10 +122,11 @@ def gram_block_cyclic(gram_rows, layout: BlockCyclic, out: Optional[torch.Tensor
 
 
 def potrf_block_cyclic_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: float, n_factor: Optional[int] = None,
-                        local=CudaLocalOps, group=None, lookahead: bool = False) -> int:
+                        local=CudaLocalOps, group=None, lookahead: bool = False, winv_store: Optional[dict] = None) -> int:
     """In-place distributed Cholesky of the leading n_factor x n_factor block (default: everything) of the symmetric
     matrix whose lower triangle is stored block-cyclically in A_loc [local_rows, >= n_factor].  Returns LAPACK-style info
-    (0, or the order of the first non-positive-definite leading minor), identical on every rank.
+    (0, or the order of the first non-positive-definite leading minor), identical on every rank.  If ``winv_store`` (a dict)
+    is given, the owner of each panel leaves the inverses of its diagonal 128-blocks there for solve_lower_block_cyclic_.
 
     Right-looking over panels; the trailing update is split into U1 (next block column) and U2 (the rest).  With
     ``lookahead=True`` the compute-only parts of the next panel (diagonal factorisation on the owner, row solve on every
@@ -188,6 +189,8 @@ def potrf_block_cyclic_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: float,
             bad = info.to(torch.int64)
             first_bad = torch.minimum(first_bad, torch.where(bad > 0, bad + k0, torch.full_like(bad, 2 ** 62)))
             Lkk[:kb, :kb].copy_(blk)
+            if winv_store is not None:           # the owner keeps the block inverses for the substitution that follows
+                winv_store[kp] = Wv.clone()
 
     def bcast(kp):
         if W > 1:
@@ -288,7 +291,8 @@ def potrf_block_cyclic_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: float,
 
 
 def solve_lower_block_cyclic_(A_loc: torch.Tensor, B_loc: torch.Tensor, layout: BlockCyclic,
-                              n_factor: Optional[int] = None, local=CudaLocalOps, group=None) -> torch.Tensor:
+                              n_factor: Optional[int] = None, local=CudaLocalOps, group=None,
+                              winv_store: Optional[dict] = None) -> torch.Tensor:
     """B_loc <- L^-1 B for the block-cyclically stored factor; B_loc [local_rows(, of the factored block), nrhs]."""
     W, rank, nb = layout.world, layout.rank, layout.nb
     n = layout.n if n_factor is None else n_factor
@@ -304,7 +308,7 @@ def solve_lower_block_cyclic_(A_loc: torch.Tensor, B_loc: torch.Tensor, layout: 
         if rank == owner:
             s = layout.slot(kp)
             bk = B_loc[s * nb: s * nb + kb]
-            local.trsm_left_(A_loc[s * nb: s * nb + kb, k0:k0 + kb], bk)
+            local.trsm_left_(A_loc[s * nb: s * nb + kb, k0:k0 + kb], bk, None if winv_store is None else winv_store.get(kp))
             xk[:kb].copy_(bk)
         if W > 1:
             dist.broadcast(xk, src=owner, group=group)

@@ -188,8 +188,9 @@ def potrf_(A: torch.Tensor, sigma2: float = 0.0, check: bool = True) -> torch.Te
     return info
 
 
-def trsm_(L_: torch.Tensor, B: torch.Tensor, trans: bool = False) -> torch.Tensor:
-    """B <- L^-1 B (or L^-T B), in place; B is [n, nrhs] row-major."""
+def trsm_(L_: torch.Tensor, B: torch.Tensor, trans: bool = False, winv_all: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """B <- L^-1 B (or L^-T B), in place; B is [n, nrhs] row-major.  winv_all: inverses of L's 128 x 128 diagonal blocks
+    when already known (from potrf_diag_), which skips the inversion kernel."""
     _req(L_, 'L'); _req(B, 'B')
     if B.dim() == 1:
         B = B.unsqueeze(1)
@@ -197,6 +198,13 @@ def trsm_(L_: torch.Tensor, B: torch.Tensor, trans: bool = False) -> torch.Tenso
     if B.shape[0] != n or (B.shape[1] > 1 and B.stride(1) != 1):
         raise ValueError('B must be a row-major [n, nrhs] tensor')
     Lh = _lib.lib()
+    if winv_all is not None:
+        _req(winv_all, 'winv_all')
+        st = Lh.gabo_trsm_winv_f64(1 if trans else 0, n, int(B.shape[1]), L_.data_ptr(), _ld(L_) if n > 1 else 1,
+                                   winv_all.data_ptr(), B.data_ptr(),
+                                   max(int(B.stride(0)), int(B.shape[1])) if n > 1 else int(B.shape[1]), _stream())
+        _lib.check('gabo_trsm_winv_f64', st)
+        return B
     nbytes = int(Lh.gabo_trsm_workspace_bytes(n, int(B.shape[1])))
     key = (L_.device.index, 'trsm', torch.cuda.current_stream().cuda_stream)
     ws = _ws_cache.get(key)

@@ -132,6 +132,10 @@ int gabo_potrf_f64(int64_t n, double* A, int64_t lda, double sigma2, int32_t* in
 size_t gabo_trsm_workspace_bytes(int64_t n, int64_t nrhs);
 int gabo_trsm_f64(int trans, int64_t n, int64_t nrhs, const double* L, int64_t ldl,
                   double* B, int64_t ldb, void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+/* gabo_trsm_winv_f64: the same solve with the inverses of L's 128 x 128 diagonal blocks supplied
+ *   (Winv_all [ceil(n/128)][128][128], e.g. from gabo_potrf_diag_f64): no inversion kernel, no workspace. */
+int gabo_trsm_winv_f64(int trans, int64_t n, int64_t nrhs, const double* L, int64_t ldl, const double* Winv_all,
+                       double* B, int64_t ldb, gabo_stream_t stream);
 /* out[0] = sum_i log L_ii  (half the log-determinant of K + sigma^2 I). */
 int gabo_logdet_f64(int64_t n, const double* L, int64_t ldl, double* out, gabo_stream_t stream);
 /* out[0] = -0.5*n*p*log(2 pi) - p*sum_i log L_ii - 0.5*||alpha||_F^2, alpha = L^-1 (y - m) already solved,

@@ -45,7 +45,7 @@ class TorchCpuLocalOps:
         return C
 
     @staticmethod
-    def trsm_left_(L, B):
+    def trsm_left_(L, B, winv_all=None):
         B.copy_(torch.linalg.solve_triangular(torch.tril(L), B, upper=False))
         return B
 

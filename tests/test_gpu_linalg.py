@@ -171,3 +171,26 @@ def test_gpr_optimize_improves_and_matches_cpu_optimum(cuda, golden):
     inv = lambda v: v + np.log(-np.expm1(-v))
     ref = minimize(nll, [inv(10.0), inv(1.0), inv(1.0)], method='L-BFGS-B')
     assert abs(ll1 - (-ref.fun)) < 1e-3 * abs(ref.fun)
+
+
+def test_trsm_with_supplied_block_inverses(cuda):
+    """gabo_potrf_diag_f64 exports the inverses of the 128-blocks; gabo_trsm_winv_f64 solves with them (no inversion)."""
+    from gaboflow_b200 import ops
+    n = 512
+    A = spd_matrix(n, 77)
+    d = torch.from_numpy(A).cuda()
+    winv = torch.empty((4, 128, 128), dtype=torch.float64, device='cuda')
+    info = ops.potrf_diag_(d, 0.01, winv)
+    assert int(info.item()) == 0
+    ref = sla.cholesky(A + 0.01 * np.eye(n), lower=True)
+    assert np.max(np.abs(np.tril(d.cpu().numpy()) - ref)) < 1e-12
+    for b in range(4):
+        blk = ref[b * 128:(b + 1) * 128, b * 128:(b + 1) * 128]
+        assert np.max(np.abs(winv[b].cpu().numpy() @ blk - np.eye(128))) < 1e-12
+    for nrhs in (1, 3, 70):
+        B = np.random.default_rng(nrhs).standard_normal((n, nrhs))
+        for trans in (False, True):
+            Bd = torch.from_numpy(B).cuda()
+            ops.trsm_(d, Bd, trans=trans, winv_all=winv)
+            want = sla.solve_triangular(ref, B, lower=True, trans='T' if trans else 'N')
+            assert np.max(np.abs(Bd.cpu().numpy() - want)) / np.max(np.abs(want)) < 1e-12
