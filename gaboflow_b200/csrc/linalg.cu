@@ -111,33 +111,50 @@ constexpr int BS = 16;              // register block
 constexpr int NBLK = NB_IN / BS;    // 8 diagonal steps
 __device__ __forceinline__ int warp_chol16_inv(double (&a)[BS], double (&w)[BS], int lane) {
     const unsigned FULL = 0xffffffffu;
-    double rinv[BS];
+    double my_rinv = 0.0;            // 1 / L[lane][lane], kept by lane `lane` only (an array of 16 would spill at 128 registers)
     int bad = 0;
 #pragma unroll
     for (int j = 0; j < BS; ++j) {
         const double d = __shfl_sync(FULL, a[j], j);
         if (!(d > 0.0) && bad == 0) bad = j + 1;
-        rinv[j] = rsqrt(d);
-        if (lane == j) a[j] = d * rinv[j];
-        else if (lane > j) a[j] *= rinv[j];
+        const double r = rsqrt(d);
+        // branch-free: entries above the diagonal are exact zeros and stay zero
+        a[j] = (lane == j) ? d * r : a[j] * r;
+        my_rinv = (lane == j) ? r : my_rinv;
 #pragma unroll
         for (int k = j + 1; k < BS; ++k) {
             const double lkj = __shfl_sync(FULL, a[j], k);
-            if (lane >= k) a[k] = fma(-a[j], lkj, a[k]);
+            a[k] = fma(-a[j], (lane >= k) ? lkj : 0.0, a[k]);
         }
     }
 #pragma unroll
     for (int i = 0; i < BS; ++i) {   // lane = column c of W: w[i] = (delta_ic - sum_{k<i} L[i][k] w[k]) / L[i][i]
         double s = (lane == i) ? 1.0 : 0.0;
+        const double ri = __shfl_sync(FULL, my_rinv, i);
 #pragma unroll
         for (int k = 0; k < i; ++k) {
             const double lik = __shfl_sync(FULL, a[k], i);
             s = fma(-lik, w[k], s);
         }
-        w[i] = (lane <= i) ? s * rinv[i] : 0.0;
+        w[i] = (lane <= i) ? s * ri : 0.0;
     }
     return bad;
 }
+
+// Phase stamps for tools/potf2_probe.cu only (the library build leaves the macro empty).
+#ifdef GABO_POTF2_PROFILE
+__device__ long long g_potf2_stamps[8];
+#define GABO_POTF2_STAMP(i) do { if (threadIdx.x == 0) g_potf2_stamps[i] = clock64(); } while (0)
+__device__ long long g_potf2_phase[4];
+#define GABO_POTF2_PHASE_BEGIN() long long ph_t = clock64(), ph_acc[3] = {0, 0, 0}
+#define GABO_POTF2_PHASE(i) do { long long ph_n = clock64(); ph_acc[i] += ph_n - ph_t; ph_t = ph_n; } while (0)
+#define GABO_POTF2_PHASE_END() do { if (threadIdx.x == 0) { g_potf2_phase[0] = ph_acc[0]; g_potf2_phase[1] = ph_acc[1]; g_potf2_phase[2] = ph_acc[2]; } } while (0)
+#else
+#define GABO_POTF2_PHASE_BEGIN() do { } while (0)
+#define GABO_POTF2_PHASE(i) do { } while (0)
+#define GABO_POTF2_PHASE_END() do { } while (0)
+#define GABO_POTF2_STAMP(i) do { } while (0)
+#endif
 
 constexpr int DLD = 20;   // leading dimension of every 16-wide block in shared memory (4 mod 16: conflict-free fragments)
 constexpr int BLKD = BS * DLD;                         // doubles per 16x16 block
@@ -159,17 +176,33 @@ __global__ void __launch_bounds__(256, 2) potf2_inv_kernel(double* __restrict__ 
     double* S = sm_potf2;                      // lower blocks of the matrix; strictly-lower blocks become the inverse
     double* Dv = sm_potf2 + NLOWBLK * BLKD;    // [128][20] inverses of the diagonal 16x16 blocks, row-major
     double* Y = Dv + NB_IN * DLD;              // [112][20] scratch of the inverse assembly
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // Warp index through a shuffle: the compiler then knows `warp == 0` is warp-uniform and emits plain SHFLs inside that
+    // branch instead of a WARPSYNC/ENDCOLLECTIVE pair around each of the ~400 shuffles (3.5x on the 16x16 step).
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int g = lane >> 2, q = lane & 3;
+    GABO_POTF2_STAMP(0);
+    // every element of the lower blocks goes global -> shared by an 8-byte cp.async (zero-filled outside jb and above the
+    // diagonal), all of a thread's 36-64 copies in flight at once; the one-at-a-time loop cost 20 us of load latency
+#pragma unroll 4
     for (int e = tid; e < NB_IN * NB_IN; e += 256) {
         const int r = e >> 7, c = e & 127;
         if ((c >> 4) > (r >> 4)) continue;     // block above the diagonal: not stored
-        double v = 0.0;
-        if (r < jb && c <= r) v = A[(int64_t)r * lda + c];
-        if (r == c) v = (r < jb) ? v + sigma2 : 1.0;   // identity padding keeps the inverse well defined
-        S[lowblk(r >> 4, c >> 4) + (r & 15) * DLD + (c & 15)] = v;
+        const bool in = (r < jb && c <= r);
+        const double* src = in ? A + (int64_t)r * lda + c : A;
+        const uint32_t dst = smem_u32(S + lowblk(r >> 4, c >> 4) + (r & 15) * DLD + (c & 15));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(src), "r"(in ? 8 : 0) : "memory");
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (tid < NB_IN) {                          // sigma^2 on the diagonal; identity padding keeps the inverse well defined
+        double* dgl = S + lowblk(tid >> 4, tid >> 4) + (tid & 15) * (DLD + 1);
+        *dgl = (tid < jb) ? *dgl + sigma2 : 1.0;
     }
     __syncthreads();
+    GABO_POTF2_STAMP(1);
+    GABO_POTF2_PHASE_BEGIN();
 #pragma unroll 1
     for (int kb = 0; kb < NBLK; ++kb) {
         double* Dk = S + lowblk(kb, kb);
@@ -189,6 +222,7 @@ __global__ void __launch_bounds__(256, 2) potf2_inv_kernel(double* __restrict__ 
             }
         }
         __syncthreads();
+        GABO_POTF2_PHASE(0);
         // panel: 8-row strips of the blocks below; X = A_strip * W_kk^T.  A strip reads only its own rows.
         const int nstrips = (NBLK - 1 - kb) * 2;
         for (int st = warp; st < nstrips; st += 8) {
@@ -205,31 +239,45 @@ __global__ void __launch_bounds__(256, 2) potf2_inv_kernel(double* __restrict__ 
             for (int ni = 0; ni < 2; ++ni) { Ar[ni * 8 + 2 * q] = c[ni][0]; Ar[ni * 8 + 2 * q + 1] = c[ni][1]; }
         }
         __syncthreads();
-        // trailing update of the lower part: S[i][j] -= sum_k S[i][o+k] S[j][o+k]; 8x8 tiles dealt round-robin to warps
-        const int ntiles = nstrips * (nstrips + 1) / 2;
-        for (int t = warp; t < ntiles; t += 8) {
-            int st = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-            while (st * (st + 1) / 2 > t) --st;
-            while ((st + 1) * (st + 2) / 2 <= t) ++st;
-            const int ct = t - st * (st + 1) / 2;
-            const int bi = kb + 1 + (st >> 1), bj = kb + 1 + (ct >> 1);
-            const double* Ar = S + lowblk(bi, kb) + ((st & 1) * 8 + g) * DLD + q;
-            const double* Br = S + lowblk(bj, kb) + ((ct & 1) * 8 + g) * DLD + q;
-            double u0 = 0.0, u1 = 0.0;
-#pragma unroll
-            for (int ks = 0; ks < BS / 4; ++ks) dmma884(u0, u1, Ar[ks * 4], Br[ks * 4]);
-            double* Cr = S + lowblk(bi, bj) + ((st & 1) * 8 + g) * DLD + (ct & 1) * 8 + 2 * q;
-            Cr[0] -= u0;
-            Cr[1] -= u1;
+        GABO_POTF2_PHASE(1);
+        // trailing update of the lower part: S[i][j] -= sum_k S[i][o+k] S[j][o+k] in 8x8 tiles.  A warp takes strip rows st
+        // and nstrips-1-st (st+1 and nstrips-st tiles: equal work per warp), keeps the row fragment and walks the columns.
+        for (int pr = warp; pr < (nstrips + 1) / 2; pr += 8) {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int st = half == 0 ? pr : nstrips - 1 - pr;
+                if (half == 1 && st == pr) break;
+                const int bi = kb + 1 + (st >> 1);
+                const double* Ar = S + lowblk(bi, kb) + ((st & 1) * 8 + g) * DLD + q;
+                const double a0 = Ar[0], a1 = Ar[4], a2 = Ar[8], a3 = Ar[12];
+#pragma unroll 2
+                for (int ct = 0; ct <= st; ++ct) {
+                    const int bj = kb + 1 + (ct >> 1);
+                    const double* Br = S + lowblk(bj, kb) + ((ct & 1) * 8 + g) * DLD + q;
+                    double u0 = 0.0, u1 = 0.0;
+                    dmma884(u0, u1, a0, Br[0]);
+                    dmma884(u0, u1, a1, Br[4]);
+                    dmma884(u0, u1, a2, Br[8]);
+                    dmma884(u0, u1, a3, Br[12]);
+                    double* Cr = S + lowblk(bi, bj) + ((st & 1) * 8 + g) * DLD + (ct & 1) * 8 + 2 * q;
+                    Cr[0] -= u0;
+                    Cr[1] -= u1;
+                }
+            }
         }
         __syncthreads();
+        GABO_POTF2_PHASE(2);
     }
+    GABO_POTF2_PHASE_END();
+    GABO_POTF2_STAMP(2);
     // the factor goes back to global memory before its off-diagonal blocks are overwritten by the inverse
-    for (int e = tid; e < jb * jb; e += 256) {
-        const int r = e / jb, c = e - r * jb;
-        if (c <= r) A[(int64_t)r * lda + c] = S[lowblk(r >> 4, c >> 4) + (r & 15) * DLD + (c & 15)];
+#pragma unroll 4
+    for (int e = tid; e < NB_IN * NB_IN; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        if (c <= r && r < jb) A[(int64_t)r * lda + c] = S[lowblk(r >> 4, c >> 4) + (r & 15) * DLD + (c & 15)];
     }
     __syncthreads();
+    GABO_POTF2_STAMP(3);
     // inverse, block columns right to left: W[j+1:, j] = -W[j+1:, j+1:] * (L[j+1:, j] * W_jj).  Block column j still holds L,
     // everything to its right already holds W, so both products have no sequential block dependency.
 #pragma unroll 1
@@ -280,6 +328,7 @@ __global__ void __launch_bounds__(256, 2) potf2_inv_kernel(double* __restrict__ 
         }
         __syncthreads();
     }
+    GABO_POTF2_STAMP(4);
     for (int e = tid; e < NB_IN * NB_IN; e += 256) {
         const int r = e >> 7, c = e & 127;
         double v = 0.0;
@@ -287,6 +336,7 @@ __global__ void __launch_bounds__(256, 2) potf2_inv_kernel(double* __restrict__ 
         else if (c < r) v = S[lowblk(r >> 4, c >> 4) + (r & 15) * DLD + (c & 15)];
         Winv[e] = v;
     }
+    GABO_POTF2_STAMP(5);
 }
 
 // ---- inverses of all 128x128 diagonal blocks of a factor L (for the solves): one CTA per block ------------------------
