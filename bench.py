@@ -189,6 +189,7 @@ def run_ours(args):
     #        rows of its panels with no exchange (X is replicated), then the leading NC x NC block is factored by the
     #        distributed right-looking Cholesky (diagonal-block broadcast + block-column all-gather over NCCL).
     from gaboflow_b200.dist import (BlockCyclic, PeerBuffers, gram_block_cyclic_mirrored, potrf_block_cyclic_,
+                                    PanelExchange, potrf_block_cyclic_p2p_,
                                     solve_lower_block_cyclic_, gp_loglik_block_cyclic)
     PANEL = 512
     lay = BlockCyclic(N, PANEL, world, rank)
@@ -203,6 +204,10 @@ def run_ours(args):
         K = peers.local
     else:
         K = torch.empty((rows, N), dtype=torch.float64, device=dev)
+    # panel exchange of the distributed factorisation through peer memory (GABO_DIST_P2P=0: NCCL broadcast + all-gather)
+    xch = None
+    if world > 1 and NC % PANEL == 0 and os.environ.get('GABO_DIST_P2P', '1') != '0':
+        xch = PanelExchange(BlockCyclic(NC, PANEL, world, rank), NC, dev)
     ws = torch.empty(int(lib.gabo_points_gram_workspace_bytes(N, N, DIM)), dtype=torch.uint8, device=dev)
     grow = lay.global_rows()
     sel_fac = (grow < NC).to(dev)
@@ -215,6 +220,8 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    dist_phases = [None]
 
     def step(events=None, from_host=False):
         nonlocal ll_dev
@@ -251,7 +258,11 @@ def run_ours(args):
                 return float(ll_dev.item())      # device -> host read of the step's result
         else:
             winv = {}
-            potrf_block_cyclic_(K, lay, SIGMA2, n_factor=NC, lookahead=os.environ.get('GABO_DIST_LOOKAHEAD', '0') == '1', winv_store=winv)
+            if xch is not None and dist_phases[0] is None:
+                potrf_block_cyclic_p2p_(K, lay, SIGMA2, xch, n_factor=NC, winv_store=winv)
+            else:
+                potrf_block_cyclic_(K, lay, SIGMA2, n_factor=NC, lookahead=os.environ.get('GABO_DIST_LOOKAHEAD', '0') == '1',
+                                    winv_store=winv, phase_ms=dist_phases[0])
             if events is not None:
                 events[2].record()
             V.copy_(yd[y_rows])
@@ -264,6 +275,12 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step()
+    if world > 1 and os.environ.get('GABO_DIST_PHASES', '0') == '1':    # diagnostic: one untimed step with per-piece events
+        dist_phases[0] = {}
+        step()
+        print(f'[rank {rank}] distributed potrf pieces (ms): ' +
+              ', '.join(f'{k} {v:.1f}' for k, v in sorted(dist_phases[0].items())), file=sys.stderr, flush=True)
+        dist_phases[0] = None
     barrier()
 
     # ---- device-resident timing: K steps, per-phase events, max over ranks ----
@@ -328,6 +345,8 @@ def run_ours(args):
     launches_all = int(reduce_max(float(launches)))
 
     if rank != 0:
+        if xch is not None:
+            xch.close()
         if peers is not None:
             del K
             peers.close()
@@ -393,6 +412,8 @@ def run_ours(args):
         line['cpu_baseline'] = cpu_reference_sample(N, n_chol_sample=min(args.ref_chol_n, NC), gram_rows=args.ref_gram_rows,
                                                     n_chol_metric=NC)
     print(json.dumps(line), flush=True)
+    if xch is not None:
+        xch.close()
     if peers is not None:
         del K
         peers.close()

@@ -46,6 +46,10 @@ SIGNATURES = {
     'gabo_trsm_right_f64': (i32, [i64, i64, vp, i64, vp, i64, vp, sz, vp]),
     'gabo_potrf_diag_f64': (i32, [i64, vp, i64, f64, vp, vp, vp, sz, vp]),
     'gabo_trsm_right_winv_f64': (i32, [i64, i64, vp, i64, vp, vp, i64, vp, sz, vp]),
+    'gabo_trsm_right_scatter_f64': (i32, [i64, i64, vp, i64, vp, vp, i64, vp, i32, i64, i64, i32, i32, vp, sz, vp]),
+    'gabo_flag_signal': (i32, [vp, i32, C.c_uint32, vp]),
+    'gabo_flag_wait_geq': (i32, [vp, C.c_uint32, vp]),
+    'gabo_copy_async': (i32, [vp, vp, sz, vp]),
     'gabo_syrk_cyclic_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, i32, vp]),
     'gabo_solve_update_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]),
 }

@@ -1,6 +1,7 @@
 // Small C-ABI entry points that are not kernels of their own: version, device query, status text, Kdiag fill.
 #include <atomic>
 #include <cstring>
+#include <cuda.h>
 #include "gabo_common.cuh"
 
 namespace gabo {
@@ -100,5 +101,70 @@ extern "C" int gabo_ipc_open(const unsigned char* handle64, void** out) {
 }
 extern "C" int gabo_ipc_close(void* ptr) {
     if (ptr != nullptr) GABO_CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+
+// ---- stream-ordered flags between ranks (distributed factorisation over peer memory) ------------------------------------
+// signal: a one-warp kernel stores `value` into up to GABO_MAX_PEERS 32-bit flags (peers' memory mapped with CUDA IPC)
+// after a system-scope fence, i.e. after everything earlier in the stream is visible to the peers.
+// wait:   cuStreamWaitValue32(>=) on a flag in THIS device's memory: the stream stalls without occupying an SM, so a rank
+// waiting for its peers never takes resources from the kernels that are running.
+namespace {
+struct FlagList { uint32_t* f[GABO_MAX_PEERS]; int n; };
+__global__ void flag_signal_kernel(const FlagList fl, uint32_t value) {
+    if ((int)threadIdx.x < fl.n) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(fl.f[threadIdx.x]), "r"(value) : "memory");
+    }
+}
+typedef CUresult (*PFN_waitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+PFN_waitValue32 get_wait_value32() {
+    static PFN_waitValue32 fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_waitValue32>(ptr);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+}  // namespace
+
+extern "C" int gabo_flag_signal(uint32_t* const* flags_host, int n, uint32_t value, gabo_stream_t stream_) {
+    if (n < 0 || n > GABO_MAX_PEERS) return -2;
+    if (n == 0) return 0;
+    if (flags_host == nullptr) return -1;
+    FlagList fl;
+    fl.n = n;
+    for (int i = 0; i < n; ++i) {
+        if (flags_host[i] == nullptr) return -1;
+        fl.f[i] = flags_host[i];
+    }
+    flag_signal_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>(fl, value);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gabo_flag_wait_geq(const uint32_t* flag, uint32_t value, gabo_stream_t stream_) {
+    if (flag == nullptr) return -1;
+    PFN_waitValue32 fn = get_wait_value32();
+    if (fn == nullptr) return GABO_ERR_CUDA - (int)cudaErrorNotSupported;
+    const CUresult r = fn(static_cast<CUstream>(stream_), reinterpret_cast<CUdeviceptr>(flag), value, CU_STREAM_WAIT_VALUE_GEQ);
+    if (r != CUDA_SUCCESS) return GABO_ERR_CUDA - (int)cudaErrorNotSupported;
+    return 0;
+}
+
+// Asynchronous copy between two device buffers of this process' address space (local or IPC-mapped peer memory): goes through
+// the copy engines, no SM involved.
+extern "C" int gabo_copy_async(void* dst, const void* src, size_t bytes, gabo_stream_t stream_) {
+    if (bytes == 0) return 0;
+    if (dst == nullptr) return -1;
+    if (src == nullptr) return -2;
+    GABO_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream_)));
     return 0;
 }

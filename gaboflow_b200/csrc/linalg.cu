@@ -967,8 +967,39 @@ extern "C" size_t gabo_trsm_right_workspace_bytes(int64_t m, int64_t nb) {
     return gabo_trsm_workspace_bytes(nb, 1) + align256((size_t)m * NB_IN * sizeof(double));
 }
 
+// Where the solved block column also goes when the panel is exchanged through peer memory (gabo_trsm_right_scatter_f64):
+// every destination holds the whole block column in GLOBAL row order; local row i of this rank is global-order row
+// row_off + (i / cyc_nb) * cyc_world * cyc_nb + i % cyc_nb.
+struct PanelScatter {
+    double* dst[GABO_MAX_PEERS];
+    int n_dst = 0;
+    int64_t ldp = 0, row_off = 0;
+    int cyc_nb = 0, cyc_world = 1;
+};
+
+// T [m][128] (staging) -> A[:, j0:j0+jb] and, row-permuted, into every destination's block column (NVLink stores when the
+// destination is a peer's memory).  One thread per column pair; a warp writes 512 contiguous bytes per row and destination.
+__global__ void __launch_bounds__(256) panel_scatter_kernel(const double* __restrict__ T, int64_t m, int jb, double* __restrict__ A,
+                                                            int64_t lda, int64_t j0, const PanelScatter sc) {
+    const int c = (threadIdx.x & 63) * 2;
+    const int64_t i = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 6);
+    if (i >= m || c >= jb) return;
+    const double2 v = *reinterpret_cast<const double2*>(T + i * NB_IN + c);
+    const bool two = c + 1 < jb;
+    A[i * lda + j0 + c] = v.x;
+    if (two) A[i * lda + j0 + c + 1] = v.y;
+    const int64_t prow = sc.row_off + (i / sc.cyc_nb) * sc.cyc_world * sc.cyc_nb + i % sc.cyc_nb;
+#pragma unroll 1
+    for (int d = 0; d < sc.n_dst; ++d) {
+        double* pr = sc.dst[d] + prow * sc.ldp + j0 + c;
+        if (two) *reinterpret_cast<double2*>(pr) = v;      // ldp even, j0 and c even, base 16-byte aligned (checked on the host)
+        else pr[0] = v.x;
+    }
+}
+
 static int trsm_right_impl(int64_t m, int64_t nb, const double* L, int64_t ldl, const double* Winv_all, double* A,
-                           int64_t lda, void* workspace, size_t workspace_bytes, gabo_stream_t stream_);
+                           int64_t lda, void* workspace, size_t workspace_bytes, gabo_stream_t stream_,
+                           const PanelScatter* scatter = nullptr);
 
 extern "C" int gabo_trsm_right_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, double* A, int64_t lda,
                                    void* workspace, size_t workspace_bytes, gabo_stream_t stream_) {
@@ -1006,8 +1037,35 @@ extern "C" int gabo_potrf_diag_f64(int64_t nb, double* A, int64_t lda, double si
     return potrf_panel(nb, A, lda, 0, nb, sigma2, info, Winv, T, stream, Winv_all);
 }
 
+// Row solve that also delivers the result to every rank: A <- A inv(L)^T as gabo_trsm_right_winv_f64, and each solved
+// 128-column block is written, in global row order, into the n_dst block-column buffers P_dst_host[d] (HOST array of device
+// pointers: this rank's own buffer and the peers' buffers mapped with CUDA IPC).  This replaces pack + all-gather + reorder
+// of the distributed factorisation by stores over NVLink issued as the blocks are produced.
+extern "C" int gabo_trsm_right_scatter_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, const double* Winv_all,
+                                           double* A, int64_t lda, double* const* P_dst_host, int n_dst, int64_t ldp,
+                                           int64_t p_row_off, int cyc_nb, int cyc_world, void* workspace,
+                                           size_t workspace_bytes, gabo_stream_t stream_) {
+    if (Winv_all == nullptr) return -5;
+    if (n_dst < 0 || n_dst > GABO_MAX_PEERS) return -9;
+    if (n_dst > 0 && P_dst_host == nullptr) return -8;
+    if (ldp < nb || (ldp & 1)) return -10;
+    if (p_row_off < 0) return -11;
+    if (cyc_nb < 1) return -12;
+    if (cyc_world < 1) return -13;
+    PanelScatter sc;
+    sc.n_dst = n_dst; sc.ldp = ldp; sc.row_off = p_row_off; sc.cyc_nb = cyc_nb; sc.cyc_world = cyc_world;
+    for (int d = 0; d < n_dst; ++d) {
+        if (P_dst_host[d] == nullptr || (reinterpret_cast<uintptr_t>(P_dst_host[d]) & 15) != 0) return -8;
+        sc.dst[d] = P_dst_host[d];
+    }
+    const int rc = trsm_right_impl(m, nb, L, ldl, Winv_all, A, lda, workspace, workspace_bytes, stream_, &sc);
+    if (rc <= -5 && rc > -9) return (rc == -7) ? -14 : (rc == -8) ? -15 : rc - 1;   // A -> 6, lda -> 7, workspace -> 14 / 15
+    return rc;
+}
+
 static int trsm_right_impl(int64_t m, int64_t nb, const double* L, int64_t ldl, const double* Winv_all, double* A,
-                           int64_t lda, void* workspace, size_t workspace_bytes, gabo_stream_t stream_) {
+                           int64_t lda, void* workspace, size_t workspace_bytes, gabo_stream_t stream_,
+                           const PanelScatter* scatter) {
     if (m < 0) return -1;
     if (nb < 0) return -2;
     if (m == 0 || nb == 0) return 0;
@@ -1040,8 +1098,13 @@ static int trsm_right_impl(int64_t m, int64_t nb, const double* L, int64_t ldl, 
         // beside a resident trailing-update CTA, which the look-ahead of the distributed factorisation relies on)
         rc = launch_gemm(true, true, m, jb, jb, 1.0, A + j0, lda, Winvs + b * NB_IN * NB_IN, NB_IN, true, T, NB_IN, false, stream);
         if (rc) return rc;
-        GABO_CUDA_TRY(cudaMemcpy2DAsync(A + j0, (size_t)lda * sizeof(double), T, (size_t)NB_IN * sizeof(double),
-                                        (size_t)jb * sizeof(double), (size_t)m, cudaMemcpyDeviceToDevice, stream));
+        if (scatter != nullptr) {
+            panel_scatter_kernel<<<(unsigned)ceil_div64(m, 4), 256, 0, stream>>>(T, m, jb, A, lda, j0, *scatter);
+            GABO_LAUNCH_CHECK();
+        } else {
+            GABO_CUDA_TRY(cudaMemcpy2DAsync(A + j0, (size_t)lda * sizeof(double), T, (size_t)NB_IN * sizeof(double),
+                                            (size_t)jb * sizeof(double), (size_t)m, cudaMemcpyDeviceToDevice, stream));
+        }
     }
     return 0;
 }

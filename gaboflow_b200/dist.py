@@ -122,11 +122,14 @@ def gram_block_cyclic(gram_rows, layout: BlockCyclic, out: Optional[torch.Tensor
 
 
 def potrf_block_cyclic_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: float, n_factor: Optional[int] = None,
-                        local=CudaLocalOps, group=None, lookahead: bool = False, winv_store: Optional[dict] = None) -> int:
+                        local=CudaLocalOps, group=None, lookahead: bool = False, winv_store: Optional[dict] = None,
+                        phase_ms: Optional[dict] = None) -> int:
     """In-place distributed Cholesky of the leading n_factor x n_factor block (default: everything) of the symmetric
     matrix whose lower triangle is stored block-cyclically in A_loc [local_rows, >= n_factor].  Returns LAPACK-style info
     (0, or the order of the first non-positive-definite leading minor), identical on every rank.  If ``winv_store`` (a dict)
     is given, the owner of each panel leaves the inverses of its diagonal 128-blocks there for solve_lower_block_cyclic_.
+    If ``phase_ms`` (a dict) is given (CUDA, no look-ahead), it receives the summed device time of each piece of the loop
+    (diag / bcast / solve / gather / u1 / u2), from CUDA events on the main stream: a diagnostic, not a bench number.
 
     Right-looking over panels; the trailing update is split into U1 (next block column) and U2 (the rest).  With
     ``lookahead=True`` the compute-only parts of the next panel (diagonal factorisation on the owner, row solve on every
@@ -240,10 +243,19 @@ def potrf_block_cyclic_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: float,
         return P.contiguous(), lr0, m
 
     ev = [torch.cuda.Event() for _ in range(4)] if use_streams else None
-    diag(0)
-    bcast(0)
-    solve(0)
-    cur = gather(0)
+    marks = []                                     # (phase that just ended, event) when phase_ms is requested
+
+    def tick(name):
+        if phase_ms is not None and A_loc.is_cuda and not use_streams:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(main)
+            marks.append((name, e))
+
+    tick(None)
+    diag(0); tick('diag')
+    bcast(0); tick('bcast')
+    solve(0); tick('solve')
+    cur = gather(0); tick('gather')
     for kp in range(npan - 1):
         k0 = kp * nb
         k1 = k0 + nb
@@ -253,15 +265,18 @@ def potrf_block_cyclic_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: float,
         # U1: the next block column only (lower part, mask in global coordinates)
         if m > 0:
             local.syrk_cyclic_(A_loc[lr0:rows_f, k1:k2], A_loc[lr0:rows_f, k0:k1], P[: k2 - k1], rb, k1, nb, W, rank)
+        tick('u1')
         # U2 on rows [lr0, rows_f) x columns [k2, n), in two halves when look-ahead is on
         def update(r_lo, r_hi):
             if r_hi > r_lo and k2 < n:
                 local.syrk_cyclic_(A_loc[r_lo:r_hi, k2:n], A_loc[r_lo:r_hi, k0:k1], P[k2 - k1:],
                                    (r_lo // nb) * W * nb, k2, nb, W, rank)
         if not use_streams:
-            update(lr0, rows_f)
-            diag(kp + 1); bcast(kp + 1); solve(kp + 1)
-            cur = gather(kp + 1)
+            update(lr0, rows_f); tick('u2')
+            diag(kp + 1); tick('diag')
+            bcast(kp + 1); tick('bcast')
+            solve(kp + 1); tick('solve')
+            cur = gather(kp + 1); tick('gather')
             continue
         # split point: about a third of the local rows (whole panels), enough to cover the diagonal factorisation
         nslots = (rows_f - lr0 + nb - 1) // nb
@@ -287,6 +302,9 @@ def potrf_block_cyclic_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: float,
     if W > 1:
         dist.all_reduce(first_bad, op=dist.ReduceOp.MIN, group=group)
     fb = int(first_bad.item())
+    if marks:
+        for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+            phase_ms[name] = phase_ms.get(name, 0.0) + e0.elapsed_time(e1)
     return 0 if fb >= 2 ** 62 else fb
 
 
@@ -408,3 +426,197 @@ def gram_block_cyclic_mirrored(kind: int, X: torch.Tensor, layout: BlockCyclic, 
         if layout.world > 1:
             dist.barrier(group=group)      # remote mirror stores of every rank have landed
     return peers.local
+
+
+class PanelExchange:
+    """Peer-memory exchange area of the distributed factorisation (one NVSwitch node, world <= 8).
+
+    Every rank allocates, exports (CUDA IPC) and maps on all peers:
+      * three block-column buffers P[b] [n][nb]: the block column below panel kp, in GLOBAL row order, lands in P[kp % 3]
+        of EVERY rank by remote stores from the ranks that solve its rows (gabo_trsm_right_scatter_f64);
+      * three buffers bc[b] for the factored diagonal block + the inverses of its 128-blocks, pushed by the owner with
+        copy-engine transfers;
+      * 32-bit flags: [0] "bc of panel kp has arrived", [1 + r] "rank r's rows of block column kp have arrived".
+    Flags carry epoch + kp + 1 and are waited for with cuStreamWaitValue32(>=): no collective kernel, no SM taken by a
+    rank that waits.  Three buffers are what makes one-panel look-ahead safe: a peer can only start writing buffer b for
+    panel kp + 3 after this rank has finished the trailing update of panel kp (see potrf_block_cyclic_p2p_)."""
+
+    NBUF = 3
+
+    def __init__(self, layout: BlockCyclic, n: int, device, group=None):
+        self.layout = layout
+        self.n, self.nb = int(n), int(layout.nb)
+        if layout.world > 8:
+            raise ValueError('PanelExchange: at most 8 ranks (one NVSwitch node)')
+        if self.nb % 2:
+            raise ValueError('PanelExchange: even panel width required')
+        self.nwb = (self.nb + 127) // 128
+        self.p_elems = self.n * self.nb
+        self.bc_elems = self.nb * self.nb + self.nwb * 128 * 128
+        self.flag_off = self.NBUF * (self.p_elems + self.bc_elems)          # in doubles
+        total = self.flag_off + 32
+        self.peers = PeerBuffers(1, total, device, group=group)
+        self.device = torch.device(device)
+        self.epoch = 0
+        self.side = torch.cuda.Stream(device=self.device, priority=-1)
+        self.peers.local[0, self.flag_off:].zero_()
+        self._warm_up()
+        torch.cuda.synchronize(self.device)
+        if layout.world > 1:
+            dist.barrier(group=group)
+
+    def _warm_up(self):
+        """Run every kernel of the factorisation once, single-rank, with nothing pending.  The first launch of a kernel
+        loads its module, which synchronises the whole context: were that to happen on the side stream while the main
+        stream is stalled on a peer's flag, the host would block and the ranks could wait for each other forever."""
+        from . import ops
+        nb = self.nb
+        nw = min(self.n, 3 * nb)
+        if nw < 1:
+            return
+        A = torch.zeros((nw, nw), dtype=torch.float64, device=self.device)
+        A.diagonal().fill_(2.0)
+        potrf_block_cyclic_p2p_(A, BlockCyclic(nw, nb, 1, 0), 0.0, self, winv_store={})
+        scratch = self.flag_ptr(self.peers.rank, 31)
+        ops.flag_signal([scratch], 1)
+        ops.flag_wait_geq(scratch, 1)
+
+    # raw pointers in THIS process of rank r's areas
+    def p_ptr(self, r: int, b: int) -> int:
+        return self.peers.ptrs[r] + 8 * b * self.p_elems
+
+    def bc_ptr(self, r: int, b: int) -> int:
+        return self.peers.ptrs[r] + 8 * (self.NBUF * self.p_elems + b * self.bc_elems)
+
+    def flag_ptr(self, r: int, idx: int) -> int:
+        return self.peers.ptrs[r] + 8 * self.flag_off + 4 * idx
+
+    # torch views of the local areas
+    def p_local(self, b: int) -> torch.Tensor:
+        o = b * self.p_elems
+        return self.peers.local[0, o: o + self.p_elems].view(self.n, self.nb)
+
+    def bc_local(self, b: int) -> torch.Tensor:
+        o = self.NBUF * self.p_elems + b * self.bc_elems
+        return self.peers.local[0, o: o + self.bc_elems]
+
+    def close(self, group=None):
+        self.peers.close(group=group)
+
+
+def potrf_block_cyclic_p2p_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: float, xch: PanelExchange,
+                            n_factor: Optional[int] = None, group=None, winv_store: Optional[dict] = None) -> int:
+    """Distributed Cholesky with the same arithmetic as potrf_block_cyclic_ but with the panel exchange done through peer
+    memory and one panel of look-ahead:
+
+        main stream                                   side stream (high priority)
+        wait P(kp) flags of all peers
+        U1(kp): next block column                 ->  owner: factor diagonal block kp+1, push it to the peers (copy engines),
+        U2(kp): rest of the trailing matrix               raise their bc flags
+                                                      all:   wait bc flag, solve own rows of block column kp+1, storing the
+                                                             result into P[(kp+1) % 3] of EVERY rank (NVLink stores),
+                                                             raise the peers' P flags
+
+    so that the whole panel chain of step kp+1 is hidden under U2(kp), and nothing on the side stream needs an SM that the
+    update kernel holds for long: the panel kernels fit beside a resident update CTA, the transfers use copy engines or
+    ride on the solve kernel's stores, and waiting is a stream memory operation.  Returns LAPACK-style info."""
+    from . import ops
+    W, rank, nb = layout.world, layout.rank, layout.nb
+    n = layout.n if n_factor is None else n_factor
+    if n % nb != 0 and n != layout.n:
+        raise ValueError('n_factor must be a multiple of the panel size')
+    if n > xch.n or nb != xch.nb:
+        raise ValueError('PanelExchange too small for this factorisation')
+    npan = (n + nb - 1) // nb
+    dev = A_loc.device
+    nwb = xch.nwb
+    main = torch.cuda.current_stream(dev)
+    side = xch.side
+    base = xch.epoch
+    xch.epoch += npan + 1
+    others = [r for r in range(W) if r != rank]
+    me = xch.peers.rank                               # index of this process in the exchange area (== rank unless W == 1)
+    if W > 1 and (W != xch.peers.world or me != rank):
+        raise ValueError('layout and PanelExchange disagree on world / rank')
+    my = [p for p in layout.my_panels() if p < npan]
+    rows_f = sum(min(nb, n - p * nb) for p in my)
+    first_bad = torch.full((1,), 2 ** 62, dtype=torch.int64, device=dev)
+    bc_bytes = 8 * xch.bc_elems
+
+    def parts(kp):
+        bcl = xch.bc_local(kp % xch.NBUF)
+        return bcl[: nb * nb].view(nb, nb), bcl[nb * nb:].view(nwb, 128, 128)
+
+    def diag_and_push(kp):
+        """Owner only: factor the diagonal block of panel kp, hand factor + block inverses to every peer."""
+        nonlocal first_bad
+        b = kp % xch.NBUF
+        k0 = kp * nb
+        kb = min(nb, n - k0)
+        Lkk, Wv = parts(kp)
+        sl = layout.slot(kp)
+        blk = A_loc[sl * nb: sl * nb + kb, k0:k0 + kb]
+        info = ops.potrf_diag_(blk, sigma2, Wv)
+        bad = info.to(torch.int64)
+        first_bad = torch.minimum(first_bad, torch.where(bad > 0, bad + k0, torch.full_like(bad, 2 ** 62)))
+        Lkk[:kb, :kb].copy_(blk)
+        if winv_store is not None:
+            winv_store[kp] = Wv.clone()
+        if k0 + kb >= n:
+            return                                   # last panel: nobody solves against it
+        for r in others:
+            ops.copy_async(xch.bc_ptr(r, b), xch.bc_ptr(me, b), bc_bytes)
+        ops.flag_signal([xch.flag_ptr(r, 0) for r in others], base + kp + 1)
+
+    def solve_and_scatter(kp):
+        """Every rank: rows of block column kp below the diagonal block, delivered to all ranks."""
+        b = kp % xch.NBUF
+        k0 = kp * nb
+        kb = min(nb, n - k0)
+        k1 = k0 + kb
+        if k1 >= n:
+            return
+        if rank != layout.owner(kp):
+            ops.flag_wait_geq(xch.flag_ptr(me, 0), base + kp + 1)
+        Lkk, Wv = parts(kp)
+        s0 = layout.slots_after(kp)
+        lr0 = s0 * nb
+        m = rows_f - lr0
+        if m > 0:
+            ops.trsm_right_scatter_(A_loc[lr0:rows_f, k0:k1], Lkk[:kb, :kb], Wv, [xch.p_ptr(r if W > 1 else me, b) for r in range(W)],
+                                    nb, (s0 * W + rank) * nb - k1, nb, W)
+        ops.flag_signal([xch.flag_ptr(r, 1 + rank) for r in others], base + kp + 1)
+
+    ev_u1 = torch.cuda.Event()
+    ev_side = torch.cuda.Event()
+    if rank == layout.owner(0):
+        diag_and_push(0)
+    solve_and_scatter(0)
+    for kp in range(npan - 1):
+        k0 = kp * nb
+        k1 = k0 + nb
+        k2 = min(k1 + nb, n)
+        lr0 = layout.slots_after(kp) * nb
+        m = rows_f - lr0
+        for r in others:
+            ops.flag_wait_geq(xch.flag_ptr(me, 1 + r), base + kp + 1)
+        if kp > 0:
+            main.wait_event(ev_side)
+        P = xch.p_local(kp % xch.NBUF)[: n - k1]
+        rb = (lr0 // nb) * W * nb
+        if m > 0:
+            ops.syrk_cyclic_(A_loc[lr0:rows_f, k1:k2], A_loc[lr0:rows_f, k0:k1], P[: k2 - k1], rb, k1, nb, W, rank)
+        ev_u1.record(main)
+        side.wait_event(ev_u1)
+        with torch.cuda.stream(side):
+            if rank == layout.owner(kp + 1):
+                diag_and_push(kp + 1)
+            solve_and_scatter(kp + 1)
+            ev_side.record(side)
+        if m > 0 and k2 < n:
+            ops.syrk_cyclic_(A_loc[lr0:rows_f, k2:n], A_loc[lr0:rows_f, k0:k1], P[k2 - k1:], rb, k2, nb, W, rank)
+    main.wait_stream(side)
+    if W > 1:
+        dist.all_reduce(first_bad, op=dist.ReduceOp.MIN, group=group)
+    fb = int(first_bad.item())
+    return 0 if fb >= 2 ** 62 else fb

@@ -312,6 +312,49 @@ def trsm_right_(A: torch.Tensor, L_: torch.Tensor, winv_all: Optional[torch.Tens
     return A
 
 
+def trsm_right_scatter_(A: torch.Tensor, L_: torch.Tensor, winv_all: torch.Tensor, dst_ptrs, ldp: int, p_row_off: int,
+                        cyc_nb: int, cyc_world: int) -> torch.Tensor:
+    """trsm_right_ that also stores the solved block column, in global row order, into the block-column buffers at the raw
+    device pointers ``dst_ptrs`` (own + IPC-mapped peers); see gabo_trsm_right_scatter_f64."""
+    import ctypes as C
+    _req(A, 'A'); _req(L_, 'L'); _req(winv_all, 'winv_all')
+    m, nb = int(A.shape[0]), int(A.shape[1])
+    if m == 0 or nb == 0:
+        return A
+    Lh = _lib.lib()
+    nbytes = int(Lh.gabo_trsm_right_workspace_bytes(m, nb))
+    key = (A.device.index, 'trsm_right', torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=A.device)
+        _ws_cache[key] = ws
+    arr = (C.c_void_p * len(dst_ptrs))(*[int(q) for q in dst_ptrs])
+    st = Lh.gabo_trsm_right_scatter_f64(m, nb, L_.data_ptr(), _ldm(L_), winv_all.data_ptr(), A.data_ptr(), _ldm(A),
+                                        C.cast(arr, C.c_void_p), len(dst_ptrs), int(ldp), int(p_row_off), int(cyc_nb),
+                                        int(cyc_world), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check('gabo_trsm_right_scatter_f64', st)
+    return A
+
+
+def flag_signal(flag_ptrs, value: int) -> None:
+    """Stream-ordered store of ``value`` into the 32-bit flags at the raw device pointers ``flag_ptrs`` (peers' memory)."""
+    import ctypes as C
+    if not flag_ptrs:
+        return
+    arr = (C.c_void_p * len(flag_ptrs))(*[int(q) for q in flag_ptrs])
+    _lib.check('gabo_flag_signal', _lib.lib().gabo_flag_signal(C.cast(arr, C.c_void_p), len(flag_ptrs), int(value), _stream()))
+
+
+def flag_wait_geq(flag_ptr: int, value: int) -> None:
+    """The current stream stalls (no SM occupied) until the 32-bit flag at ``flag_ptr`` (local memory) is >= value."""
+    _lib.check('gabo_flag_wait_geq', _lib.lib().gabo_flag_wait_geq(int(flag_ptr), int(value), _stream()))
+
+
+def copy_async(dst_ptr: int, src_ptr: int, nbytes: int) -> None:
+    """cudaMemcpyAsync on the current stream between raw device pointers (local or IPC-mapped peer memory)."""
+    _lib.check('gabo_copy_async', _lib.lib().gabo_copy_async(int(dst_ptr), int(src_ptr), int(nbytes), _stream()))
+
+
 def syrk_cyclic_(Cm: torch.Tensor, A: torch.Tensor, B: torch.Tensor, row_base: int, col_base: int, cyc_nb: int = 0,
                  cyc_world: int = 1, cyc_rank: int = 0) -> torch.Tensor:
     """C[m,n] -= A[m,k] B[n,k]^T where global col <= global row (see gabo_syrk_cyclic_f64)."""

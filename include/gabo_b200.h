@@ -32,6 +32,7 @@ extern "C" {
 
 #define GABO_ABI_VERSION 1
 #define GABO_ERR_CUDA (-1000)
+#define GABO_MAX_PEERS 8      /* ranks of one NVSwitch node that exchange through peer memory */
 
 typedef void* gabo_stream_t; /* cudaStream_t */
 
@@ -201,6 +202,22 @@ int gabo_potrf_diag_f64(int64_t nb, double* A, int64_t lda, double sigma2, int32
                         void* workspace, size_t workspace_bytes, gabo_stream_t stream);
 int gabo_trsm_right_winv_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, const double* Winv_all,
                              double* A, int64_t lda, void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+/* gabo_trsm_right_scatter_f64: gabo_trsm_right_winv_f64 that ALSO delivers the solved block column to every rank: each
+ *   solved 128-column block is stored, in global row order, into the n_dst (<= GABO_MAX_PEERS) block-column buffers
+ *   P_dst_host[d] [rows below the panel][ldp] -- this rank's own and the peers' (CUDA IPC mappings; NVLink stores issued
+ *   as the blocks are produced, no pack / all-gather / reorder).  Local row i lands on row
+ *   p_row_off + (i / cyc_nb) * cyc_world * cyc_nb + i % cyc_nb.  ldp even, buffers 16-byte aligned. */
+int gabo_trsm_right_scatter_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, const double* Winv_all,
+                                double* A, int64_t lda, double* const* P_dst_host, int n_dst, int64_t ldp,
+                                int64_t p_row_off, int cyc_nb, int cyc_world, void* workspace, size_t workspace_bytes,
+                                gabo_stream_t stream);
+/* Stream-ordered flags between the ranks of a node.  gabo_flag_signal: after everything earlier in `stream` is visible
+ *   system-wide, store `value` into the n 32-bit flags flags_host[i] (HOST array of device pointers, typically one flag in
+ *   each peer's memory).  gabo_flag_wait_geq: `stream` stalls (cuStreamWaitValue32, no SM occupied) until *flag >= value;
+ *   `flag` must be in this device's memory.  gabo_copy_async: cudaMemcpyAsync between local / IPC-mapped buffers. */
+int gabo_flag_signal(uint32_t* const* flags_host, int n, uint32_t value, gabo_stream_t stream);
+int gabo_flag_wait_geq(const uint32_t* flag, uint32_t value, gabo_stream_t stream);
+int gabo_copy_async(void* dst, const void* src, size_t bytes, gabo_stream_t stream);
 /* gabo_syrk_cyclic_f64: C[m,n] -= A[m,k] B[n,k]^T restricted to GLOBAL col <= GLOBAL row, where local row r of C is
  *   global row row_base + ((r / cyc_nb) * cyc_world + cyc_rank) * cyc_nb + r % cyc_nb (cyc_nb == 0: row_base + r) and
  *   local column c is global column col_base + c. */

@@ -88,3 +88,85 @@ def test_cyclic_mirrored_gram_single_process(cuda, world):
     for r in range(world):
         rows = lays[r].global_rows().cuda()
         assert torch.equal(bufs[r], full[rows])
+
+
+def test_flag_signal_and_stream_wait(cuda):
+    """gabo_flag_signal / gabo_flag_wait_geq: a stream stalled on a flag resumes when another stream raises it."""
+    from gaboflow_b200 import ops
+    flags = torch.zeros(8, dtype=torch.int32, device='cuda')
+    out = torch.zeros(1, dtype=torch.float64, device='cuda')
+    # every kernel used below is launched once first: a first launch loads its module, which synchronises the context and
+    # would block the host for as long as the waiter stream is stalled
+    out.add_(1.0).zero_()
+    ops.flag_signal([flags.data_ptr() + 28], 1)
+    float(out.item()); flags.cpu()
+    torch.cuda.synchronize()
+    waiter, signaller = torch.cuda.Stream(), torch.cuda.Stream()
+    with torch.cuda.stream(waiter):
+        ops.flag_wait_geq(flags.data_ptr() + 4, 7)
+        out.add_(1.0)                                  # must not run before the flag is raised
+    with torch.cuda.stream(signaller):
+        ops.flag_signal([flags.data_ptr() + 4, flags.data_ptr() + 8], 6)      # too small: the waiter stays blocked
+    signaller.synchronize()
+    assert not waiter.query()
+    assert float(out.item()) == 0.0
+    with torch.cuda.stream(signaller):
+        ops.flag_signal([flags.data_ptr() + 4], 9)     # >= 7: releases the waiter
+    waiter.synchronize()
+    assert float(out.item()) == 1.0
+    assert flags.cpu().tolist()[:3] == [0, 9, 6]
+
+
+@pytest.mark.parametrize('world,rank', [(1, 0), (3, 1)])
+def test_trsm_right_scatter(cuda, world, rank):
+    """gabo_trsm_right_scatter_f64: same solve as gabo_trsm_right_winv_f64, and every destination receives the rows in
+    global (block-cyclic) order."""
+    from gaboflow_b200 import ops
+    rng = np.random.default_rng(11 + world)
+    nb, m = 512, 3 * 512 - 40                           # ragged last local panel
+    L = np.tril(rng.standard_normal((nb, nb))) * 0.05 + np.eye(nb) * 2.0
+    A = rng.standard_normal((m, nb))
+    Ld = torch.from_numpy(L).cuda()
+    Ad = torch.from_numpy(A).cuda()
+    Wv = torch.empty((4, 128, 128), dtype=torch.float64, device='cuda')
+    blk = (torch.from_numpy(L @ L.T).cuda()).contiguous()
+    ops.potrf_diag_(blk, 0.0, Wv)                       # factor of L L^T = L; block inverses in Wv
+    Aref = Ad.clone()
+    ops.trsm_right_(Aref, torch.tril(blk), Wv)
+    s0 = 2                                              # first local slot below the panel
+    row_off = (s0 * world + rank) * nb - 1024           # panel kp = 1 -> k1 = 1024
+    nrows = row_off + ((m - 1) // nb) * world * nb + (m - 1) % nb + 1
+    dsts = [torch.full((nrows, nb), np.nan, dtype=torch.float64, device='cuda') for _ in range(2)]
+    ops.trsm_right_scatter_(Ad, torch.tril(blk), Wv, [d.data_ptr() for d in dsts], nb, row_off, nb, world)
+    assert torch.equal(Ad, Aref)
+    i = np.arange(m)
+    prow = torch.from_numpy(row_off + (i // nb) * world * nb + i % nb).cuda()
+    for d in dsts:
+        assert torch.equal(d[prow], Aref)
+        untouched = torch.ones(nrows, dtype=torch.bool, device='cuda')
+        untouched[prow] = False
+        assert bool(torch.isnan(d[untouched]).all())
+
+
+def test_p2p_driver_world1_matches_collective_driver(cuda):
+    """potrf_block_cyclic_p2p_ (peer-memory exchange + look-ahead) gives the same bits as potrf_block_cyclic_."""
+    from gaboflow_b200 import SphereGaussianKernel
+    from gaboflow_b200.dist import BlockCyclic, gram_block_cyclic, potrf_block_cyclic_, potrf_block_cyclic_p2p_, PanelExchange
+    from oracle import gabo_oracle as orc
+    n = 2560
+    Xd = torch.from_numpy(orc.synth_sphere(n, 51, seed=4)).cuda()
+    k = SphereGaussianKernel(51, range(51), beta_min=0.0, beta=2.0)
+    lay = BlockCyclic(n, 512, 1, 0)
+    A = gram_block_cyclic(lambda r0, r1, out: k.K(Xd, uplo='lower', row0=r0, row1=r1, out=out), lay, device='cuda')
+    B = A.clone()
+    assert potrf_block_cyclic_(A, lay, 1e-2, n_factor=2048) == 0
+    xch = PanelExchange(lay, 2048, 'cuda')
+    try:
+        for _ in range(2):                              # twice: flag epochs, buffer reuse
+            C2 = B.clone()
+            store = {}
+            assert potrf_block_cyclic_p2p_(C2, lay, 1e-2, xch, n_factor=2048, winv_store=store) == 0
+            assert torch.equal(torch.tril(C2[:2048, :2048]), torch.tril(A[:2048, :2048]))
+            assert sorted(store) == [0, 1, 2, 3]
+    finally:
+        xch.close()
