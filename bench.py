@@ -373,8 +373,10 @@ def run_ours(args):
                                  f'full rows of the dense K in {PANEL}-row panels, 1-D block-cyclic over {world} ranks'),
                    'l2': f'no flush: {rows * N * 8 / 1e9:.1f} GB of K per GPU >> 126 MB L2',
                    'parallelism': 'single GPU' if world == 1 else
-                                  f'Gram: row panels block-cyclic over {world} ranks, no collective; Cholesky: right-looking over panels, '
-                                  f'diagonal-block broadcast + block-column all-gather over NCCL'},
+                                  f'Gram: row panels block-cyclic over {world} ranks, no collective; Cholesky: right-looking over panels, ' +
+                                  ('one panel of look-ahead, block column delivered to every rank by NVLink stores from the row-solve '
+                                   'kernel, diagonal block pushed by copy engines, stream-ordered flags (no collective in the loop)'
+                                   if xch is not None else 'diagonal-block broadcast + block-column all-gather over NCCL')},
         'phases_ms': {'gram': gram_ms, 'potrf': potrf_ms, 'solve_loglik': solve_ms},
         'cholesky': {'n': NC, 'seconds': potrf_s, 'tflops': potrf_tflops,
                      'frac_fp64_tensor_peak': (potrf_tflops / (FP64_PEAK_TFLOPS * world)) if potrf_tflops else None},
