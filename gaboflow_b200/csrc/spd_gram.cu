@@ -211,10 +211,19 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_gram_kernel(const Sp
                         }
                     };
                     congruence();
-                    // eigenvalues: Householder + implicit QL (fast path); cyclic Jacobi when the spectrum is wide enough
-                    // that the absolute accuracy of QL would eat into the 1e-12 relative budget of log(lambda)
+                    // eigenvalues: Householder (FP64), then FP32 QL + FP64 Newton refinement; the all-FP64 QL when that
+                    // does not validate (near-multiple eigenvalues); cyclic Jacobi when the spectrum is wide enough that the
+                    // absolute accuracy of the tridiagonal route would eat into the 1e-12 relative budget of log(lambda)
                     double ev[D];
-                    tridiag_ql_eigvals<D>(Mx, ev);
+                    {
+                        double td[D], te[D];
+                        householder_tridiag<D>(Mx, td, te);
+                        if (!tridiag_eigvals_mixed<D>(td, te, ev)) {
+                            ql_tri_eigvals<D, double>(td, te);
+#pragma unroll
+                            for (int k = 0; k < D; ++k) ev[k] = td[k];
+                        }
+                    }
                     double emin = ev[0], emax = ev[0];
 #pragma unroll
                     for (int k = 1; k < D; ++k) { emin = fmin(emin, ev[k]); emax = fmax(emax, ev[k]); }

@@ -68,14 +68,13 @@ __device__ __forceinline__ void jacobi_eig(double (&A)[D][D], double (&V)[WITH_V
     }
 }
 
-// Eigenvalues of a symmetric D x D matrix (upper storage of A, destroyed) by Householder tridiagonalisation followed by
-// the implicit-shift QL iteration, eigenvalues only -- about 4x fewer FP64 pipe slots than cyclic Jacobi for d = 6.
-// Everything is unrolled over compile-time indices so d[], e[] and A stay in registers; the active block always starts
+// ---- symmetric eigenvalues: Householder tridiagonalisation + implicit-shift QL, and the mixed-precision variant ---------
+// Everything is unrolled over compile-time indices so d[], e[] and A stay in registers; the active QL block always starts
 // at the compile-time row l, and its data-dependent bottom m only predicates the unrolled sweep steps.
-// Absolute accuracy ~ eps * ||A||; callers fall back to Jacobi (relative accuracy) for ill-conditioned matrices.
+
+// A (symmetric, upper storage, destroyed) -> tridiagonal (d, e); e[i] couples d[i] and d[i+1]; e[D-1] = 0 is a dummy slot.
 template <int D>
-__device__ __forceinline__ void tridiag_ql_eigvals(double (&A)[D][D], double (&d)[D]) {
-    double e[D];   // e[i] couples d[i] and d[i+1]; e[D-1] is a dummy slot
+__device__ __forceinline__ void householder_tridiag(double (&A)[D][D], double (&d)[D], double (&e)[D]) {
 #pragma unroll
     for (int k = 0; k < D - 2; ++k) {
         double sigma = 0.0;
@@ -122,15 +121,40 @@ __device__ __forceinline__ void tridiag_ql_eigvals(double (&A)[D][D], double (&d
     }
     d[D - 1] = A[D - 1][D - 1];
     e[D - 1] = 0.0;
+}
 
-    // Convergence tests on the exponents with INTEGER arithmetic (an FP64 compare occupies the FP64 pipe that bounds this
-    // kernel): e is negligible against its neighbours when exponent(e) + 49 <= exponent(max(|d_i|, |d_i+1|)), i.e.
-    // |e| < 2^-48 * max(...) ~ 3.6e-15 * max: neglected coupling far inside the 1e-12 budget.  (hi word >> 20 = exponent.)
-    auto negligible = [](double ee, double da, double db) {
-        const int he = __double2hiint(ee) & 0x7fffffff;
-        const int ha = __double2hiint(da) & 0x7fffffff, hb = __double2hiint(db) & 0x7fffffff;
+// Scalar-type glue of the QL iteration.  Convergence tests run on the exponents with INTEGER arithmetic (an FP64 compare
+// occupies the FP64 pipe that bounds the SPD kernels): e is negligible against its neighbours when
+// |e| < 2^-48 max(|d_i|, |d_i+1|) (double: 3.6e-15, far inside the 1e-12 budget) or 2^-22 max (float).
+template <typename T> struct QlScalar;
+template <> struct QlScalar<double> {
+    static __device__ __forceinline__ double rsq(double x) { return rsqrt(x); }
+    static __device__ __forceinline__ double fmad(double a, double b, double c) { return fma(a, b, c); }
+    static __device__ __forceinline__ double cps(double a, double b) { return copysign(a, b); }
+    static __device__ __forceinline__ double quot(double a, double b) { return a / b; }
+    static __device__ __forceinline__ int mag(double x) { return __double2hiint(x) & 0x7fffffff; }
+    static __device__ __forceinline__ bool is_zero(double x) { return ((__double2hiint(x) & 0x7fffffff) | __double2loint(x)) == 0; }
+    static constexpr int kNegl = 49 << 20;
+};
+template <> struct QlScalar<float> {
+    static __device__ __forceinline__ float rsq(float x) { return rsqrtf(x); }
+    static __device__ __forceinline__ float fmad(float a, float b, float c) { return fmaf(a, b, c); }
+    static __device__ __forceinline__ float cps(float a, float b) { return copysignf(a, b); }
+    static __device__ __forceinline__ float quot(float a, float b) { return __fdividef(a, b); }
+    static __device__ __forceinline__ int mag(float x) { return __float_as_int(x) & 0x7fffffff; }
+    static __device__ __forceinline__ bool is_zero(float x) { return (__float_as_int(x) & 0x7fffffff) == 0; }
+    static constexpr int kNegl = 23 << 23;
+};
+
+// Eigenvalues of the symmetric tridiagonal (d, e), returned in d (unordered); e is destroyed.  Absolute accuracy
+// ~ eps(T) * ||A||.
+template <int D, typename T>
+__device__ __forceinline__ void ql_tri_eigvals(T (&d)[D], T (&e)[D]) {
+    using Q = QlScalar<T>;
+    auto negligible = [](T ee, T da, T db) {
+        const int he = Q::mag(ee), ha = Q::mag(da), hb = Q::mag(db);
         const int hm = ha > hb ? ha : hb;
-        return he + (49 << 20) <= hm;
+        return he + Q::kNegl <= hm;
     };
 #pragma unroll
     for (int l = 0; l < D - 1; ++l) {
@@ -141,35 +165,35 @@ __device__ __forceinline__ void tridiag_ql_eigvals(double (&A)[D][D], double (&d
             for (int mm = D - 2; mm >= l; --mm)
                 if (negligible(e[mm], d[mm], d[mm + 1])) m = mm;
             if (m == l) break;
-            double dm = d[D - 1];
+            T dm = d[D - 1];
 #pragma unroll
             for (int mm = l + 1; mm < D - 1; ++mm)
                 if (m == mm) dm = d[mm];
             // Wilkinson shift: e^2 / (delta + sign(delta) sqrt(delta^2 + e^2)), delta = (d[l+1] - d[l]) / 2
-            const double dl = 0.5 * (d[l + 1] - d[l]);
-            const double e2 = e[l] * e[l];
-            const double hh = fma(dl, dl, e2);
-            double g = dm - d[l] + e2 / (dl + copysign(hh * rsqrt(hh), dl));
-            double s = 1.0, c = 1.0, p = 0.0;
+            const T dl = T(0.5) * (d[l + 1] - d[l]);
+            const T e2 = e[l] * e[l];
+            const T hh = Q::fmad(dl, dl, e2);
+            T g = dm - d[l] + Q::quot(e2, dl + Q::cps(hh * Q::rsq(hh), dl));
+            T s = T(1), c = T(1), p = T(0);
             bool aborted = false;
 #pragma unroll
             for (int i = D - 2; i >= l; --i) {
                 if (i < m && !aborted) {
-                    const double f = s * e[i], b = c * e[i];
-                    const double h2 = fma(f, f, g * g);
-                    if (((__double2hiint(h2) & 0x7fffffff) | __double2loint(h2)) == 0) {
+                    const T f = s * e[i], b = c * e[i];
+                    const T h2 = Q::fmad(f, f, g * g);
+                    if (Q::is_zero(h2)) {
                         d[i + 1] -= p;
                         aborted = true;
                     } else {
-                        const double rr = rsqrt(h2);
+                        const T rr = Q::rsq(h2);
                         e[i + 1] = h2 * rr;
                         s = f * rr;
                         c = g * rr;
                         g = d[i + 1] - p;
-                        const double r2 = fma(d[i] - g, s, 2.0 * c * b);
+                        const T r2 = Q::fmad(d[i] - g, s, T(2) * c * b);
                         p = s * r2;
                         d[i + 1] = g + p;
-                        g = fma(c, r2, -b);
+                        g = Q::fmad(c, r2, -b);
                     }
                 }
             }
@@ -179,9 +203,127 @@ __device__ __forceinline__ void tridiag_ql_eigvals(double (&A)[D][D], double (&d
             }
 #pragma unroll
             for (int mm = l + 1; mm < D; ++mm)
-                if (m == mm) e[mm] = 0.0;
+                if (m == mm) e[mm] = T(0);
         }
     }
+}
+
+// FP32 QL for STARTING VALUES only (tridiag_eigvals_mixed validates what it is given, so this routine may fail): the
+// sweep always runs over the whole block below l (no search for interior splits, no zero-rotation guard) and only e[l]
+// is tested, against 2^-20 of its neighbours; at most 6 iterations per eigenvalue.  About half the instructions of the
+// guarded version above.
+template <int D>
+__device__ __forceinline__ void ql_tri_eigvals_start_f32(float (&d)[D], float (&e)[D]) {
+#pragma unroll
+    for (int l = 0; l < D - 1; ++l) {
+        for (int iter = 0; iter < 6; ++iter) {
+            const int he = __float_as_int(e[l]) & 0x7fffffff;
+            const int ha = __float_as_int(d[l]) & 0x7fffffff, hb = __float_as_int(d[l + 1]) & 0x7fffffff;
+            if (he + (20 << 23) <= (ha > hb ? ha : hb)) break;
+            const float dl = 0.5f * (d[l + 1] - d[l]);
+            const float e2 = e[l] * e[l];
+            const float hh = fmaf(dl, dl, e2);
+            float g = d[D - 1] - d[l] + __fdividef(e2, dl + copysignf(hh * rsqrtf(hh), dl));
+            float s = 1.0f, c = 1.0f, p = 0.0f;
+#pragma unroll
+            for (int i = D - 2; i >= l; --i) {
+                const float f = s * e[i], b = c * e[i];
+                const float h2 = fmaf(f, f, g * g);
+                const float rr = rsqrtf(h2);
+                e[i + 1] = h2 * rr;
+                s = f * rr;
+                c = g * rr;
+                g = d[i + 1] - p;
+                const float r2 = fmaf(d[i] - g, s, 2.0f * c * b);
+                p = s * r2;
+                d[i + 1] = g + p;
+                g = fmaf(c, r2, -b);
+            }
+            d[l] -= p;
+            e[l] = g;
+            e[D - 1] = 0.0f;
+        }
+    }
+}
+
+// Eigenvalues of a symmetric D x D matrix (upper storage of A, destroyed), all in FP64 -- about 4x fewer FP64 pipe slots
+// than cyclic Jacobi for d = 6.  Callers fall back to Jacobi (relative accuracy) for ill-conditioned matrices.
+template <int D>
+__device__ __forceinline__ void tridiag_ql_eigvals(double (&A)[D][D], double (&d)[D]) {
+    double e[D];
+    householder_tridiag<D>(A, d, e);
+    ql_tri_eigvals<D, double>(d, e);
+}
+
+// 1/x to ~2^-40 relative: hardware seed + one Newton step (the divides below only scale small corrections).
+__device__ __forceinline__ double rcp_fast40(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(fma(-x, r, 1.0), r, r);
+}
+
+// Mixed-precision eigenvalues of the symmetric positive-definite tridiagonal (d, e) (both kept): the data-dependent QL
+// iteration runs in FP32 on the FP32 pipe -- it only has to land each eigenvalue inside the basin of its own root -- and
+// FP64 does two Newton steps per eigenvalue on the characteristic polynomial, evaluated with its derivative by the
+// three-term recurrence (no divisions, fixed trip count, three independent chains in flight).  Work is done on T / trace(T)
+// so that neither precision can over- or underflow.  Validation: every second Newton correction must be >= 1000x smaller
+// than the first (quadratic convergence -> remaining error <= 1e-6 of the second correction) and the eigenvalues must sum
+// to the trace to 1e-13 (two starts that fell to the same root would miss it by their gap).  Returns false when either
+// test fails (near-multiple eigenvalues, FP32 non-convergence, non-positive trace, NaN): the caller then runs the FP64 QL.
+template <int D>
+__device__ __forceinline__ bool tridiag_eigvals_mixed(const double (&d)[D], const double (&e)[D], double (&ev)[D]) {
+    double tr = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) tr += d[k];
+    if (!(tr > 0.0) || !(tr < 1e300)) return false;
+    const double rt = 1.0 / tr;
+    double ds[D], e2[D];
+    float df[D], ef[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        ds[k] = d[k] * rt;
+        const double es = e[k] * rt;
+        e2[k] = es * es;
+        df[k] = (float)ds[k];
+        ef[k] = (float)es;
+    }
+    ql_tri_eigvals_start_f32<D>(df, ef);
+    bool ok = true;
+    double sum = 0.0;
+    constexpr int G = 3;   // eigenvalues refined together
+#pragma unroll
+    for (int g0 = 0; g0 < D; g0 += G) {
+        double x[G], d1[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) x[u] = (g0 + u < D) ? (double)df[g0 + u] : 0.0;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            double p1[G], p2[G], q1[G], q2[G];   // p_k, p_{k-1} and derivatives
+#pragma unroll
+            for (int u = 0; u < G; ++u) { p2[u] = 1.0; q2[u] = 0.0; p1[u] = ds[0] - x[u]; q1[u] = -1.0; }
+#pragma unroll
+            for (int k = 1; k < D; ++k) {
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    const double t = ds[k] - x[u];
+                    const double pn = fma(t, p1[u], -e2[k - 1] * p2[u]);
+                    const double qn = fma(t, q1[u], fma(-e2[k - 1], q2[u], -p1[u]));
+                    p2[u] = p1[u]; q2[u] = q1[u]; p1[u] = pn; q1[u] = qn;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                const double dlt = p1[u] * rcp_fast40(q1[u]);
+                x[u] -= dlt;
+                if (it == 0) d1[u] = fabs(dlt);
+                else if (g0 + u < D) ok = ok && (fabs(dlt) <= fmax(1e-3 * d1[u], 1e-15));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < G; ++u)
+            if (g0 + u < D) { ev[g0 + u] = x[u] * tr; sum += x[u]; }
+    }
+    return ok && (fabs(sum - 1.0) <= 1e-13);
 }
 
 // Lower Cholesky factor of the symmetric matrix S (upper storage read), L lower (L[i][j], j <= i).
