@@ -207,6 +207,50 @@ def test_spd_ai_all_dims_vs_oracle(cuda, d):
     assert rel_err(kst.compute_Kdiag(X), orc.stein_kdiag(X, beta=beta)) < 5e-12
 
 
+@pytest.mark.parametrize('d', [3, 6, 8])
+def test_spd_ai_prescribed_spectra(cuda, d):
+    """Pairs whose generalised eigenvalues are KNOWN: S2 = L Q diag(lam) Q^T L^T with S = L L^T, so that
+    d^2(S, S2) = sum log^2 lam exactly.  The spectra exercise every branch of the eigenvalue routine: all equal and tightly
+    clustered (the Newton refinement cannot validate -> FP64 QL), well separated, and wide (-> Jacobi)."""
+    from gaboflow_b200 import SpdAffineInvariantGaussianKernel
+    rng = np.random.default_rng(700 + d)
+    m = d * (d + 1) // 2
+    base = np.linspace(0.6, 1.9, d)
+    spectra = [np.full(d, 1.7), np.full(d, 1.0), base, base * 3.0,
+               1.0 + 1e-9 * np.arange(d), 1.3 + 1e-6 * np.arange(d), 0.8 + 1e-4 * np.arange(d), 1.1 + 1e-2 * np.arange(d),
+               np.r_[np.full(d - 1, 2.0), 0.5], np.r_[np.full(d // 2, 0.7), np.full(d - d // 2, 1.4)],
+               np.r_[base[:-2], base[-3] * (1 + 3e-8), base[-3] * (1 - 2e-8)],
+               np.geomspace(1e-3, 30.0, d), np.geomspace(0.01, 1.0, d), np.geomspace(1.0, 45.0, d)]
+    n1 = 40
+    A = rng.standard_normal((n1, d, d))
+    S = A @ A.transpose(0, 2, 1) + d * np.eye(d)
+    L = np.linalg.cholesky(S)
+    S2, d2 = [], []
+    for lam in spectra:
+        for _ in range(3):
+            Q, _ = np.linalg.qr(rng.standard_normal((d, d)))
+            S2.append(Q @ np.diag(lam) @ Q.T)
+            d2.append(np.sum(np.log(lam) ** 2))
+    S2 = np.array(S2)
+    d2 = np.array(d2)
+    # every S2 block is paired with every S: S2_ij = L_i C_j L_i^T would differ per row, so instead test the pencil
+    # (S_i, L_i C_j L_i^T) through the diagonal of a rectangular Gram computed row by row
+    X = orc.sym_to_mandel(S)
+    k = SpdAffineInvariantGaussianKernel(m, range(m), beta_min=0.0, beta=0.3, variance=1.0)
+    cond = np.repeat([lam.max() / lam.min() for lam in spectra], 3)
+    for i in range(0, n1, 8):
+        X2 = orc.sym_to_mandel(np.einsum('ab,jbc,dc->jad', L[i], S2, L[i]))
+        Krow = k.compute_K(X[i:i + 1], X2)[0]
+        Kor = orc.spd_ai_gaussian_K(X[i:i + 1], X2, beta=0.3)[0]
+        ref = np.exp(-0.3 * d2)
+        # a pencil with eigenvalue ratio c is only DEFINED to ~1e-16 c by its FP64 entries (measured with
+        # tools/spd_spectra_diag.py: oracle and kernel both sit 1e-11 from the exact value at c = 3e4, 1e-15 apart from
+        # each other everywhere else), so the budget scales with c beyond 1e3
+        tol = np.where(cond > 1e3, 1e-10, RTOL64)
+        assert np.all(np.abs(Krow - Kor) / Kor < tol), float(np.max(np.abs(Krow - Kor) / Kor / tol))
+        assert np.all(np.abs(Krow - ref) / ref < np.where(cond > 1e3, 1e-10, 1e-13)), float(np.max(np.abs(Krow - ref) / ref))
+
+
 def test_spd_row_blocks_and_lower(cuda):
     from gaboflow_b200 import SpdAffineInvariantGaussianKernel
     X = torch.from_numpy(orc.synth_spd_mandel(300, 6, seed=9)).cuda()
