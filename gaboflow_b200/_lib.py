@@ -30,6 +30,8 @@ SIGNATURES = {
     'gabo_trsm_winv_f64': (i32, [i32, i64, i64, vp, i64, vp, vp, i64, vp]),
     'gabo_logdet_f64': (i32, [i64, vp, i64, vp, vp]),
     'gabo_gp_loglik_f64': (i32, [i64, i64, vp, i64, vp, i64, vp, vp]),
+    'gabo_gp_grad_beta_workspace_bytes': (sz, []),
+    'gabo_gp_grad_beta_f64': (i32, [i64, i64, vp, i64, vp, i64, vp, i64, f64, f64, vp, vp, sz, vp]),
     'gabo_gp_predict_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, f64, vp, vp, vp]),
     'gabo_expected_improvement_f64': (i32, [i64, vp, vp, f64, vp, vp]),
     'gabo_profile_trailing_updates': (i32, [i32]),

@@ -622,6 +622,40 @@ __global__ void __launch_bounds__(1024) loglik_kernel(int64_t n, int64_t p, cons
     }
 }
 
+// ---- gradient of the log marginal likelihood w.r.t. the kernel's beta -----------------------------
+// Every kernel of the path is K = variance * exp(beta * g(x, x')), so dK/dbeta = K log(K / variance) / beta, and
+//   d ll / d beta = 1/2 sum_ij G_ij dK_ij/dbeta,   G = alpha alpha^T - p Kinv   (alpha = Ky^-1 (y - m), [n, p]).
+// One pass over the LOWER triangles of K (recomputed by the Gram kernel) and of -Kinv (as gabo_gemm_nt_sub_f64 leaves it):
+// stage 1 writes one partial sum per CTA (rows strided over CTAs), stage 2 adds them in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) grad_beta_partial_kernel(int64_t n, int64_t p, const double* __restrict__ K, int64_t ldk,
+                                                                const double* __restrict__ negKinv, int64_t ldi,
+                                                                const double* __restrict__ alpha, int64_t lda,
+                                                                double inv_variance, double* __restrict__ partial) {
+    __shared__ double sred[32];
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+        for (int64_t j = threadIdx.x; j <= i; j += blockDim.x) {
+            const double k = K[i * ldk + j];
+            if (k > 0.0) {
+                double g = (double)p * negKinv[i * ldi + j];
+                for (int64_t c = 0; c < p; ++c) g = fma(alpha[i * lda + c], alpha[j * lda + c], g);
+                const double w = (j == i) ? 1.0 : 2.0;
+                acc = fma(w * g, k * log(k * inv_variance), acc);
+            }
+        }
+    }
+    const double t = block_sum(acc, sred);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(1024) grad_beta_final_kernel(int nparts, const double* __restrict__ partial, double scale,
+                                                               double* __restrict__ out) {
+    __shared__ double sred[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) acc += partial[i];
+    const double t = block_sum(acc, sred);
+    if (threadIdx.x == 0) out[0] = scale * t;
+}
+
 // mean[j][c] = sum_i A[i][j] V[i][c] + mean_const ; var[j] = kdiag[j] - sum_i A[i][j]^2.  CTA = 32 columns x 32 row lanes.
 __global__ void __launch_bounds__(1024) predict_kernel(int64_t n, int64_t M, int64_t p, const double* __restrict__ A,
                                                        int64_t lda, const double* __restrict__ V, int64_t ldv,
@@ -903,6 +937,38 @@ extern "C" int gabo_logdet_f64(int64_t n, const double* L, int64_t ldl, double* 
     if (n > 0 && L == nullptr) return -2;
     if (ldl < n) return -3;
     loglik_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(n, 1, L, ldl, nullptr, 0, out);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" size_t gabo_gp_grad_beta_workspace_bytes(void) { return 1024 * sizeof(double); }
+
+// out[0] = 1/(2 beta) sum_ij (alpha alpha^T - p Kinv)_ij K_ij log(K_ij / variance), from the lower triangles of K and of
+// negKinv = -Kinv.  Entries with K_ij <= 0 (underflow) contribute nothing.
+extern "C" int gabo_gp_grad_beta_f64(int64_t n, int64_t p, const double* K, int64_t ldk, const double* negKinv, int64_t ldi,
+                                     const double* alpha, int64_t lda, double variance, double beta, double* out,
+                                     void* workspace, size_t workspace_bytes, gabo_stream_t stream_) {
+    if (n < 0) return -1;
+    if (p < 1) return -2;
+    if (out == nullptr) return -11;
+    if (!(variance > 0.0)) return -9;
+    if (beta == 0.0) return -10;
+    if (n > 0) {
+        if (K == nullptr) return -3;
+        if (ldk < n) return -4;
+        if (negKinv == nullptr) return -5;
+        if (ldi < n) return -6;
+        if (alpha == nullptr) return -7;
+        if (lda < p) return -8;
+    }
+    if (workspace == nullptr) return -12;
+    if (workspace_bytes < gabo_gp_grad_beta_workspace_bytes()) return -13;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int nparts = (int)(n < 1024 ? (n > 0 ? n : 1) : 1024);
+    double* partial = static_cast<double*>(workspace);
+    grad_beta_partial_kernel<<<nparts, 256, 0, stream>>>(n, p, K, ldk, negKinv, ldi, alpha, lda, 1.0 / variance, partial);
+    GABO_LAUNCH_CHECK();
+    grad_beta_final_kernel<<<1, 1024, 0, stream>>>(nparts, partial, 0.5 / beta, out);
     GABO_LAUNCH_CHECK();
     return 0;
 }

@@ -101,6 +101,43 @@ class GPR(Parameterized):
         p = int(V.shape[1])
         return mean, cov.unsqueeze(2).expand(-1, -1, p).contiguous()
 
+    def loglik_gradients(self) -> dict:
+        """Analytic derivatives of the log marginal likelihood w.r.t. the VALUES of the hyper-parameters (SURVEY section
+        8f-1; the reference obtains them by TensorFlow autodiff through ``GPR.build_likelihood``):
+
+            d ll / d theta = 1/2 sum_c alpha_c^T dK alpha_c - P/2 tr(Ky^-1 dK),   alpha = Ky^-1 (Y - m),  Ky = K + s2 I
+
+        noise s2: dK = I;  kernel variance v: dK = K/v, which needs only tr(Ky^-1) because K = Ky - s2 I;  beta: every
+        kernel of the path is v exp(beta_eff g), so dK = K log(K/v)/beta_eff, reduced against alpha alpha^T - P Ky^-1 in one
+        pass (``gabo_gp_grad_beta_f64``);  constant mean c: sum(alpha).  Ky^-1 = L^-T L^-1 comes from the cached factor
+        (triangular solve of the identity on the DMMA core, then one symmetric product).  Keys: 'likelihood.variance',
+        'kern.variance', 'kern.<beta name>', 'mean_function.c'."""
+        L, V = self._factorise()
+        n, P = int(V.shape[0]), int(V.shape[1])
+        dev = L.device
+        alpha = V.clone()
+        ops.trsm_(L, alpha, trans=True)
+        Z = torch.eye(n, dtype=torch.float64, device=dev)
+        ops.trsm_(L, Z, trans=False)                                  # L^-1
+        Zt = Z.t().contiguous()
+        neg_kinv = Z.zero_()                                          # reuse the buffer: lower triangle of -Ky^-1
+        ops.gemm_nt_sub_(neg_kinv, Zt, Zt, lower=True)
+        tr_kinv = -float(neg_kinv.diagonal().sum().item())
+        resid = self.Y - self._mean_const()
+        aa = float((alpha * alpha).sum().item())
+        ay = float((alpha * resid).sum().item())
+        s2 = float(self.likelihood.variance)
+        v = float(self.kern.variance)
+        grads = {'likelihood.variance': 0.5 * (aa - P * tr_kinv),
+                 'kern.variance': 0.5 * ((ay - s2 * aa) - P * (n - s2 * tr_kinv)) / v,
+                 'mean_function.c': float(alpha.sum().item())}
+        bname = self.kern.beta_param_name()
+        if bname is not None:
+            Kf = Zt                                                    # reuse: noise-free Gram, lower tiles
+            self.kern.K(self.X, uplo='lower', out=Kf)
+            grads['kern.' + bname] = float(ops.gp_grad_beta(Kf, neg_kinv, alpha, v, self.kern.beta_effective()).item())
+        return grads
+
     # ---- AutoFlow-style NumPy API ---------------------------------------------------------------------
     def compute_log_likelihood(self) -> float:
         return float(self.build_likelihood().item())
@@ -126,12 +163,12 @@ class GPR(Parameterized):
             ps.append(('mean_function.c', self.mean_function.c))
         return ps
 
-    def optimize(self, method='L-BFGS-B', maxiter=1000, **kwargs):
+    def optimize(self, method='L-BFGS-B', maxiter=1000, analytic_grad=True, **kwargs):
         """Maximise the log marginal likelihood over the free hyper-parameters, as ``GPR.optimize()`` of GPflow 0.5 does
         with SciPy L-BFGS-B in the unconstrained (softplus) space (reference call sites: ``sphere_kernels.py:133``,
         ``spd_kernels.py:155-187``).  Every objective evaluation runs on the GPU (Gram -> Cholesky -> solve -> log-lik);
-        gradients are finite differences until the analytic ones exist, which is affordable because
-        the models of the reference have 2-4 hyper-parameters.  Returns the SciPy result."""
+        gradients are analytic (``loglik_gradients``, chained through the softplus transform); ``analytic_grad=False``
+        falls back to SciPy's finite differences.  Returns the SciPy result."""
         from scipy.optimize import minimize
         ps = self._free_params()
         if not ps:
@@ -160,7 +197,24 @@ class GPR(Parameterized):
             except np.linalg.LinAlgError:     # non-PD Gram (e.g. beta below the PD threshold): reject the step
                 return 1e25
 
+        def objective_and_grad(x):
+            set_all(x)
+            try:
+                f = -self.compute_log_likelihood()
+            except np.linalg.LinAlgError:
+                return 1e25, np.zeros_like(x)
+            g = self.loglik_gradients()
+            out = np.empty_like(x)
+            for i, (name, p) in enumerate(ps):
+                dval = 1.0 if p.transform != 'positive' else -np.expm1(-float(p))    # d softplus(x)/dx = 1 - exp(-value)
+                out[i] = -g[name] * dval
+            return f, out
+
         x0 = np.array([to_free(p) for _, p in ps], dtype=np.float64)
-        res = minimize(objective, x0, method=method, options={'maxiter': maxiter}, **kwargs)
+        known = {'likelihood.variance', 'kern.variance', 'mean_function.c', 'kern.' + str(self.kern.beta_param_name())}
+        if analytic_grad and all(name in known for name, _ in ps):
+            res = minimize(objective_and_grad, x0, method=method, jac=True, options={'maxiter': maxiter}, **kwargs)
+        else:
+            res = minimize(objective, x0, method=method, options={'maxiter': maxiter}, **kwargs)
         set_all(res.x)
         return res

@@ -238,6 +238,21 @@ def gp_loglik(L_: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gp_grad_beta(K: torch.Tensor, neg_kinv: torch.Tensor, alpha: torch.Tensor, variance: float, beta: float) -> torch.Tensor:
+    """d loglik / d beta for a kernel variance * exp(beta g): 1/(2 beta) sum_ij (alpha alpha^T - p Kinv)_ij K_ij log(K_ij/variance),
+    from the lower triangles of the noise-free Gram K and of neg_kinv = -(K + sigma^2 I)^-1 (gabo_gp_grad_beta_f64)."""
+    _req(K, 'K'); _req(neg_kinv, 'neg_kinv'); _req(alpha, 'alpha')
+    n, p = int(alpha.shape[0]), int(alpha.shape[1])
+    out = torch.empty((1,), dtype=torch.float64, device=K.device)
+    Lh = _lib.lib()
+    ws = torch.empty(int(Lh.gabo_gp_grad_beta_workspace_bytes()), dtype=torch.uint8, device=K.device)
+    ld = lambda t: max(int(t.stride(0)), int(t.shape[1])) if t.shape[0] > 1 else int(t.shape[1])
+    st = Lh.gabo_gp_grad_beta_f64(n, p, K.data_ptr(), ld(K), neg_kinv.data_ptr(), ld(neg_kinv), alpha.data_ptr(), ld(alpha),
+                                  float(variance), float(beta), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check('gabo_gp_grad_beta_f64', st)
+    return out
+
+
 def gp_predict(A: torch.Tensor, V: torch.Tensor, kdiag: torch.Tensor, mean_const: float = 0.0):
     """mean[M,p] = A^T V + mean_const, var[M] = kdiag - colsum(A*A) from A = L^-1 K(X,X*) and V = L^-1 (y-m)."""
     _req(A, 'A'); _req(V, 'V'); _req(kdiag, 'kdiag')

@@ -99,6 +99,19 @@ class Kern(Parameterized):
     def Kdiag(self, X):
         raise NotImplementedError
 
+    # analytic hyper-parameter gradients (gaboflow_b200.gpr): every kernel of the path has the form
+    # variance * exp(beta_eff * g(x, x')) with beta_eff = <beta Param> + constant shift, which is all GPR needs to know
+    def beta_param_name(self):
+        for name in ('beta_shifted', 'beta', 'beta_param'):
+            if isinstance(self.__dict__.get(name), Param):
+                return name
+        return None
+
+    def beta_effective(self) -> float:
+        if hasattr(self, '_beta_eff'):
+            return float(self._beta_eff())
+        return float(self.__dict__[self.beta_param_name()])
+
     # AutoFlow-style wrappers: NumPy in, NumPy out (host<->device copies included)
     def compute_K(self, X, Z):
         return self.K(X, Z).cpu().numpy()

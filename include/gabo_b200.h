@@ -145,6 +145,15 @@ int gabo_gp_loglik_f64(int64_t n, int64_t p, const double* L, int64_t ldl,
                        const double* alpha, int64_t ldalpha, double* out, gabo_stream_t stream);
 /* Posterior at M test points from A = L^-1 K(X,X*) [n,M] and V = L^-1 (y-m) [n,p]:
  *   mean[M,p] = A^T V + mean_const ;  var[M] = kdiag[M] - colsum(A*A)   (GPR.build_predict, full_cov False). */
+/* gabo_gp_grad_beta_f64: derivative of the log marginal likelihood w.r.t. the kernel's beta (the
+ *   reference gets it from TensorFlow autodiff through GPflow's GPR.build_likelihood).  Every kernel of the path is
+ *   K = variance * exp(beta * g), hence dK/dbeta = K log(K/variance) / beta and
+ *   out[0] = 1/(2 beta) sum_ij (alpha alpha^T - p Kinv)_ij K_ij log(K_ij/variance), read from the LOWER triangles of K
+ *   (noise-free Gram) and negKinv = -(K + sigma^2 I)^-1; alpha [n, p] = (K + sigma^2 I)^-1 (y - m).  Deterministic. */
+size_t gabo_gp_grad_beta_workspace_bytes(void);
+int gabo_gp_grad_beta_f64(int64_t n, int64_t p, const double* K, int64_t ldk, const double* negKinv, int64_t ldi,
+                          const double* alpha, int64_t lda, double variance, double beta, double* out,
+                          void* workspace, size_t workspace_bytes, gabo_stream_t stream);
 int gabo_gp_predict_f64(int64_t n, int64_t M, int64_t p, const double* A, int64_t lda,
                         const double* V, int64_t ldv, const double* kdiag, double mean_const,
                         double* mean_out, double* var_out, gabo_stream_t stream);

@@ -194,3 +194,77 @@ def test_trsm_with_supplied_block_inverses(cuda):
             ops.trsm_(d, Bd, trans=trans, winv_all=winv)
             want = sla.solve_triangular(ref, B, lower=True, trans='T' if trans else 'N')
             assert np.max(np.abs(Bd.cpu().numpy() - want)) / np.max(np.abs(want)) < 1e-12
+
+
+def _fd(f, h):
+    return (f(+h) - f(-h)) / (2.0 * h)
+
+
+def test_loglik_gradients_vs_oracle_finite_differences(cuda):
+    """GPR.loglik_gradients (analytic, gabo_gp_grad_beta_f64 + trace identities) against central finite differences of
+    the ORACLE's log-likelihood: sphere Gaussian with beta_min shift, two output columns, constant mean."""
+    from gaboflow_b200 import GPR, SphereGaussianKernel
+    from gaboflow_b200.gpr import Constant
+    n = 300
+    X = orc.synth_sphere(n, 3, seed=21)
+    Y = np.random.default_rng(22).standard_normal((n, 2))
+    bmin, b, v, s2, c = 1.5, 2.5, 1.7, 0.3, 0.2
+    k = SphereGaussianKernel(3, range(3), beta_min=bmin, beta=b, variance=v)
+    m = GPR(X, Y, kern=k, mean_function=Constant(c))
+    m.likelihood.variance = s2
+    g = m.loglik_gradients()
+    ll = lambda bb, vv, ss, cc: orc.gp_loglik(orc.sphere_gaussian_K(X, beta=bb + bmin, variance=vv), Y, ss, mean=cc)
+    ref = {'kern.beta_shifted': _fd(lambda h: ll(b + h, v, s2, c), 1e-5),
+           'kern.variance': _fd(lambda h: ll(b, v + h, s2, c), 1e-5),
+           'likelihood.variance': _fd(lambda h: ll(b, v, s2 + h, c), 1e-5),
+           'mean_function.c': _fd(lambda h: ll(b, v, s2, c + h), 1e-5)}
+    for name, r in ref.items():
+        assert abs(g[name] - r) < 1e-6 * max(1.0, abs(r)), (name, g[name], r)
+
+
+@pytest.mark.parametrize('which', ['sphere_laplace', 'spd_ai', 'spd_stein', 'spd_logeuclid'])
+def test_loglik_gradients_other_kernels(cuda, which):
+    """Same check for the other kernel families, with finite differences of the GPU log-likelihood itself."""
+    from gaboflow_b200 import (GPR, SphereLaplaceKernel, SpdAffineInvariantGaussianKernel, SpdSteinGaussianKernel,
+                               SpdLogEuclideanGaussianKernel)
+    n = 160
+    if which == 'sphere_laplace':
+        X = orc.synth_sphere(n, 4, seed=31)
+        k = SphereLaplaceKernel(4, range(4), beta=1.3, variance=0.9)
+    else:
+        X = orc.synth_spd_mandel(n, 3, seed=32)
+        if which == 'spd_ai':
+            k = SpdAffineInvariantGaussianKernel(6, range(6), beta_min=0.2, beta=0.4, variance=1.2)
+        elif which == 'spd_stein':
+            k = SpdSteinGaussianKernel(6, range(6), beta=1.6, variance=1.1)
+        else:
+            k = SpdLogEuclideanGaussianKernel(6, range(6), beta=0.5, variance=0.8)
+    y = np.random.default_rng(33).standard_normal((n, 1))
+    m = GPR(X, y, kern=k)
+    m.likelihood.variance = 0.25
+    g = m.loglik_gradients()
+    bname = k.beta_param_name()
+    for name, par in (('kern.' + bname, getattr(k, bname)), ('kern.variance', k.variance),
+                      ('likelihood.variance', m.likelihood.variance)):
+        v0 = float(par)
+
+        def f(h, par=par, v0=v0):
+            par.assign(v0 + h)
+            out = m.compute_log_likelihood()
+            par.assign(v0)
+            return out
+        r = _fd(f, 1e-5 * max(1.0, abs(v0)))
+        assert abs(g[name] - r) < 2e-6 * max(1.0, abs(r)), (which, name, g[name], r)
+
+
+def test_optimize_with_analytic_gradients_matches_finite_difference_run(cuda, golden):
+    from gaboflow_b200 import GPR, SphereGaussianKernel
+    g = golden['sphere_s2']
+    runs = []
+    for analytic in (True, False):
+        k = SphereGaussianKernel(input_dim=3, active_dims=range(3), beta_min=7.0, beta=10.0, variance=1.)
+        m = GPR(g['x_man'], g['y_train'], kern=k)
+        res = m.optimize(analytic_grad=analytic)
+        runs.append((m.compute_log_likelihood(), res.nfev))
+    assert abs(runs[0][0] - runs[1][0]) < 1e-4 * abs(runs[1][0])
+    assert runs[0][1] < runs[1][1]            # fewer likelihood evaluations than finite differences
