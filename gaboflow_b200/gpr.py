@@ -71,7 +71,7 @@ class GPR(Parameterized):
             return self._L, self._V
         n = int(self.X.shape[0])
         if self._L is None or self._L.shape[0] != n:
-            self._L = torch.empty((n, n), dtype=torch.float64, device=self.X.device)
+            self._L = self._factor_view(n)
         self.kern.K(self.X, uplo='lower', out=self._L)
         ops.potrf_(self._L, float(self.likelihood.variance), check=True)
         V = (self.Y - self._mean_const()).contiguous()
@@ -79,6 +79,47 @@ class GPR(Parameterized):
         self._V = V
         self._cache_key = key
         return self._L, self._V
+
+    def _factor_view(self, n: int) -> torch.Tensor:
+        """[n, n] view of the factor buffer, which is allocated with head-room so that ``append`` grows in place."""
+        buf = getattr(self, '_Lbuf', None)
+        if buf is None or buf.shape[0] < n:
+            cap = max(256, ((n + n // 8 + 255) // 256) * 256)
+            new = torch.empty((cap, cap), dtype=torch.float64, device=self.X.device)
+            if buf is not None and self._L is not None and self._L.shape[0] <= n:
+                m = int(self._L.shape[0])
+                new[:m, :m].copy_(self._L)
+            self._Lbuf = buf = new
+        return buf[:n, :n]
+
+    def append(self, x_new, y_new) -> None:
+        """Add ONE observation without refactorising (the reference rebuilds the whole model per BO
+        iteration, ``examples/bo_sphere/...``).  With Ky' = [[Ky, k], [k^T, k** + s2]] the factor gains one row:
+
+            l = L^-1 k  (gabo_trsm_f64, one right-hand side),   d = sqrt(k** + s2 - l^T l),   L' = [[L, 0], [l^T, d]]
+
+        and V' = L'^-1 (Y' - m) gains the entry (y_new - m - l^T V) / d.  O(N^2) instead of O(N^3); hyper-parameters are
+        unchanged, so the cached factor stays valid.  Raises LinAlgError if the extended matrix is not positive definite."""
+        L, V = self._factorise()
+        n, P = int(V.shape[0]), int(V.shape[1])
+        xn = to_device(x_new).reshape(1, -1)
+        yn = to_device(y_new).reshape(1, P)
+        k = self.kern.K(self.X, xn).contiguous()                      # [n, 1]
+        kss = float(self.kern.Kdiag(xn)[0].item()) + float(self.likelihood.variance)
+        ops.trsm_(L, k, trans=False)                                  # l
+        d2 = kss - float((k * k).sum().item())
+        if not d2 > 0.0:
+            raise np.linalg.LinAlgError('append: the extended covariance is not positive definite')
+        d = float(np.sqrt(d2))
+        Lnew = self._factor_view(n + 1)                               # may move the factor into a larger buffer
+        Lnew[n, :n].copy_(k[:, 0])
+        Lnew[n, n] = d
+        vnew = (yn - self._mean_const() - k.t() @ V) / d              # [1, P]
+        self.X = torch.cat([self.X, xn], dim=0)
+        self.Y = torch.cat([self.Y, yn], dim=0)
+        self._L = Lnew
+        self._V = torch.cat([V, vnew], dim=0)
+        self._cache_key = self._key()
 
     # ---- device-level graph pieces (GPflow: build_likelihood / build_predict) --------------------------
     def build_likelihood(self) -> torch.Tensor:

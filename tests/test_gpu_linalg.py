@@ -268,3 +268,31 @@ def test_optimize_with_analytic_gradients_matches_finite_difference_run(cuda, go
         runs.append((m.compute_log_likelihood(), res.nfev))
     assert abs(runs[0][0] - runs[1][0]) < 1e-4 * abs(runs[1][0])
     assert runs[0][1] < runs[1][1]            # fewer likelihood evaluations than finite differences
+
+
+def test_gpr_append_matches_refactorisation(cuda):
+    """GPR.append (rank-1 growth of the cached factor) against a model rebuilt from scratch on the same data."""
+    from gaboflow_b200 import GPR, SphereGaussianKernel
+    n0, extra = 250, 9                      # crosses the 256-row capacity of the first factor buffer
+    X = orc.synth_sphere(n0 + extra, 3, seed=41)
+    y = np.random.default_rng(42).standard_normal((n0 + extra, 1))
+    Xs = orc.synth_sphere(17, 3, seed=43)
+    mk = lambda: SphereGaussianKernel(3, range(3), beta_min=1.0, beta=2.0, variance=1.4)
+    m = GPR(X[:n0], y[:n0], kern=mk())
+    m.likelihood.variance = 0.05
+    m.compute_log_likelihood()
+    for i in range(n0, n0 + extra):
+        m.append(X[i], y[i])
+    full = GPR(X, y, kern=mk())
+    full.likelihood.variance = 0.05
+    assert abs(m.compute_log_likelihood() / full.compute_log_likelihood() - 1) < 1e-11
+    La, Lf = m._factorise()[0], full._factorise()[0]
+    assert float((torch.tril(La) - torch.tril(Lf)).abs().max()) < 1e-11
+    ma, va = m.predict_f(Xs)
+    mf, vf = full.predict_f(Xs)
+    assert np.max(np.abs(ma - mf)) < 1e-10 and np.max(np.abs(va - vf)) < 1e-10
+    with pytest.raises(np.linalg.LinAlgError):          # a duplicate point with zero noise is singular
+        m2 = GPR(X[:50], y[:50], kern=mk())
+        m2.likelihood.variance = 1e-300
+        m2.compute_log_likelihood()
+        m2.append(X[3], y[3])
