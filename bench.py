@@ -197,7 +197,8 @@ def run_ours(args):
     # W = 2: symmetry is exploited across the two GPUs (each computes the lower tiles of its panels and stores the mirror
     # tiles into the peer's HBM over NVLink).  W >= 4: every rank recomputes the full rows of its panels -- measured on
     # B200, producing an entry on the FP64 pipe (~3 ps) is ~4x cheaper than moving it over NVLink (8 B at ~0.5 TB/s).
-    p2p_mirror = (world == 2 and N % PANEL == 0 and not args.no_p2p)
+    p2p_mirror = (world >= 2 and N % PANEL == 0 and not args.no_p2p)
+    gram_frac = int(os.environ.get('GABO_GRAM_RECOMPUTE_FRAC256', '96'))
     peers = None
     if p2p_mirror:
         peers = PeerBuffers(rows, N, dev)
@@ -208,7 +209,8 @@ def run_ours(args):
     xch = None
     if world > 1 and NC % PANEL == 0 and os.environ.get('GABO_DIST_P2P', '1') != '0':
         xch = PanelExchange(BlockCyclic(NC, PANEL, world, rank), NC, dev)
-    ws = torch.empty(int(lib.gabo_points_gram_workspace_bytes(N, N, DIM)), dtype=torch.uint8, device=dev)
+    ws = torch.empty(int(max(lib.gabo_points_gram_workspace_bytes(N, N, DIM), lib.gabo_points_gram_cyclic_workspace_bytes(N, DIM))),
+                     dtype=torch.uint8, device=dev)
     grow = lay.global_rows()
     sel_fac = (grow < NC).to(dev)
     y_rows = grow[grow < NC].to(dev)
@@ -234,7 +236,8 @@ def run_ours(args):
         if world == 1:
             ops.points_gram(ops.SPHERE_GAUSSIAN, Xd, None, beta=BETA, variance=VARIANCE, out=K, uplo='mirror', workspace=ws)
         elif p2p_mirror:
-            gram_block_cyclic_mirrored(ops.SPHERE_GAUSSIAN, Xd, lay, peers, BETA, VARIANCE, workspace=ws, sync=True)
+            gram_block_cyclic_mirrored(ops.SPHERE_GAUSSIAN, Xd, lay, peers, BETA, VARIANCE, workspace=ws, sync=True,
+                                       recompute_frac256=gram_frac)
         else:
             for pnl in lay.my_panels():
                 sl = lay.slot(pnl) * PANEL
@@ -368,8 +371,9 @@ def run_ours(args):
         'config': {'workload': f'sphere Gaussian Gram N={N} on S^50 (D={DIM}) + FP64 Cholesky of K+1e-2 I at N={NC} + solve + loglik',
                    'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2, 'seeds': [SEED_X, SEED_Y],
                    'gram_mode': 'lower tiles computed once, mirror-stored (full dense K)' if world == 1 else
-                                (f'{PANEL}-row panels block-cyclic over {world} ranks; lower tiles computed by the row owner, mirror tiles '
-                                 f'stored into the peer GPU over NVLink from inside the kernel' if p2p_mirror else
+                                (f'{PANEL}-row panels block-cyclic over {world} ranks; lower tiles computed by the row owner; upper tiles: '
+                                 f'{gram_frac}/256 of the cross-GPU panel pairs recomputed by their row owner, the rest stored into the '
+                                 f'owning GPU over NVLink from inside the kernel (full dense K)' if p2p_mirror else
                                  f'full rows of the dense K in {PANEL}-row panels, 1-D block-cyclic over {world} ranks'),
                    'l2': f'no flush: {rows * N * 8 / 1e9:.1f} GB of K per GPU >> 126 MB L2',
                    'parallelism': 'single GPU' if world == 1 else

@@ -17,6 +17,7 @@
 //     registers; the epilogue (clamp, acos, square, scale, exp, variance) runs on those registers and stores
 //     with streaming 128-bit writes; the symmetric mode computes lower tiles only and mirror-stores them
 //     (both stores fill whole 32-byte sectors: 64 B per quad row / per 8-lane column group).
+#include <vector>
 #include "gabo_common.cuh"
 #include "gabo_math.cuh"
 
@@ -50,13 +51,40 @@ struct GramParams {
     // is this GPU's own buffer, the others are NVLink peer mappings)
     int cyc_world, cyc_rank;
     double* peer[8];
+    // hybrid mode: a panel pair (PI > PJ) owned by DIFFERENT ranks and selected by cyclic_recompute() is NOT mirrored over
+    // NVLink; the owner of row panel PJ recomputes that upper block itself ("extra" tiles, enumerated after the
+    // cyc_lower_tiles lower tiles; cyc_extra lists their (local slot, PI) pairs).  cyc_frac == 0: everything is mirrored.
+    int cyc_frac;
+    int64_t cyc_lower_tiles;
+    const int32_t* cyc_extra;
 };
 
 constexpr int CYC_PT = 4;   // tiles per 512-row panel
 
-// u-th lower tile owned by this rank -> local row tile lt, global row tile gbi, column tile bj.
-// Tiles before local slot s: C(s) = 8 W s (s-1) + (16 rank + 10) s   (rows of global panel s W + rank own 4P+1 .. 4P+4 tiles).
-__device__ __forceinline__ void cyclic_tile_coords(const GramParams& p, int64_t u, int64_t& lt, int64_t& gbi, int64_t& bj) {
+// Hybrid mode: is the upper block (PJ rows, PI columns), PI > PJ, recomputed by the owner of PJ instead of mirrored to it?
+// Only pairs owned by different ranks qualify (a same-rank mirror never touches NVLink); a hash of the pair selects
+// frac256 / 256 of them, uniformly over ranks and panels.
+__host__ __device__ __forceinline__ bool cyclic_recompute(int64_t PI, int64_t PJ, int world, int frac256) {
+    if (frac256 <= 0 || PI % world == PJ % world) return false;
+    uint32_t h = (uint32_t)PI * 0x9E3779B1u ^ (uint32_t)PJ * 0x85EBCA77u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    return (int)(h & 255u) < frac256;
+}
+
+// u-th tile owned by this rank -> local row tile lt, global row tile gbi, column tile bj; extra = recomputed upper tile.
+// Lower tiles before local slot s: C(s) = 8 W s (s-1) + (16 rank + 10) s   (rows of global panel s W + rank own 4P+1 .. 4P+4 tiles).
+__device__ __forceinline__ void cyclic_tile_coords(const GramParams& p, int64_t u, int64_t& lt, int64_t& gbi, int64_t& bj,
+                                                   bool& extra) {
+    extra = u >= p.cyc_lower_tiles;
+    if (extra) {
+        const int64_t e = u - p.cyc_lower_tiles;
+        const int64_t s = p.cyc_extra[2 * (e / 16)], PI = p.cyc_extra[2 * (e / 16) + 1];
+        const int64_t rr = (e % 16) / 4, cc = e % 4;
+        lt = s * CYC_PT + rr;
+        gbi = (s * p.cyc_world + p.cyc_rank) * CYC_PT + rr;
+        bj = PI * CYC_PT + cc;
+        return;
+    }
     const double W = (double)p.cyc_world, b = 16.0 * p.cyc_rank + 10.0 - 8.0 * W;
     int64_t s = (int64_t)floor((-b + sqrt(b * b + 32.0 * W * (double)u)) / (16.0 * W));
     if (s < 0) s = 0;
@@ -291,7 +319,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
     auto issue = [&](int64_t tl) {
         const int64_t t = (int64_t)blockIdx.x + tl * gridDim.x;
         int64_t bi, bj, gbi;
-        if (CYC) cyclic_tile_coords(p, t, bi, gbi, bj);
+        bool extra = false;
+        if (CYC) cyclic_tile_coords(p, t, bi, gbi, bj, extra);
         else { tile_coords(p, t, bi, bj); gbi = p.tile_r0 + bi; }
         const int s = (int)(tl & 1);
         mbar_arrive_expect_tx(&full_bar[s], 2 * TILE_BYTES);
@@ -306,10 +335,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
         if (tid == 0 && tl + 1 < my_tiles) issue(tl + 1);
         const int64_t t = (int64_t)blockIdx.x + tl * gridDim.x;
         int64_t bi, bj, gbi;
-        if (CYC) cyclic_tile_coords(p, t, bi, gbi, bj);
+        bool extra = false;
+        if (CYC) cyclic_tile_coords(p, t, bi, gbi, bj, extra);
         else { tile_coords(p, t, bi, bj); gbi = p.tile_r0 + bi; }
         const int64_t grow_tile = gbi * BT, gcol_tile = bj * BT;
-        const bool mirror = (p.uplo == GABO_SYMM_MIRROR) && (gcol_tile != grow_tile);
+        bool mirror = (p.uplo == GABO_SYMM_MIRROR) && (gcol_tile != grow_tile);
+        if (CYC) {   // hybrid: recomputed upper tiles have no mirror image to write, and their lower twins do not send one
+            const int64_t PI = gbi / CYC_PT, PJ = bj / CYC_PT;
+            if (extra || cyclic_recompute(PI, PJ, p.cyc_world, p.cyc_frac)) mirror = false;
+        }
         const bool diag_tile = p.symmetric && (gcol_tile == grow_tile);
         // where the tile and its mirror image are stored: rows of K are local rows of this rank (CYC: local row tile bi),
         // the mirror image belongs to the rank that owns global row panel bj / CYC_PT
@@ -489,7 +523,7 @@ int points_gram_impl(int kind, const Tin* X, int64_t n1, int64_t ldx, const Tin*
     p.symmetric = symmetric ? 1 : 0;
     p.vec_ok = ((ldk % 2) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0) ? 1 : 0;
     p.beta = beta; p.variance = variance;
-    p.cyc_world = 0; p.cyc_rank = 0;
+    p.cyc_world = 0; p.cyc_rank = 0; p.cyc_frac = 0; p.cyc_lower_tiles = 0; p.cyc_extra = nullptr;
     for (int r = 0; r < 8; ++r) p.peer[r] = nullptr;
     p.tile_r0 = row0 / BT;
     p.tiles_m = ceil_div64(row1 - row0, BT);
@@ -525,7 +559,25 @@ extern "C" int gabo_points_gram_f64(int kind, const double* X, int64_t n1, int64
 extern "C" int gabo_points_gram_cyclic_f64(int kind, const double* X, int64_t n, int64_t ldx, int dim, double beta,
                                            double variance, double* const* K_bases_host, int64_t ldk, int world, int rank,
                                            void* workspace, size_t workspace_bytes, gabo_stream_t stream_) {
+    return gabo_points_gram_cyclic_hybrid_f64(kind, X, n, ldx, dim, beta, variance, K_bases_host, ldk, world, rank, 0,
+                                              workspace, workspace_bytes, stream_);
+}
+
+extern "C" size_t gabo_points_gram_cyclic_workspace_bytes(int64_t n, int dim) {
+    if (n <= 0 || dim <= 0) return 0;
+    const int64_t npanels = (n + 511) / 512;
+    return gabo_points_gram_workspace_bytes(n, n, dim) + (size_t)(npanels * npanels + 64) * sizeof(int32_t);
+}
+
+// Same, with part of the upper triangle RECOMPUTED instead of mirrored: recompute_frac256 / 256 of the panel pairs owned
+// by different ranks (chosen by a hash of the pair, cyclic_recompute) are produced by the owner of the ROW panel itself,
+// the others arrive as mirror stores from the owner of the column panel.  Balances the FP64 pipe against NVLink.
+extern "C" int gabo_points_gram_cyclic_hybrid_f64(int kind, const double* X, int64_t n, int64_t ldx, int dim, double beta,
+                                                  double variance, double* const* K_bases_host, int64_t ldk, int world,
+                                                  int rank, int recompute_frac256, void* workspace, size_t workspace_bytes,
+                                                  gabo_stream_t stream_) {
     using namespace gabo;
+    if (recompute_frac256 < 0 || recompute_frac256 > 256) return -12;
     if (kind < GABO_SPHERE_GAUSSIAN || kind > GABO_SQDIST_GAUSSIAN) return -1;
     if (n < 0) return -3;
     if (n == 0) return 0;
@@ -539,9 +591,10 @@ extern "C" int gabo_points_gram_cyclic_f64(int kind, const double* X, int64_t n,
     if (n % (BT * CYC_PT) != 0) return -3;            // whole 512-row panels only
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PackPlan pl = make_plan(n, n, dim);
-    const size_t need = pl.bytesA + pl.bytesNorm1;
-    if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return -12;
-    if (workspace_bytes < need) return -13;
+    const size_t pack_bytes = align256(pl.bytesA + pl.bytesNorm1);
+    const size_t need = recompute_frac256 > 0 ? gabo_points_gram_cyclic_workspace_bytes(n, dim) : pl.bytesA + pl.bytesNorm1;
+    if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return -13;
+    if (workspace_bytes < need) return -14;
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     double* Ap = reinterpret_cast<double*>(ws);
     double* nA = reinterpret_cast<double*>(ws + pl.bytesA);
@@ -559,7 +612,27 @@ extern "C" int gabo_points_gram_cyclic_f64(int kind, const double* X, int64_t n,
     p.tile_r0 = 0; p.tiles_m = nslots * CYC_PT; p.tiles_n = n / BT;
     p.cyc_world = world; p.cyc_rank = rank;
     for (int r = 0; r < 8; ++r) p.peer[r] = (r < world) ? K_bases_host[r] : nullptr;
-    p.ntiles = 8 * (int64_t)world * nslots * (nslots - 1) + (16 * (int64_t)rank + 10) * nslots;
+    p.cyc_lower_tiles = 8 * (int64_t)world * nslots * (nslots - 1) + (16 * (int64_t)rank + 10) * nslots;
+    p.cyc_frac = recompute_frac256;
+    p.cyc_extra = nullptr;
+    int64_t extra_pairs = 0;
+    if (recompute_frac256 > 0) {
+        // (local slot, column panel) of every upper block this rank recomputes; small (< npanels^2 / 2 entries), rebuilt and
+        // uploaded per call (a pageable-source cudaMemcpyAsync has consumed the host buffer when it returns)
+        std::vector<int32_t> list;
+        for (int64_t sl = 0; sl < nslots; ++sl) {
+            const int64_t PJ = sl * world + rank;
+            for (int64_t PI = PJ + 1; PI < npanels; ++PI)
+                if (cyclic_recompute(PI, PJ, world, recompute_frac256)) { list.push_back((int32_t)sl); list.push_back((int32_t)PI); }
+        }
+        extra_pairs = (int64_t)list.size() / 2;
+        if (pack_bytes + list.size() * sizeof(int32_t) > workspace_bytes) return -14;
+        int32_t* dlist = reinterpret_cast<int32_t*>(ws + pack_bytes);
+        if (!list.empty())
+            GABO_CUDA_TRY(cudaMemcpyAsync(dlist, list.data(), list.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+        p.cyc_extra = dlist;
+    }
+    p.ntiles = p.cyc_lower_tiles + 16 * extra_pairs;
     if (p.K == nullptr) return -8;
     if (pl.kld == 4) return launch_points_gram<4>(p, stream);
     if (pl.kld == 20) return launch_points_gram<20>(p, stream);

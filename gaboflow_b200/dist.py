@@ -414,13 +414,17 @@ class PeerBuffers:
 
 
 def gram_block_cyclic_mirrored(kind: int, X: torch.Tensor, layout: BlockCyclic, peers: PeerBuffers, beta: float,
-                               variance: float, workspace=None, group=None, sync: bool = True) -> torch.Tensor:
+                               variance: float, workspace=None, group=None, sync: bool = True,
+                               recompute_frac256: int = 0) -> torch.Tensor:
     """Symmetric Gram K(X,X) into the block-cyclic row panels of all ranks: each rank computes the lower tiles of its own
-    panels once and writes their mirror images into the owning peers' memory from inside the kernel."""
+    panels once and writes their mirror images into the owning peers' memory from inside the kernel.  With
+    ``recompute_frac256 = f``, f/256 of the panel pairs owned by different ranks are recomputed by the row owner instead of
+    mirrored, which balances the FP64 pipe against NVLink."""
     from . import ops
     if layout.nb != 512:
         raise ValueError('the mirrored Gram uses 512-row panels')
-    ops.points_gram_cyclic(kind, X, peers.ptrs, int(peers.local.stride(0)), layout.world, layout.rank, beta, variance, workspace)
+    ops.points_gram_cyclic(kind, X, peers.ptrs, int(peers.local.stride(0)), layout.world, layout.rank, beta, variance, workspace,
+                           recompute_frac256=recompute_frac256)
     if sync:
         torch.cuda.synchronize(X.device)
         if layout.world > 1:

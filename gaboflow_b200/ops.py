@@ -395,21 +395,22 @@ def solve_update_(Y: torch.Tensor, Lp: torch.Tensor, X: torch.Tensor) -> torch.T
 
 
 def points_gram_cyclic(kind: int, X: torch.Tensor, bases, ldk: int, world: int, rank: int, beta: float = 1.0,
-                       variance: float = 1.0, workspace: Optional[torch.Tensor] = None) -> None:
-    """Block-cyclic symmetric Gram with peer-memory mirror stores (gabo_points_gram_cyclic_f64).  `bases`: list of `world`
-    device pointers (ints), entry r = base of rank r's local buffer as mapped in this process."""
+                       variance: float = 1.0, workspace: Optional[torch.Tensor] = None, recompute_frac256: int = 0) -> None:
+    """Block-cyclic symmetric Gram with peer-memory mirror stores (gabo_points_gram_cyclic_hybrid_f64).  `bases`: list of
+    `world` device pointers (ints), entry r = base of rank r's local buffer as mapped in this process.  recompute_frac256 = f:
+    f/256 of the panel pairs owned by different ranks are recomputed by the row owner instead of mirrored over NVLink."""
     import ctypes as C
     L = _lib.lib()
     X = _rowmajor2d(_req(X, 'X'))
     n, dim = int(X.shape[0]), int(X.shape[1])
-    nbytes = int(L.gabo_points_gram_workspace_bytes(n, n, dim))
+    nbytes = int(L.gabo_points_gram_cyclic_workspace_bytes(n, dim))
     if workspace is None or workspace.numel() < nbytes:
         workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=X.device)
     arr = (C.c_void_p * world)(*[C.c_void_p(int(b)) for b in bases])
-    st = L.gabo_points_gram_cyclic_f64(int(kind), X.data_ptr(), n, _ld(X), dim, float(beta), float(variance),
-                                       C.cast(arr, C.c_void_p), int(ldk), int(world), int(rank),
-                                       workspace.data_ptr(), workspace.numel(), _stream())
-    _lib.check('gabo_points_gram_cyclic_f64', st)
+    st = L.gabo_points_gram_cyclic_hybrid_f64(int(kind), X.data_ptr(), n, _ld(X), dim, float(beta), float(variance),
+                                              C.cast(arr, C.c_void_p), int(ldk), int(world), int(rank), int(recompute_frac256),
+                                              workspace.data_ptr(), workspace.numel(), _stream())
+    _lib.check('gabo_points_gram_cyclic_hybrid_f64', st)
 
 
 def expected_improvement(mean: torch.Tensor, var: torch.Tensor, fmin: float) -> torch.Tensor:

@@ -202,6 +202,14 @@ size_t gabo_trsm_right_workspace_bytes(int64_t m, int64_t nb);
 int gabo_points_gram_cyclic_f64(int kind, const double* X, int64_t n, int64_t ldx, int dim, double beta, double variance,
                                 double* const* K_bases_host, int64_t ldk, int world, int rank,
                                 void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+/* gabo_points_gram_cyclic_hybrid_f64: as above, but recompute_frac256 / 256 of the panel pairs owned by DIFFERENT ranks
+ *   (selected by a hash of the pair) are RECOMPUTED by the owner of the row panel instead of being mirrored to it over
+ *   NVLink (0: mirror all).  Producing an entry costs ~3 ps of FP64 pipe, moving it ~10 ps of NVLink: recomputing part of the
+ *   upper triangle balances the two.  Workspace: gabo_points_gram_cyclic_workspace_bytes(n, dim). */
+size_t gabo_points_gram_cyclic_workspace_bytes(int64_t n, int dim);
+int gabo_points_gram_cyclic_hybrid_f64(int kind, const double* X, int64_t n, int64_t ldx, int dim, double beta,
+                                       double variance, double* const* K_bases_host, int64_t ldk, int world, int rank,
+                                       int recompute_frac256, void* workspace, size_t workspace_bytes, gabo_stream_t stream);
 int gabo_trsm_right_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, double* A, int64_t lda,
                         void* workspace, size_t workspace_bytes, gabo_stream_t stream);
 /* gabo_potrf_diag_f64: factor one diagonal block (nb <= 512) in place AND return the inverses of its 128 x 128 diagonal

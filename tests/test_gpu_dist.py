@@ -69,20 +69,22 @@ def test_block_cyclic_driver_world1(cuda):
     assert abs(ll / ref - 1) < 1e-8
 
 
+@pytest.mark.parametrize('mod', [0, 64, 128, 256])
 @pytest.mark.parametrize('world', [1, 2, 3])
-def test_cyclic_mirrored_gram_single_process(cuda, world):
-    """gabo_points_gram_cyclic_f64 with all `world` ranks emulated on one GPU (every 'peer' buffer is local memory):
-    same kernel and addressing as the NVLink run, launched once per rank."""
+def test_cyclic_mirrored_gram_single_process(cuda, world, mod):
+    """gabo_points_gram_cyclic_hybrid_f64 with all `world` ranks emulated on one GPU (every 'peer' buffer is local memory):
+    same kernel and addressing as the NVLink run, launched once per rank.  mod > 0: mod/256 of the cross-rank upper blocks
+    are recomputed by the row owner instead of mirrored; either way every entry is written (NaN pre-fill) with the same bits."""
     from gaboflow_b200 import ops
     from gaboflow_b200.dist import BlockCyclic
     from oracle import gabo_oracle as orc
-    n = 512 * 5
+    n = 512 * 7
     X = torch.from_numpy(orc.synth_sphere(n, 51, seed=8)).cuda()
     lays = [BlockCyclic(n, 512, world, r) for r in range(world)]
     bufs = [torch.full((l.local_rows, n), float('nan'), dtype=torch.float64, device='cuda') for l in lays]
     ptrs = [b.data_ptr() for b in bufs]
     for r in range(world):
-        ops.points_gram_cyclic(ops.SPHERE_GAUSSIAN, X, ptrs, n, world, r, beta=2.0, variance=1.0)
+        ops.points_gram_cyclic(ops.SPHERE_GAUSSIAN, X, ptrs, n, world, r, beta=2.0, variance=1.0, recompute_frac256=mod)
     torch.cuda.synchronize()
     full = ops.points_gram(ops.SPHERE_GAUSSIAN, X, None, beta=2.0, uplo='mirror')
     for r in range(world):
