@@ -189,16 +189,16 @@ def run_ours(args):
     #        rows of its panels with no exchange (X is replicated), then the leading NC x NC block is factored by the
     #        distributed right-looking Cholesky (diagonal-block broadcast + block-column all-gather over NCCL).
     from gaboflow_b200.dist import (BlockCyclic, PeerBuffers, gram_block_cyclic_mirrored, potrf_block_cyclic_,
-                                    PanelExchange, potrf_block_cyclic_p2p_,
+                                    PanelExchange, potrf_block_cyclic_p2p_, default_recompute_frac256,
                                     solve_lower_block_cyclic_, gp_loglik_block_cyclic)
     PANEL = 512
     lay = BlockCyclic(N, PANEL, world, rank)
     rows = lay.local_rows
-    # W = 2: symmetry is exploited across the two GPUs (each computes the lower tiles of its panels and stores the mirror
-    # tiles into the peer's HBM over NVLink).  W >= 4: every rank recomputes the full rows of its panels -- measured on
-    # B200, producing an entry on the FP64 pipe (~3 ps) is ~4x cheaper than moving it over NVLink (8 B at ~0.5 TB/s).
+    # W >= 2: symmetry is exploited across the GPUs: each rank computes the lower tiles of its panels; the upper tiles are
+    # either stored into the owning GPU's HBM over NVLink from inside the kernel or recomputed by their row owner -- the
+    # split (a hashed share of the cross-GPU panel pairs) balances the FP64 pipe against NVLink (dist.default_recompute_frac256).
     p2p_mirror = (world >= 2 and N % PANEL == 0 and not args.no_p2p)
-    gram_frac = int(os.environ.get('GABO_GRAM_RECOMPUTE_FRAC256', '96'))
+    gram_frac = int(os.environ.get('GABO_GRAM_RECOMPUTE_FRAC256', str(default_recompute_frac256(world))))
     peers = None
     if p2p_mirror:
         peers = PeerBuffers(rows, N, dev)

@@ -28,7 +28,7 @@ for p in lay.my_panels():
     ops.points_gram(ops.SPHERE_GAUSSIAN, Xd, None, beta=2.0, out=ref[s:s + 512], row0=p * 512, row1=(p + 1) * 512, uplo='full')
 ws = torch.empty(int(ops._lib.lib().gabo_points_gram_cyclic_workspace_bytes(N, 51)), dtype=torch.uint8, device=dev)
 ok = True
-for mod in (0, 48, 80, 112, 144, 256):   # fraction (of 256) of the cross-rank upper panel pairs recomputed by the row owner
+for mod in [int(v) for v in os.environ.get("GABO_SWEEP", "0,64,96,128,160,256").split(",")]:   # fraction (of 256) of the cross-rank upper panel pairs recomputed by the row owner
     K.fill_(float('nan'))
     dist.barrier(); torch.cuda.synchronize()
     gram_block_cyclic_mirrored(ops.SPHERE_GAUSSIAN, Xd, lay, peers, 2.0, 1.0, workspace=ws, recompute_frac256=mod)
