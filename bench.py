@@ -237,7 +237,7 @@ def run_ours(args):
             ops.points_gram(ops.SPHERE_GAUSSIAN, Xd, None, beta=BETA, variance=VARIANCE, out=K, uplo='mirror', workspace=ws)
         elif p2p_mirror:
             gram_block_cyclic_mirrored(ops.SPHERE_GAUSSIAN, Xd, lay, peers, BETA, VARIANCE, workspace=ws, sync=True,
-                                       recompute_frac256=gram_frac)
+                                       recompute_frac256=gram_frac, xch=xch)
         else:
             for pnl in lay.my_panels():
                 sl = lay.slot(pnl) * PANEL

@@ -422,7 +422,7 @@ def default_recompute_frac256(world: int) -> int:
 
 def gram_block_cyclic_mirrored(kind: int, X: torch.Tensor, layout: BlockCyclic, peers: PeerBuffers, beta: float,
                                variance: float, workspace=None, group=None, sync: bool = True,
-                               recompute_frac256: int = 0) -> torch.Tensor:
+                               recompute_frac256: int = 0, xch: Optional['PanelExchange'] = None) -> torch.Tensor:
     """Symmetric Gram K(X,X) into the block-cyclic row panels of all ranks: each rank computes the lower tiles of its own
     panels once and writes their mirror images into the owning peers' memory from inside the kernel.  With
     ``recompute_frac256 = f``, f/256 of the panel pairs owned by different ranks are recomputed by the row owner instead of
@@ -432,7 +432,18 @@ def gram_block_cyclic_mirrored(kind: int, X: torch.Tensor, layout: BlockCyclic, 
         raise ValueError('the mirrored Gram uses 512-row panels')
     ops.points_gram_cyclic(kind, X, peers.ptrs, int(peers.local.stride(0)), layout.world, layout.rank, beta, variance, workspace,
                            recompute_frac256=recompute_frac256)
-    if sync:
+    if sync and xch is not None and layout.world > 1:
+        # stream-ordered handshake instead of a host barrier: tell every peer that this rank's mirror stores are out, and
+        # make the stream wait for the same message from every peer (flags 16 + source rank of the exchange area).  The
+        # caller guarantees that no peer still READS its panels of the previous matrix (in the bench: the all-reduce and
+        # host read of the log-likelihood end every step).
+        xch.gram_epoch += 1
+        me = layout.rank
+        others = [r for r in range(layout.world) if r != me]
+        ops.flag_signal([xch.flag_ptr(r, 16 + me) for r in others], xch.gram_epoch)
+        for r in others:
+            ops.flag_wait_geq(xch.flag_ptr(me, 16 + r), xch.gram_epoch)
+    elif sync:
         torch.cuda.synchronize(X.device)
         if layout.world > 1:
             dist.barrier(group=group)      # remote mirror stores of every rank have landed
@@ -469,6 +480,7 @@ class PanelExchange:
         self.peers = PeerBuffers(1, total, device, group=group)
         self.device = torch.device(device)
         self.epoch = 0
+        self.gram_epoch = 0
         self.side = torch.cuda.Stream(device=self.device, priority=-1)
         self.peers.local[0, self.flag_off:].zero_()
         self._warm_up()
