@@ -13,6 +13,14 @@ A step is one pass of the hot path over one synthetic batch (BASELINE.json confi
 `phases_ms` / `cholesky` split it.  Inputs are synthetic (seeded), already resident in HBM for `value`; `e2e` repeats
 the steps through the public kernel-class / GPR API from pinned HOST buffers with the host<->device copies inside the
 timed region.  The working set (34 GB of K) is >> the 126 MB L2, so no explicit flush is needed between iterations.
+
+N > 1 (one rank per GPU under torchrun, strong scaling: the same matrix on more GPUs).  K lives in 512-row panels, 1-D
+block-cyclic over the ranks.  gram: lower tiles by the row owner; upper tiles either stored into the owning GPU over
+NVLink from inside the kernel or recomputed by their row owner (hashed split, dist.default_recompute_frac256); completion
+is a stream-ordered flag handshake.  potrf: right-looking over panels with one panel of look-ahead; the block column
+reaches every rank by NVLink stores from the row-solve kernel, the diagonal block by copy engines, ordering by
+cuStreamWaitValue32 flags (no collective inside the loop; GABO_DIST_P2P=0 selects the NCCL broadcast + all-gather
+version).  solve / loglik: 512-vector broadcast per panel, one all-reduce.  Times are CUDA events, max over ranks.
 """
 from __future__ import annotations
 
