@@ -106,6 +106,66 @@ struct SpdGramParams {
     double beta, variance;
 };
 
+// M = W S W^T for one pair: W lower (packed triangle wrow: entry (a,k), k <= a, at a(a+1)/2 + k), S symmetric (upper storage).
+template <int D>
+__device__ __forceinline__ void ai_congruence(const double* __restrict__ wrow, const double (&B)[D][D], double (&Mx)[D][D]) {
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        double T[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k <= a; ++k) v = fma(wrow[a * (a + 1) / 2 + k], GABO_SYM(B, k, c), v);
+            T[c] = v;
+        }
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k <= b; ++k) v = fma(T[k], wrow[b * (b + 1) / 2 + k], v);
+            Mx[b][a] = v;   // upper storage
+        }
+    }
+}
+
+// Out-of-line slow path of the affine-invariant pair (kept out of the hot loop: ~3 k instructions that would otherwise sit
+// between the fast path's blocks in the instruction cache and inflate its register allocation).  Taken when the
+// mixed-precision eigenvalues do not validate (near-multiple eigenvalues) or the spectrum is wide: all-FP64 QL on the
+// tridiagonal, then cyclic Jacobi (relative accuracy) if lambda_min <= 0.02 lambda_max.  S2 travels by value (packed upper
+// triangle) so that the caller's copy can stay in registers.  Returns sum_k log^2 lambda_k.
+template <int D>
+struct SymPacked { double v[D * (D + 1) / 2]; };
+
+template <int D>
+__device__ __noinline__ double ai_sumlog2_slow(const double* __restrict__ wrow, const SymPacked<D> Sp) {
+    double B[D][D];
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = r; c < D; ++c) B[r][c] = Sp.v[r * D - r * (r - 1) / 2 + (c - r)];
+    double Mx[D][D], ev[D];
+    ai_congruence<D>(wrow, B, Mx);
+    tridiag_ql_eigvals<D>(Mx, ev);
+    double emin = ev[0], emax = ev[0];
+#pragma unroll
+    for (int k = 1; k < D; ++k) { emin = fmin(emin, ev[k]); emax = fmax(emax, ev[k]); }
+    if (!(emin > 0.02 * emax)) {
+        ai_congruence<D>(wrow, B, Mx);
+        double dummy[1][1];
+        jacobi_eig<D, false>(Mx, dummy);
+#pragma unroll
+        for (int k = 0; k < D; ++k) ev[k] = Mx[k][k];
+    }
+    double s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const double lg = log(ev[k]);
+        s2 = fma(lg, lg, s2);
+    }
+    return s2;
+}
+
 template <int D, int KIND>
 __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_gram_kernel(const SpdGramParams p) {
     constexpr int DD = D * D;
@@ -188,57 +248,30 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_gram_kernel(const Sp
                 if (p.symmetric && gi == j) {
                     val = p.variance;   // d_AI(X,X) = 0 exactly
                 } else {
-                    // M = W_i S_j W_i^T  (W lower): T = W S row by row, then M[a][b] = sum_k T[a][k] W[b][k]
-                    double Mx[D][D];
-                    auto congruence = [&]() {
-#pragma unroll
-                        for (int a = 0; a < D; ++a) {
-                            double T[D];
-#pragma unroll
-                            for (int c = 0; c < D; ++c) {
-                                double v = 0.0;
-#pragma unroll
-                                for (int k = 0; k <= a; ++k) v = fma(sR[r][a * (a + 1) / 2 + k], GABO_SYM(B, k, c), v);
-                                T[c] = v;
-                            }
-#pragma unroll
-                            for (int b = 0; b <= a; ++b) {
-                                double v = 0.0;
-#pragma unroll
-                                for (int k = 0; k <= b; ++k) v = fma(T[k], sR[r][b * (b + 1) / 2 + k], v);
-                                Mx[b][a] = v;   // upper storage
-                            }
-                        }
-                    };
-                    congruence();
-                    // eigenvalues: Householder (FP64), then FP32 QL + FP64 Newton refinement; the all-FP64 QL when that
-                    // does not validate (near-multiple eigenvalues); cyclic Jacobi when the spectrum is wide enough that the
-                    // absolute accuracy of the tridiagonal route would eat into the 1e-12 relative budget of log(lambda)
-                    double ev[D];
-                    {
-                        double td[D], te[D];
-                        householder_tridiag<D>(Mx, td, te);
-                        if (!tridiag_eigvals_mixed<D>(td, te, ev)) {
-                            ql_tri_eigvals<D, double>(td, te);
-#pragma unroll
-                            for (int k = 0; k < D; ++k) ev[k] = td[k];
-                        }
-                    }
+                    // M = W_i S_j W_i^T, Householder (FP64), then FP32 QL + FP64 Newton refinement of the eigenvalues; the
+                    // out-of-line slow path when that does not validate or the spectrum is wide (ai_sumlog2_slow)
+                    double Mx[D][D], ev[D], td[D], te[D];
+                    ai_congruence<D>(sR[r], B, Mx);
+                    householder_tridiag<D>(Mx, td, te);
+                    bool fast = tridiag_eigvals_mixed<D>(td, te, ev);
                     double emin = ev[0], emax = ev[0];
 #pragma unroll
                     for (int k = 1; k < D; ++k) { emin = fmin(emin, ev[k]); emax = fmax(emax, ev[k]); }
-                    if (!(emin > 0.02 * emax)) {
-                        congruence();
-                        double dummy[1][1];
-                        jacobi_eig<D, false>(Mx, dummy);
-#pragma unroll
-                        for (int k = 0; k < D; ++k) ev[k] = Mx[k][k];
-                    }
+                    fast = fast && (emin > 0.02 * emax);
                     double s2 = 0.0;
+                    if (fast) {
 #pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        const double lg = log(ev[k]);   // SPD_utils_tf.py:136-139
-                        s2 = fma(lg, lg, s2);
+                        for (int k = 0; k < D; ++k) {
+                            const double lg = log(ev[k]);   // SPD_utils_tf.py:136-139
+                            s2 = fma(lg, lg, s2);
+                        }
+                    } else {
+                        SymPacked<D> Sp;
+#pragma unroll
+                        for (int rr = 0; rr < D; ++rr)
+#pragma unroll
+                            for (int cc = rr; cc < D; ++cc) Sp.v[rr * D - rr * (rr - 1) / 2 + (cc - rr)] = B[rr][cc];
+                        s2 = ai_sumlog2_slow<D>(sR[r], Sp);
                     }
                     if (KIND == GABO_SPD_AI_GAUSSIAN) val = p.variance * exp(-p.beta * s2);          // kernels_spd_tf.py:241-248
                     else val = p.variance * exp(-p.beta * sqrt(s2));                                 // kernels_spd_tf.py:396-400
