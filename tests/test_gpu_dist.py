@@ -172,3 +172,25 @@ def test_p2p_driver_world1_matches_collective_driver(cuda):
             assert sorted(store) == [0, 1, 2, 3]
     finally:
         xch.close()
+
+
+def test_p2p_driver_ragged_last_panel(cuda):
+    """Peer-memory driver on a size that is not a multiple of the panel (last panel 252 rows), whole matrix factored."""
+    from gaboflow_b200 import SphereGaussianKernel
+    from gaboflow_b200.dist import BlockCyclic, gram_block_cyclic, potrf_block_cyclic_, potrf_block_cyclic_p2p_, PanelExchange
+    from oracle import gabo_oracle as orc
+    n = 4 * 512 + 252
+    Xd = torch.from_numpy(orc.synth_sphere(n, 51, seed=14)).cuda()
+    k = SphereGaussianKernel(51, range(51), beta_min=0.0, beta=2.0)
+    lay = BlockCyclic(n, 512, 1, 0)
+    A = gram_block_cyclic(lambda r0, r1, out: k.K(Xd, uplo='lower', row0=r0, row1=r1, out=out), lay, device='cuda')
+    B = A.clone()
+    assert potrf_block_cyclic_(A, lay, 1e-2) == 0
+    xch = PanelExchange(lay, n, 'cuda')
+    try:
+        assert potrf_block_cyclic_p2p_(B, lay, 1e-2, xch) == 0
+        assert torch.equal(torch.tril(B), torch.tril(A))
+        ref = np.linalg.cholesky(orc.sphere_gaussian_K(Xd.cpu().numpy(), beta=2.0) + 1e-2 * np.eye(n))
+        assert float(np.max(np.abs(torch.tril(B).cpu().numpy() - ref))) < 1e-12
+    finally:
+        xch.close()
