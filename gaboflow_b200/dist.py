@@ -416,8 +416,8 @@ class PeerBuffers:
 def default_recompute_frac256(world: int) -> int:
     """Share (of 256) of the cross-GPU upper panel pairs that the hybrid Gram recomputes instead of mirroring; measured on
     B200 / NVSwitch at N = 65536, D = 51 (tools/dist_gram_check.py): 2 GPUs 80 (8.4 ms; mirror-all 11.1, recompute-all 10.1),
-    8 GPUs 160 (2.7 ms; 4.2 / 3.07); in between interpolated."""
-    return {1: 0, 2: 80, 3: 104, 4: 128, 5: 144, 6: 144}.get(int(world), 160)
+    4 GPUs 144-160 (5.0 ms; 112: 5.8, 128: 5.35), 8 GPUs 160 (2.7 ms; mirror-all 4.2, recompute-all 3.07, 192: 2.8)."""
+    return {1: 0, 2: 80, 3: 128}.get(int(world), 152 if int(world) == 4 else 160)
 
 
 def gram_block_cyclic_mirrored(kind: int, X: torch.Tensor, layout: BlockCyclic, peers: PeerBuffers, beta: float,
