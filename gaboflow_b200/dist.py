@@ -4,12 +4,19 @@ CPU tests of the host logic), the C-ABI kernels for all local arithmetic.
 Layout: the Gram matrix is distributed by ROW PANELS of nb rows, 1-D block-cyclic: global panel p
 lives on rank p % world in local slot p // world, each rank storing full rows [local_rows, n] (row-major, so a "column
 panel" of the symmetric matrix is a row panel here).
-  * Gram generation needs no exchange: X is replicated (<= 27 MB) and every rank produces its own row panels.
-  * Cholesky is right-looking over panels: the owner factors the nb x nb diagonal block (gabo_potrf_f64) and broadcasts
-    it; every rank solves its rows of the block column (gabo_trsm_right_f64); the block column is all-gathered so that
-    each rank can update the lower part of its own rows (gabo_syrk_cyclic_f64, mask in global coordinates).
-  * Forward substitution is pipelined over panels with an nb-vector broadcast per step; log-likelihood terms are
-    summed with one all-reduce.
+  * Gram (gram_block_cyclic_mirrored): X is replicated (<= 27 MB); every rank computes the lower tiles of its own panels;
+    an upper block is either stored into its owner's HBM over NVLink from inside the kernel or recomputed by that owner
+    (hashed split, default_recompute_frac256); completion is a stream-ordered flag handshake.  gram_block_cyclic is the
+    exchange-free variant (every rank produces whole rows).
+  * Cholesky, right-looking over panels, two drivers with identical arithmetic (bit-identical factors):
+      potrf_block_cyclic_p2p_  peer-memory exchange (PanelExchange) + one panel of look-ahead: the diagonal block is pushed
+                               by copy engines, the block column lands on every rank by NVLink stores from the row-solve
+                               kernel, ordering by cuStreamWaitValue32 flags -- no collective inside the loop;
+      potrf_block_cyclic_      owner factors the diagonal block and broadcasts it, every rank solves its rows, the block
+                               column is all-gathered (NCCL / gloo); the version the CPU tests exercise.
+    Every rank then updates the lower part of its own rows (gabo_syrk_cyclic_f64, mask in global coordinates).
+  * Forward substitution is pipelined over panels with an nb-vector broadcast per step and reuses the block inverses the
+    factorisation produced; log-likelihood terms are summed with one all-reduce.
 """
 from __future__ import annotations
 
