@@ -1,7 +1,8 @@
 """Expected Improvement on the B200 posterior: the slice of GPflowOpt's ``ExpectedImprovement`` [third party] that the
 reference's optimisers consume (``examples/bo_sphere/benchmark_examples/bo_sphere_ackley_manifold.py:145``;
 ``BoManifolds/BO_utils/manifold_optimization.py:250-271,427`` call ``acquisition.evaluate`` on candidate points).
-Gradients with respect to the candidates are not available yet."""
+``evaluate_with_gradients`` (what ``manifold_optimization.py:260-271`` asks GPflowOpt for) is available for the sphere
+kernels: the Euclidean gradient, which the manifold optimiser projects onto the tangent space."""
 from __future__ import annotations
 
 import torch
@@ -29,3 +30,9 @@ class ExpectedImprovement:
     def evaluate(self, Xcand):
         """NumPy in, NumPy out: EI at the candidate points, shape [M, 1]."""
         return self.build_acquisition(Xcand).cpu().numpy()
+
+    def evaluate_with_gradients(self, Xcand):
+        """(EI [M, 1], dEI/dx [M, D]) as NumPy arrays (GPflowOpt ``Acquisition.evaluate_with_gradients``); sphere kernels."""
+        mean, var, _, _, dei = self.model.build_predict_with_gradients(to_device(Xcand), fmin=self.fmin)
+        ei = ops.expected_improvement(mean, var, self.fmin)
+        return ei.cpu().numpy(), dei.cpu().numpy()

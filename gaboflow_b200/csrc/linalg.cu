@@ -1238,6 +1238,112 @@ __global__ void ei_kernel(int64_t M, const double* __restrict__ mean, const doub
 }  // namespace
 }  // namespace gabo
 
+// ---- gradients of the posterior and of EI with respect to a candidate point on the sphere ------
+// For the sphere kernels k_i(x*) = variance exp(-beta d_i^p), d_i = acos(x* . x_i) (p = 2 Gaussian, 1 Laplace):
+//   dk_i/dx* = c_i x_i,  c_i = k_i beta p d_i^(p-1) / sin d_i   (Gaussian: -> 2 beta k_i as d -> 0),
+// so  d mean/dx* = sum_i alpha_i c_i x_i  and  d var/dx* = -2 sum_i (Ky^-1 k)_i c_i x_i  are weighted sums of the training
+// points.  d_i is recovered from the cross-Gram entry itself (beta d^p = -log(k/variance)), so the kernel reads only what
+// the prediction already produced.  One CTA per candidate: 256 coefficients at a time into shared memory, then 4 x 64
+// threads (point group x coordinate) accumulate; fixed summation order.  The Euclidean gradient of the acquisition follows
+// from dEI/dmu = -Phi(z), dEI/dsd = phi(z) (the reference consumes it at manifold_optimization.py:260-271).
+namespace gabo {
+namespace {
+__global__ void __launch_bounds__(256) sphere_post_grad_kernel(int kind, int64_t n, int dim, const double* __restrict__ X,
+                                                               int64_t ldx, const double* __restrict__ Kx, int64_t ldk,
+                                                               const double* __restrict__ alpha,
+                                                               const double* __restrict__ Bm, int64_t ldb, double beta,
+                                                               double variance, const double* __restrict__ mean,
+                                                               const double* __restrict__ var, double fmin,
+                                                               double* __restrict__ gmean, double* __restrict__ gvar,
+                                                               double* __restrict__ dei) {
+    __shared__ double c1[256], c2[256];
+    __shared__ double red[4][64][2];
+    const int64_t m = blockIdx.x;
+    const int j = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const double inv_var = 1.0 / variance;
+    double a1 = 0.0, a2 = 0.0;
+    for (int64_t i0 = 0; i0 < n; i0 += 256) {
+        const int64_t i = i0 + threadIdx.x;
+        double w1 = 0.0, w2 = 0.0;
+        if (i < n) {
+            const double k = Kx[i * ldk + m];
+            const double r = k * inv_var;
+            double coef = 0.0;
+            if (r > 0.0) {
+                const double bd = fmax(-log(r), 0.0);               // beta d^p
+                if (kind == GABO_SPHERE_GAUSSIAN) {
+                    const double d = sqrt(bd / beta);
+                    coef = 2.0 * beta * k * ((d > 1e-8) ? d / fmax(sin(d), 1e-12) : 1.0);
+                } else {
+                    const double d = bd / beta;
+                    coef = beta * k / fmax(sin(d), 1e-12);              // not differentiable at d = 0 (as the kernel itself)
+                }
+            }
+            w1 = alpha[i] * coef;
+            w2 = Bm[i * ldb + m] * coef;
+        }
+        c1[threadIdx.x] = w1;
+        c2[threadIdx.x] = w2;
+        __syncthreads();
+        if (j < dim) {
+            const int lim = (int)((n - i0) < 256 ? (n - i0) : 256);
+            for (int ii = grp; ii < lim; ii += 4) {
+                const double x = X[(i0 + ii) * ldx + j];
+                a1 = fma(c1[ii], x, a1);
+                a2 = fma(c2[ii], x, a2);
+            }
+        }
+        __syncthreads();
+    }
+    red[grp][j][0] = a1;
+    red[grp][j][1] = a2;
+    __syncthreads();
+    if (grp == 0 && j < dim) {
+        const double g1 = (red[0][j][0] + red[1][j][0]) + (red[2][j][0] + red[3][j][0]);
+        const double g2 = -2.0 * ((red[0][j][1] + red[1][j][1]) + (red[2][j][1] + red[3][j][1]));
+        gmean[m * dim + j] = g1;
+        gvar[m * dim + j] = g2;
+        if (dei != nullptr) {
+            const double v = var[m];
+            const double sd = sqrt(fmax(v, 1e-6));
+            const double z = (fmin - mean[m]) / sd;
+            const double cdf = 0.5 * erfc(-z * 0.70710678118654752440);
+            const double phi = exp(-0.5 * z * z) * 0.39894228040143267794;
+            dei[m * dim + j] = -cdf * g1 + ((v > 1e-6) ? phi / (2.0 * sd) * g2 : 0.0);   // the variance floor has zero slope
+        }
+    }
+}
+}  // namespace
+}  // namespace gabo
+
+extern "C" int gabo_sphere_posterior_grad_f64(int kind, int64_t n, int64_t M, int dim, const double* X, int64_t ldx,
+                                              const double* Kx, int64_t ldk, const double* alpha, const double* Bm,
+                                              int64_t ldb, double beta, double variance, const double* mean,
+                                              const double* var, double fmin, double* gmean, double* gvar, double* dei,
+                                              gabo_stream_t stream) {
+    if (kind != GABO_SPHERE_GAUSSIAN && kind != GABO_SPHERE_LAPLACE) return -1;
+    if (n < 0) return -2;
+    if (M < 0) return -3;
+    if (dim < 1 || dim > 64) return -4;
+    if (M == 0) return 0;
+    if (n > 0 && X == nullptr) return -5;
+    if (ldx < dim) return -6;
+    if (n > 0 && Kx == nullptr) return -7;
+    if (ldk < M) return -8;
+    if (n > 0 && alpha == nullptr) return -9;
+    if (n > 0 && Bm == nullptr) return -10;
+    if (ldb < M) return -11;
+    if (!(beta > 0.0)) return -12;
+    if (!(variance > 0.0)) return -13;
+    if (dei != nullptr && (mean == nullptr || var == nullptr)) return -14;
+    if (gmean == nullptr) return -17;
+    if (gvar == nullptr) return -18;
+    gabo::sphere_post_grad_kernel<<<(unsigned)M, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        kind, n, dim, X, ldx, Kx, ldk, alpha, Bm, ldb, beta, variance, mean, var, fmin, gmean, gvar, dei);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int gabo_expected_improvement_f64(int64_t M, const double* mean, const double* var, double fmin, double* out,
                                              gabo_stream_t stream) {
     if (M < 0) return -1;

@@ -179,6 +179,29 @@ class GPR(Parameterized):
             grads['kern.' + bname] = float(ops.gp_grad_beta(Kf, neg_kinv, alpha, v, self.kern.beta_effective()).item())
         return grads
 
+    def build_predict_with_gradients(self, Xnew, fmin=None):
+        """Posterior mean / variance at the candidates AND their Euclidean gradients w.r.t. the candidates, for the sphere
+        kernels (the reference differentiates through TensorFlow and hands the result to the manifold
+        optimiser, ``BO_utils/manifold_optimization.py:260-271``).  Returns (mean [M,1], var [M], dmean [M,D], dvar [M,D],
+        dEI [M,D] or None); with ``fmin`` the EI gradient is formed in the same kernel.  One output column only."""
+        kind = getattr(self.kern, '_kind', None)
+        if kind not in (ops.SPHERE_GAUSSIAN, ops.SPHERE_LAPLACE):
+            raise NotImplementedError('candidate gradients are implemented for the sphere kernels')
+        L, V = self._factorise()
+        if int(V.shape[1]) != 1:
+            raise NotImplementedError('candidate gradients need a single output column')
+        Xn = to_device(Xnew)
+        Kx = self.kern.K(self.X, Xn)                       # [N, M]
+        A = Kx.clone()
+        ops.trsm_(L, A, trans=False)                       # L^-1 Kx
+        mean, var = ops.gp_predict(A, V, self.kern.Kdiag(Xn), self._mean_const())
+        ops.trsm_(L, A, trans=True)                        # Ky^-1 Kx
+        alpha = V.clone()
+        ops.trsm_(L, alpha, trans=True)
+        dmean, dvar, dei = ops.sphere_posterior_grad(kind, self.X, Kx, alpha, A, self.kern.beta_effective(),
+                                                     float(self.kern.variance), mean, var, fmin)
+        return mean, var, dmean, dvar, dei
+
     # ---- AutoFlow-style NumPy API ---------------------------------------------------------------------
     def compute_log_likelihood(self) -> float:
         return float(self.build_likelihood().item())

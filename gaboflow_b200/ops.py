@@ -413,6 +413,37 @@ def points_gram_cyclic(kind: int, X: torch.Tensor, bases, ldk: int, world: int, 
     _lib.check('gabo_points_gram_cyclic_hybrid_f64', st)
 
 
+def sphere_posterior_grad(kind: int, X: torch.Tensor, Kx: torch.Tensor, alpha: torch.Tensor, Bm: torch.Tensor, beta: float,
+                          variance: float, mean: Optional[torch.Tensor] = None, var: Optional[torch.Tensor] = None,
+                          fmin: Optional[float] = None):
+    """Euclidean gradients w.r.t. M candidate points on the sphere (gabo_sphere_posterior_grad_f64): returns
+    (d mean/dx* [M,D], d var/dx* [M,D], d EI/dx* [M,D] or None).  Kx = K(X, X*) [N,M], alpha = Ky^-1 (y-m) [N],
+    Bm = Ky^-1 Kx [N,M]; the EI gradient needs the posterior mean / var [M] and fmin."""
+    X = _rowmajor2d(_req(X, 'X'))
+    _req(Kx, 'Kx'); _req(alpha, 'alpha'); _req(Bm, 'Bm')
+    n, dim = int(X.shape[0]), int(X.shape[1])
+    M = int(Kx.shape[1])
+    al = alpha.reshape(-1).contiguous()
+    if al.numel() != n or Kx.shape[0] != n or tuple(Bm.shape) != (n, M):
+        raise ValueError('shape mismatch in sphere_posterior_grad')
+    gmean = torch.empty((M, dim), dtype=torch.float64, device=X.device)
+    gvar = torch.empty((M, dim), dtype=torch.float64, device=X.device)
+    dei = None
+    mptr = vptr = dptr = None
+    if fmin is not None:
+        mean_c = _req(mean, 'mean').reshape(-1).contiguous()
+        var_c = _req(var, 'var').reshape(-1).contiguous()
+        dei = torch.empty((M, dim), dtype=torch.float64, device=X.device)
+        mptr, vptr, dptr = mean_c.data_ptr(), var_c.data_ptr(), dei.data_ptr()
+    ld = lambda t: max(int(t.stride(0)), int(t.shape[1])) if t.shape[0] > 1 else int(t.shape[1])
+    st = _lib.lib().gabo_sphere_posterior_grad_f64(int(kind), n, M, dim, X.data_ptr(), _ld(X), Kx.data_ptr(), ld(Kx),
+                                                   al.data_ptr(), Bm.data_ptr(), ld(Bm), float(beta), float(variance),
+                                                   mptr, vptr, float(fmin) if fmin is not None else 0.0,
+                                                   gmean.data_ptr(), gvar.data_ptr(), dptr, _stream())
+    _lib.check('gabo_sphere_posterior_grad_f64', st)
+    return gmean, gvar, dei
+
+
 def expected_improvement(mean: torch.Tensor, var: torch.Tensor, fmin: float) -> torch.Tensor:
     """EI over the candidates (gabo_expected_improvement_f64); mean / var are [M] or [M,1] device tensors."""
     _req(mean, 'mean'); _req(var, 'var')

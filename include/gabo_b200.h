@@ -164,6 +164,15 @@ int gabo_gemm_nt_sub_f64(int64_t m, int64_t n, int64_t k, const double* A, int64
                          const double* B, int64_t ldb, double* C, int64_t ldc, int lower,
                          gabo_stream_t stream);
 
+/* gabo_sphere_posterior_grad_f64: Euclidean gradients of the posterior mean / variance and of Expected Improvement with
+ *   respect to each of M candidate points on the sphere (what GPflowOpt's evaluate_with_gradients hands to
+ *   BO_utils/manifold_optimization.py:260-271).  Kx [n, M] = K(X, X*) (noise-free cross-Gram), alpha [n] = Ky^-1 (y - m),
+ *   Bm [n, M] = Ky^-1 Kx, mean / var [M] the posterior at the candidates.  gmean, gvar, dei: [M, dim]; dei may be NULL
+ *   (then mean / var / fmin are ignored).  dim <= 64.  kind: GABO_SPHERE_GAUSSIAN or GABO_SPHERE_LAPLACE. */
+int gabo_sphere_posterior_grad_f64(int kind, int64_t n, int64_t M, int dim, const double* X, int64_t ldx,
+                                   const double* Kx, int64_t ldk, const double* alpha, const double* Bm, int64_t ldb,
+                                   double beta, double variance, const double* mean, const double* var, double fmin,
+                                   double* gmean, double* gvar, double* dei, gabo_stream_t stream);
 /* Expected Improvement over M candidates from the posterior mean / variance (GPflowOpt ExpectedImprovement
  * [third party]; consumed by the reference at BO_utils/manifold_optimization.py:250-271,427):
  *   out = (fmin - mean) Phi(z) + var N(fmin; mean, sqrt(var)), var floored at 1e-6, z = (fmin - mean)/sqrt(var). */

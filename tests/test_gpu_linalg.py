@@ -296,3 +296,46 @@ def test_gpr_append_matches_refactorisation(cuda):
         m2.likelihood.variance = 1e-300
         m2.compute_log_likelihood()
         m2.append(X[3], y[3])
+
+
+@pytest.mark.parametrize('laplace', [False, True])
+def test_candidate_gradients_vs_oracle_finite_differences(cuda, laplace):
+    """gabo_sphere_posterior_grad_f64 (d mean/dx*, d var/dx*, d EI/dx*) against central finite differences of the ORACLE's
+    posterior and EI in the ambient coordinates (the Euclidean gradient the manifold optimiser projects)."""
+    from gaboflow_b200 import GPR, SphereGaussianKernel, SphereLaplaceKernel, ExpectedImprovement
+    n, D, M = 220, 4, 6
+    X = orc.synth_sphere(n, D, seed=51)
+    y = np.sin(3.0 * X[:, :1]) + 0.1 * np.random.default_rng(52).standard_normal((n, 1))
+    Xs = orc.synth_sphere(M, D, seed=53)
+    beta, v, s2 = 1.8, 1.3, 0.05
+    if laplace:
+        k = SphereLaplaceKernel(D, range(D), beta=beta, variance=v)
+        Kfun = lambda A, B=None: orc.sphere_laplace_K(A, B, beta=beta, variance=v)
+    else:
+        k = SphereGaussianKernel(D, range(D), beta_min=0.5, beta=beta - 0.5, variance=v)
+        Kfun = lambda A, B=None: orc.sphere_gaussian_K(A, B, beta=beta, variance=v)
+    m = GPR(X, y, kern=k)
+    m.likelihood.variance = s2
+    acq = ExpectedImprovement(m)
+    fmin = acq.fmin
+    mean, var, dmean, dvar, dei = m.build_predict_with_gradients(Xs, fmin=fmin)
+    ei, dei2 = acq.evaluate_with_gradients(Xs)
+    assert np.array_equal(dei.cpu().numpy(), dei2)
+    Kor = Kfun(X)
+    np.fill_diagonal(Kor, v)          # K(X) has a diagonal of exactly `variance` here; the reference's carries acos noise (DESIGN.md 2-1)
+
+    def post(x):
+        mu, vv = orc.gp_predict(Kor, Kfun(X, x[None, :]), np.full(1, v), y, s2)
+        mu, vv = float(np.ravel(mu)[0]), float(np.ravel(vv)[0])
+        return mu, vv, float(np.ravel(orc.expected_improvement(np.array([mu]), np.array([vv]), fmin))[0])
+
+    h = 1e-6
+    for c in range(M):
+        mu0, v0, e0 = post(Xs[c])
+        assert abs(float(mean[c, 0]) - mu0) < 1e-8 and abs(float(var[c]) - v0) < 1e-8 and abs(float(ei[c, 0]) - e0) < 1e-8
+        for j in range(D):
+            e = np.zeros(D); e[j] = h
+            (mp, vp, ep), (mm, vm, em) = post(Xs[c] + e), post(Xs[c] - e)
+            for got, ref in ((float(dmean[c, j]), (mp - mm) / (2 * h)), (float(dvar[c, j]), (vp - vm) / (2 * h)),
+                             (float(dei[c, j]), (ep - em) / (2 * h))):
+                assert abs(got - ref) < 2e-5 * max(1.0, abs(ref)), (laplace, c, j, got, ref)
