@@ -284,7 +284,8 @@ def run_ours(args):
             return ll_val_host[0]
         return None
 
-    for _ in range(args.warmup):
+    warm = max(args.warmup, 3)             # the timing rules ask for at least 3 untimed steps; the line reports what ran
+    for _ in range(warm):
         step()
     if world > 1 and os.environ.get('GABO_DIST_PHASES', '0') == '1':    # diagnostic: one untimed step with per-piece events
         dist_phases[0] = {}
@@ -325,7 +326,7 @@ def run_ours(args):
     ll_val = float(ll_dev.item()) if world == 1 else ll_val_host[0]
 
     # ---- end to end from pinned host buffers through the public API ----
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(3):
         step(from_host=True)
     barrier()
     e_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
@@ -374,7 +375,7 @@ def run_ours(args):
     gram_flops = entries * (2 * DIM + F_TR) * (0.5 if sym else 1.0)    # symmetric tiles are computed once and mirrored
     line = {
         'metric': 'sphere_gram_entries_per_s', 'value': value, 'unit': 'entries/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+        'warmup': warm, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'sphere Gaussian Gram N={N} on S^50 (D={DIM}) + FP64 Cholesky of K+1e-2 I at N={NC} + solve + loglik',
                    'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2, 'seeds': [SEED_X, SEED_Y],
