@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, 'libgabo_b200.so')
+LIB_PATH = os.environ.get('GABO_LIB_PATH') or os.path.join(_PKG_DIR, 'libgabo_b200.so')   # the override is for A/B builds (tools/)
 
 i32, i64, f64, f32, vp, sz = C.c_int, C.c_int64, C.c_double, C.c_float, C.c_void_p, C.c_size_t
 
@@ -35,6 +35,7 @@ SIGNATURES = {
     'gabo_gp_predict_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, f64, vp, vp, vp]),
     'gabo_sphere_posterior_grad_f64': (i32, [i32, i64, i64, i32, vp, i64, vp, i64, vp, vp, i64, f64, f64, vp, vp, f64, vp, vp, vp, vp]),
     'gabo_expected_improvement_f64': (i32, [i64, vp, vp, f64, vp, vp]),
+    'gabo_math_probe_f64': (i32, [i32, vp, i64, f64, vp, vp]),
     'gabo_profile_trailing_updates': (i32, [i32]),
     'gabo_profile_trailing_read': (i32, [C.POINTER(i64), C.POINTER(f64), C.POINTER(f64), C.POINTER(f64), C.POINTER(f64)]),
     'gabo_gemm_nt_sub_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, i32, vp]),

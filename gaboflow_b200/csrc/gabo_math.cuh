@@ -119,12 +119,24 @@ __device__ __forceinline__ void acos_clamped_fast_n(const double (&t)[N], double
     }
 }
 
+// out-of-line libm fallback of the batched exp (N inlined copies of exp() would sit in the middle of the hot loops' code)
+// scale * e^x as (scale * e^(x/2)) * e^(x/2): e^(x/2) is still a normal number where e^x is subnormal, so a result in the
+// subnormal range is rounded once, from full-precision factors (scale * exp(x) would multiply an already truncated subnormal).
+static __device__ __noinline__ double exp_scaled_slow(double x, double scale) {
+    const double r = exp(0.5 * x);
+    return (scale * r) * r;
+}
+
 // exp(x) * scale for x <= 0; `tab` = shared-memory table 2^(j/32) ALREADY multiplied by `scale`.
+// The power of two 2^m is applied by an integer add on the exponent field of v = tab[j] * poly, which is only valid
+// while the result stays a NORMAL number: lanes whose biased exponent would reach 0 (scale * e^x below DBL_MIN -- with a
+// small `scale` that happens for |x| well under 700), as well as |x| >= 700 / NaN / inf, take the libm slow path.
 template <int N>
 __device__ __forceinline__ void exp_neg_scaled_fast_n(const double (&x)[N], double (&out)[N], const double* __restrict__ tab,
                                                       double scale) {
     double r[N], p[N];
     int n[N];
+    bool slow[N];
     bool anyslow = false;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -133,7 +145,7 @@ __device__ __forceinline__ void exp_neg_scaled_fast_n(const double (&x)[N], doub
         const double nf = tn - kExpC[0];
         r[i] = fma(nf, kExpC[3], fma(nf, kExpC[2], x[i]));
         p[i] = kExpC[4];
-        anyslow = anyslow || (hi_abs(x[i]) >= 0x4085e000);      // |x| >= 700 (or NaN / inf)
+        slow[i] = (hi_abs(x[i]) >= 0x4085e000);      // |x| >= 700 (or NaN / inf)
     }
 #pragma unroll
     for (int c = 5; c <= 9; ++c)
@@ -143,12 +155,15 @@ __device__ __forceinline__ void exp_neg_scaled_fast_n(const double (&x)[N], doub
     for (int i = 0; i < N; ++i) {
         p[i] = fma(p[i], r[i], kExpC[9]);
         const double v = tab[n[i] & 31] * p[i];
-        out[i] = __hiloint2double(__double2hiint(v) + ((n[i] >> 5) << 20), __double2loint(v));
+        const int hv = __double2hiint(v), m = n[i] >> 5;
+        out[i] = __hiloint2double(hv + (m << 20), __double2loint(v));
+        slow[i] = slow[i] || ((hv >> 20) + m <= 0);  // result would be subnormal / underflow: the exponent add wraps
+        anyslow = anyslow || slow[i];
     }
     if (__any_sync(0xffffffffu, anyslow)) {
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            if (hi_abs(x[i]) >= 0x4085e000) out[i] = scale * exp(x[i]);
+            if (slow[i]) out[i] = exp_scaled_slow(x[i], scale);
     }
 }
 
@@ -158,6 +173,36 @@ __device__ __forceinline__ void acos_fast_n(const double (&t)[N], double (&out)[
 template <int N>
 __device__ __forceinline__ void exp_neg_fast_n(const double (&x)[N], double (&out)[N], const double* __restrict__ tab) {
     exp_neg_scaled_fast_n<N>(x, out, tab, 1.0);
+}
+
+// ---- lean natural logarithm for POSITIVE, NORMAL, finite x (the eigenvalues of an SPD congruence) ------------------------
+//   x = 2^k m, m in [sqrt(1/2), sqrt(2));  s = (m-1)/(m+1);  log m = 2 atanh(s) = 2s + s z P(z), z = s^2 <= 0.0295,
+//   P = the series 2/3 + 2/5 z + ... + 2/19 z^8 (next term < 1e-17);  the quotient is a hardware reciprocal seed, two
+//   Newton steps and one residual correction.  ~30 instructions, no branches, constants as c[bank] operands; CUDA's log()
+//   costs ~50 plus two UMOV per literal coefficient.  Error < 2e-16 relative (tests: test_fast_math_accuracy).
+static __constant__ double kLogC[11] = {
+    2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0, 2.0 / 9.0, 2.0 / 11.0, 2.0 / 13.0, 2.0 / 15.0, 2.0 / 17.0, 2.0 / 19.0,
+    0x1.62e42fefa3800p-1,      // [9]  ln2 hi (41 bits: k * hi is exact for |k| < 2^11)
+    0x1.ef35793c76730p-45};    // [10] ln2 lo
+
+__device__ __forceinline__ double log_pos_normal(double x) {
+    const int t = __double2hiint(x) + 0x00095f62;                       // 0x3ff00000 - 0x3fe6a09e
+    const int k = (t >> 20) - 1023;
+    const double m = __hiloint2double((t & 0x000fffff) + 0x3fe6a09e, __double2loint(x));
+    const double f = m - 1.0, den = m + 1.0;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    r = fma(fma(-den, r, 1.0), r, r);
+    r = fma(fma(-den, r, 1.0), r, r);
+    double s = f * r;
+    s = fma(fma(-s, den, f), r, s);
+    const double z = s * s;
+    double p = kLogC[8];
+#pragma unroll
+    for (int i = 7; i >= 0; --i) p = fma(p, z, kLogC[i]);
+    const double kd = (double)k;
+    const double tail = fma(kd, kLogC[10], (s * z) * p);
+    return fma(kd, kLogC[9], s + s) + tail;
 }
 
 }  // namespace gabo

@@ -7,12 +7,16 @@
 //           SpdLogEuclideanGaussianKernel.K (kernels_spd_tf.py:634) which becomes a per-point Mandel(logm).
 //
 // Data layout in HBM: S, W as [n, d*d] row-major doubles (W lower triangular, zeros above), logdet [n],
-// logm as Mandel [n, m].  Pair kernel: a CTA owns a 32-row x 128-column block of K; thread = one column j with
+// logm as Mandel [n, m].  Pair kernels: a CTA owns a 32-row x 128-column block of K; thread = one column j with
 // S_j held in registers, looping over the 32 rows whose operand (W_i or S_i) sits in shared memory and is read as a
-// warp broadcast; the d x d congruence, the cyclic Jacobi eigen-solve and the log/exp run entirely in registers.
-// Row stores are 256 B contiguous per warp; the mirrored block goes through a padded shared-memory transpose so it
-// is written as 256 B rows too.
+// warp broadcast.  Affine-invariant kinds (spd_ai_gram_kernel): per pair the d x d congruence W_i S_j W_i^T and its
+// Householder tridiagonalisation in FP64, eigenvalue STARTS by an implicit-shift QL in FP32 run for TWO rows at once in
+// packed FFMA2 registers, two FP64 Newton steps per eigenvalue on the characteristic polynomial (validated; an all-FP64
+// QL / cyclic Jacobi slow path otherwise), lean log / exp.  Stein (spd_gram_kernel): LDL^T of S_i + S_j in registers.
+// Row stores are 256 B contiguous per warp; the mirrored block goes through a padded shared-memory transpose.
+#include <cstdlib>
 #include "spd_small.cuh"
+#include "gabo_math.cuh"
 
 namespace gabo {
 namespace {
@@ -292,12 +296,196 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_gram_kernel(const Sp
     }
 }
 
+// ---- affine-invariant pair kernel, second generation ----------------------------------------------------------------------
+// Measured on the first version (profiles/r01_spd_gram_mixed_ncu.txt): issue-bound at 3.3 k warp instructions per pair-warp,
+// 41 % of them the FP32 QL start (rsqrtf()/__fdividef() denormal guards, convergence tests, a 6x unrolled iteration loop)
+// and a 67 KB loop body that does not fit the 32 KB L1.5 instruction cache (stall_no_instruction 1.3 per issue).  Here:
+//   * two rows per trip; their FP32 QL chains share packed FFMA2 instructions (ql_tri_eigvals_start_f32x2);
+//   * the FP64 phases are ROLLED over the two rows (results pass through a per-thread shared-memory stash), the QL
+//     iteration loop is rolled, log/exp are the lean versions of gabo_math.cuh: loop body ~25 KB;
+//   * the mirror transpose buffer holds 8 rows (64 B mirrored segments = whole sectors), 38 KB of shared memory per CTA.
+constexpr int AI_TH = 8;           // rows per mirror-transpose phase
+constexpr int AI_SLD = TJ + 1;     // padded leading dimension of the transpose buffer
+
+template <int D>
+struct AiSmem {
+    static constexpr int MP = D * (D + 1) / 2;
+    static constexpr int NST = 2 * D;                       // stash per (row of the pair, thread): ds[D], es[D-1], trace
+    static constexpr size_t w_off = 0;                                              // [TI][MP]
+    static constexpr size_t stash_off = w_off + sizeof(double) * TI * MP;           // [2][NST][TJ]
+    static constexpr size_t out_off = stash_off + sizeof(double) * 2 * NST * TJ;    // [AI_TH][AI_SLD]
+    static constexpr size_t tab_off = out_off + sizeof(double) * AI_TH * AI_SLD;    // [32]
+    static constexpr size_t bytes = tab_off + sizeof(double) * 32;
+};
+
+// slow path of one pair with S_j handed over as a packed upper triangle (see ai_sumlog2_slow)
+template <int D, int KIND>
+__global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_ai_gram_kernel(const SpdGramParams p) {
+    constexpr int DD = D * D;
+    constexpr int MP = D * (D + 1) / 2;
+    constexpr int NST = AiSmem<D>::NST;
+    extern __shared__ __align__(16) unsigned char ai_smem_raw[];
+    double (*sW)[MP] = reinterpret_cast<double (*)[MP]>(ai_smem_raw + AiSmem<D>::w_off);
+    double* const sStash = reinterpret_cast<double*>(ai_smem_raw + AiSmem<D>::stash_off);
+    double (*sOut)[AI_SLD] = reinterpret_cast<double (*)[AI_SLD]>(ai_smem_raw + AiSmem<D>::out_off);
+    double* const sTab = reinterpret_cast<double*>(ai_smem_raw + AiSmem<D>::tab_off);
+
+    const int tid = threadIdx.x;
+    const int64_t i0 = p.row0 + (int64_t)blockIdx.y * TI;
+    const int64_t j0 = (int64_t)blockIdx.x * TJ;
+    if (p.uplo != GABO_FULL && j0 > i0 + TI - 1) return;   // symmetric modes: blocks strictly above the diagonal
+    const bool mirror = (p.uplo == GABO_SYMM_MIRROR);
+
+    for (int e = tid; e < TI * MP; e += TJ) {
+        const int r = e / MP, idx = e - r * MP;
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= idx) ++a;
+        const int k = idx - a * (a + 1) / 2;
+        const int64_t gi = i0 + r;
+        sW[r][idx] = (gi < p.row1) ? p.R[gi * DD + a * D + k] : (a == k ? 1.0 : 0.0);   // W_i (identity past the last row)
+    }
+    if (tid < 32) sTab[tid] = kExp2Tab[tid] * p.variance;
+
+    const int64_t j = j0 + tid;
+    const bool jok = j < p.n2;
+    double B[D][D];   // S2[j], upper storage used
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = r; c < D; ++c) B[r][c] = jok ? p.Cm[j * DD + r * D + c] : (r == c ? 1.0 : 0.0);
+    __syncthreads();
+
+    const double nbeta = -p.beta, variance = p.variance;
+    const int rows_here = (int)((p.row1 - i0) < (int64_t)TI ? (p.row1 - i0) : (int64_t)TI);
+    double* const stash0 = sStash + tid;   // entry k of row u of the pair: stash0[(u * NST + k) * TJ]
+
+#pragma unroll 1
+    for (int hb = 0; hb < TI; hb += AI_TH) {
+        if (hb >= rows_here) break;
+#pragma unroll 1
+        for (int r = hb; r < hb + AI_TH; r += 2) {
+            // lanes that have a pair to evaluate in row r / r + 1 (the rest computes along on benign data and is discarded)
+            bool act[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int64_t gi = i0 + r + u;
+                act[u] = jok && (r + u < rows_here) && !(mirror && j > gi) && !(p.symmetric && gi == j);
+            }
+            double val[2] = {0.0, 0.0};
+            if (__any_sync(0xffffffffu, act[0] || act[1])) {
+                // phase A (FP64, rolled over the two rows): congruence, Householder, trace normalisation -> stash
+#pragma unroll 1
+                for (int u = 0; u < 2; ++u) {
+                    double Mx[D][D], td[D], te[D];
+                    ai_congruence<D>(sW[r + u], B, Mx);
+                    householder_tridiag<D>(Mx, td, te);
+                    double tr = 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) tr += td[k];
+                    const double rt = rcp_nr2(tr);
+                    double* st = stash0 + (size_t)u * NST * TJ;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) st[k * TJ] = td[k] * rt;
+#pragma unroll
+                    for (int k = 0; k < D - 1; ++k) st[(D + k) * TJ] = te[k] * rt;
+                    st[(2 * D - 1) * TJ] = tr;
+                }
+                // phase B (FP32, both rows in packed halves): implicit-shift QL for the starting values
+                f32x2_t dp[D], ep[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) dp[k] = f2_pack((float)stash0[k * TJ], (float)stash0[(NST + k) * TJ]);
+#pragma unroll
+                for (int k = 0; k < D - 1; ++k) ep[k] = f2_pack((float)stash0[(D + k) * TJ], (float)stash0[(NST + D + k) * TJ]);
+                ep[D - 1] = 0ull;
+                ql_tri_eigvals_start_f32x2<D>(dp, ep);
+                // phase C (FP64, rolled): Newton refinement, validation, sum of squared logs
+                double arg[2];
+#pragma unroll 1
+                for (int u = 0; u < 2; ++u) {
+                    const double* st = stash0 + (size_t)u * NST * TJ;
+                    double ds[D], e2[D], ev[D];
+                    float x0[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        ds[k] = st[k * TJ];
+                        x0[k] = u ? f2_hi(dp[k]) : f2_lo(dp[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < D - 1; ++k) { const double es = st[(D + k) * TJ]; e2[k] = es * es; }
+                    e2[D - 1] = 0.0;
+                    const double tr = st[(2 * D - 1) * TJ];
+                    bool fast = tridiag_newton_refine<D>(ds, e2, x0, ev);
+                    double emin = ev[0], emax = ev[0];
+#pragma unroll
+                    for (int k = 1; k < D; ++k) { emin = fmin(emin, ev[k]); emax = fmax(emax, ev[k]); }
+                    fast = fast && (emin > 0.02 * emax) && (tr > 1e-280) && (tr < 1e280);
+                    double s2 = 0.0;
+                    if (fast) {
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            const double lg = log_pos_normal(ev[k] * tr);   // SPD_utils_tf.py:136-139
+                            s2 = fma(lg, lg, s2);
+                        }
+                    } else if (u ? act[1] : act[0]) {
+                        SymPacked<D> Sp;
+#pragma unroll
+                        for (int rr = 0; rr < D; ++rr)
+#pragma unroll
+                            for (int cc = rr; cc < D; ++cc) Sp.v[rr * D - rr * (rr - 1) / 2 + (cc - rr)] = B[rr][cc];
+                        s2 = ai_sumlog2_slow<D>(sW[r + u], Sp);
+                    }
+                    const double a = (KIND == GABO_SPD_AI_GAUSSIAN) ? nbeta * s2 : nbeta * sqrt(s2);   // kernels_spd_tf.py:241-248 / 396-400
+                    if (u) arg[1] = a; else arg[0] = a;
+                }
+                exp_neg_scaled_fast_n<2>(arg, val, sTab, variance);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int64_t gi = i0 + r + u;
+                if (p.symmetric && gi == j) val[u] = variance;   // d_AI(X,X) = 0 exactly
+                const bool skip = mirror && (j > gi);
+                if (jok && (r + u < rows_here) && !skip) st_cs(p.K + (gi - p.row0) * p.ldk + j, val[u]);
+                if (mirror) sOut[r + u - hb][tid] = val[u];
+            }
+        }
+        if (mirror) {
+            // transposed write of this 8-row strip: 8 lanes per mirrored row, 64 B contiguous
+            __syncthreads();
+            const int lane = tid & 31, warp = tid >> 5;
+            const int cr = lane & 7;
+            for (int jl = warp * 4 + (lane >> 3); jl < TJ; jl += 16) {
+                const int64_t gj = j0 + jl;          // becomes the row of the mirrored entry
+                const int64_t gi = i0 + hb + cr;     // becomes the column
+                if (gj < p.n2 && hb + cr < rows_here && gj < gi) st_cs(p.K + gj * p.ldk + gi, sOut[cr][jl]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int D, int KIND>
+int launch_spd_ai(const SpdGramParams& p, dim3 grid, cudaStream_t stream) {
+    static bool attr_set = false;   // idempotent; a race only repeats the call
+    if (!attr_set) {
+        GABO_CUDA_TRY(cudaFuncSetAttribute(spd_ai_gram_kernel<D, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)AiSmem<D>::bytes));
+        attr_set = true;
+    }
+    spd_ai_gram_kernel<D, KIND><<<grid, TJ, AiSmem<D>::bytes, stream>>>(p);
+    return 0;
+}
+
 template <int D>
 int launch_spd_gram(int kind, const SpdGramParams& p, cudaStream_t stream) {
     dim3 grid((unsigned)ceil_div64(p.n2, TJ), (unsigned)ceil_div64(p.row1 - p.row0, TI));
-    if (kind == GABO_SPD_AI_GAUSSIAN) spd_gram_kernel<D, GABO_SPD_AI_GAUSSIAN><<<grid, TJ, 0, stream>>>(p);
-    else if (kind == GABO_SPD_AI_LAPLACE) spd_gram_kernel<D, GABO_SPD_AI_LAPLACE><<<grid, TJ, 0, stream>>>(p);
-    else spd_gram_kernel<D, GABO_SPD_STEIN><<<grid, TJ, 0, stream>>>(p);
+    static const bool ai_v1 = (getenv("GABO_SPD_AI_V1") != nullptr);   // A/B switch for profiling: first-generation kernel
+    int rc = 0;
+    if (kind == GABO_SPD_STEIN) spd_gram_kernel<D, GABO_SPD_STEIN><<<grid, TJ, 0, stream>>>(p);
+    else if (ai_v1 && kind == GABO_SPD_AI_GAUSSIAN) spd_gram_kernel<D, GABO_SPD_AI_GAUSSIAN><<<grid, TJ, 0, stream>>>(p);
+    else if (ai_v1) spd_gram_kernel<D, GABO_SPD_AI_LAPLACE><<<grid, TJ, 0, stream>>>(p);
+    else if (kind == GABO_SPD_AI_GAUSSIAN) rc = launch_spd_ai<D, GABO_SPD_AI_GAUSSIAN>(p, grid, stream);
+    else rc = launch_spd_ai<D, GABO_SPD_AI_LAPLACE>(p, grid, stream);
+    if (rc) return rc;
     GABO_LAUNCH_CHECK();
     return 0;
 }
@@ -368,13 +556,15 @@ extern "C" int gabo_spd_gram_f64(int kind, int d, const double* W1, const double
     p.row0 = row0; p.row1 = row1; p.symmetric = symmetric ? 1 : 0; p.uplo = uplo; p.beta = beta; p.variance = variance;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (d) {
+#ifndef GABO_SPD_ONLY_D6   /* development builds: compile the d = 6 pair kernels only (the full set takes ~100 s) */
         case 2: return launch_spd_gram<2>(kind, p, s);
         case 3: return launch_spd_gram<3>(kind, p, s);
         case 4: return launch_spd_gram<4>(kind, p, s);
         case 5: return launch_spd_gram<5>(kind, p, s);
-        case 6: return launch_spd_gram<6>(kind, p, s);
         case 7: return launch_spd_gram<7>(kind, p, s);
-        default: return launch_spd_gram<8>(kind, p, s);
+        case 8: return launch_spd_gram<8>(kind, p, s);
+#endif
+        default: return launch_spd_gram<6>(kind, p, s);
     }
 }
 

@@ -453,3 +453,14 @@ def expected_improvement(mean: torch.Tensor, var: torch.Tensor, fmin: float) -> 
     st = _lib.lib().gabo_expected_improvement_f64(int(m.numel()), m.data_ptr(), v.data_ptr(), float(fmin), out.data_ptr(), _stream())
     _lib.check('gabo_expected_improvement_f64', st)
     return out.reshape(mean.shape)
+
+
+def math_probe(which: int, x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """Diagnostic (gabo_math_probe_f64): the lean device acos (0) / scale*exp for x <= 0 (1) / log of positive normals (2)
+    that the Gram epilogues inline, evaluated element-wise on a 1-D FP64 tensor."""
+    _req(x, 'x')
+    xc = x.reshape(-1).contiguous()
+    out = torch.empty_like(xc)
+    st = _lib.lib().gabo_math_probe_f64(int(which), xc.data_ptr(), int(xc.numel()), float(scale), out.data_ptr(), _stream())
+    _lib.check('gabo_math_probe_f64', st)
+    return out.reshape(x.shape)

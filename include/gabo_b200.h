@@ -179,6 +179,11 @@ int gabo_sphere_posterior_grad_f64(int kind, int64_t n, int64_t M, int dim, cons
 int gabo_expected_improvement_f64(int64_t M, const double* mean, const double* var, double fmin, double* out,
                                   gabo_stream_t stream);
 
+/* Diagnostic: element-wise evaluation of the lean device math that the Gram epilogues inline (csrc/gabo_math.cuh), through
+ * the same batched code paths: which = 0 acos(clamp(x,-1,1)) (sphere_utils_tf.py:59-60), 1 scale*exp(x) for x <= 0
+ * (kernels_sphere_tf.py:88), 2 log(x) for positive normal x (SPD_utils_tf.py:136).  For accuracy tests only. */
+int gabo_math_probe_f64(int which, const double* x, int64_t n, double scale, double* out, gabo_stream_t stream);
+
 /* Diagnostic: in-situ timing of the dominant kernel.  gabo_profile_trailing_updates(1) makes gabo_potrf_f64 bracket each big
  * trailing-update launch (gemm_kernel, k = 512) with CUDA events on its stream; gabo_profile_trailing_read sums them
  * (launch count, device ms, algorithmic flops, and the longest launch); (0) switches it off and drops the records. */
