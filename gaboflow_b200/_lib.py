@@ -20,8 +20,8 @@ SIGNATURES = {
     'gabo_points_gram_f64': (i32, [i32, vp, i64, i64, vp, i64, i64, i32, f64, f64, vp, i64, i64, i64, i32, vp, sz, vp]),
     'gabo_points_gram_f32': (i32, [i32, vp, i64, i64, vp, i64, i64, i32, f32, f32, vp, i64, i64, i64, i32, vp, sz, vp]),
     'gabo_kdiag_const_f64': (i32, [i64, f64, vp, vp]),
-    'gabo_spd_prep_f64': (i32, [vp, i64, i64, i32, vp, vp, vp, vp, vp, vp]),
-    'gabo_spd_gram_f64': (i32, [i32, i32, vp, vp, vp, i64, vp, vp, i64, i32, f64, f64, vp, i64, i64, i64, i32, vp]),
+    'gabo_spd_prep_f64': (i32, [vp, i64, i64, i32, vp, vp, vp, vp, vp, i64, vp, vp]),
+    'gabo_spd_gram_f64': (i32, [i32, i32, vp, vp, vp, i64, vp, vp, i64, vp, i64, i32, f64, f64, vp, i64, i64, i64, i32, vp]),
     'gabo_spd_stein_kdiag_f64': (i32, [vp, i64, f64, f64, vp, vp]),
     'gabo_potrf_workspace_bytes': (sz, [i64]),
     'gabo_potrf_f64': (i32, [i64, vp, i64, f64, vp, vp, sz, vp]),
@@ -82,7 +82,7 @@ def lib():
             fn = getattr(handle, name)   # AttributeError if the ABI and the header ever diverge
             fn.restype = res
             fn.argtypes = args
-        if handle.gabo_abi_version() != 1:
+        if handle.gabo_abi_version() != 2:
             raise ImportError('libgabo_b200.so ABI version mismatch; rebuild')
         _lib = handle
     return _lib

@@ -14,7 +14,6 @@
 // packed FFMA2 registers, two FP64 Newton steps per eigenvalue on the characteristic polynomial (validated; an all-FP64
 // QL / cyclic Jacobi slow path otherwise), lean log / exp.  Stein (spd_gram_kernel): LDL^T of S_i + S_j in registers.
 // Row stores are 256 B contiguous per warp; the mirrored block goes through a padded shared-memory transpose.
-#include <cstdlib>
 #include "spd_small.cuh"
 #include "gabo_math.cuh"
 
@@ -28,7 +27,8 @@ constexpr int TJ = 128;   // columns per CTA == threads per CTA
 template <int D>
 __global__ void spd_prep_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, double* __restrict__ outS,
                                 double* __restrict__ outW, double* __restrict__ outLogdet,
-                                double* __restrict__ outLogm, int32_t* __restrict__ info) {
+                                double* __restrict__ outLogm, double* __restrict__ outLt, int64_t ldt,
+                                int32_t* __restrict__ info) {
     constexpr int M = D * (D + 1) / 2;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -61,6 +61,12 @@ __global__ void spd_prep_kernel(const double* __restrict__ X, int64_t n, int64_t
         for (int r = 0; r < D; ++r)
 #pragma unroll
             for (int c = 0; c < D; ++c) outW[i * D * D + r * D + c] = bad ? nanv : (c <= r ? W[r][c] : 0.0);
+    }
+    if (outLt) {   // packed lower factor, transposed: entry (a,k) of point i at outLt[(a(a+1)/2 + k) * ldt + i] (coalesced per entry)
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int k = 0; k <= a; ++k) outLt[(int64_t)(a * (a + 1) / 2 + k) * ldt + i] = bad ? nanv : L[a][k];
     }
     if (outLogdet) {
         double prod = 1.0;
@@ -102,60 +108,59 @@ __global__ void spd_prep_kernel(const double* __restrict__ X, int64_t n, int64_t
 struct SpdGramParams {
     const double* R;        // row operand [n1, d*d]: W (AI kinds) or S (Stein)
     const double* Rld;      // logdet of row points (Stein) or nullptr
-    const double* Cm;       // column operand S2 [n2, d*d]
+    const double* Cm;       // Stein: column operand S2 [n2, d*d]
+    const double* Lt;       // AI kinds: column operand, packed lower Cholesky factors, transposed [MP][ldt]
     const double* Cld;      // logdet of column points (Stein) or nullptr
     double* K;
-    int64_t ldk, n1, n2, row0, row1;
+    int64_t ldk, ldt, n1, n2, row0, row1;
     int symmetric, uplo;
     double beta, variance;
 };
 
-// M = W S W^T for one pair: W lower (packed triangle wrow: entry (a,k), k <= a, at a(a+1)/2 + k), S symmetric (upper storage).
+// M = (W L)(W L)^T for one pair: W = chol(S_i)^-1 and L = chol(S_j), both lower triangular and packed (entry (a,k), k <= a,
+// at a(a+1)/2 + k).  G = W L is lower triangular again, so the congruence W S_j W^T costs 2 * d(d+1)(d+2)/6 = 112 FMA at
+// d = 6 (182 through the dense S_j) and never holds more than two triangles in registers.  Mx: upper storage.
 template <int D>
-__device__ __forceinline__ void ai_congruence(const double* __restrict__ wrow, const double (&B)[D][D], double (&Mx)[D][D]) {
+__device__ __forceinline__ void ai_congruence(const double* __restrict__ wrow, const double (&Lj)[D * (D + 1) / 2],
+                                              double (&Mx)[D][D]) {
+    double G[D][D];
 #pragma unroll
-    for (int a = 0; a < D; ++a) {
-        double T[D];
+    for (int a = 0; a < D; ++a)
 #pragma unroll
-        for (int c = 0; c < D; ++c) {
-            double v = 0.0;
+        for (int c = 0; c <= a; ++c) {
+            double v = wrow[a * (a + 1) / 2 + c] * Lj[c * (c + 1) / 2 + c];
 #pragma unroll
-            for (int k = 0; k <= a; ++k) v = fma(wrow[a * (a + 1) / 2 + k], GABO_SYM(B, k, c), v);
-            T[c] = v;
+            for (int k = c + 1; k <= a; ++k) v = fma(wrow[a * (a + 1) / 2 + k], Lj[k * (k + 1) / 2 + c], v);
+            G[a][c] = v;
         }
 #pragma unroll
-        for (int b = 0; b <= a; ++b) {
-            double v = 0.0;
+    for (int b = 0; b < D; ++b)
 #pragma unroll
-            for (int k = 0; k <= b; ++k) v = fma(T[k], wrow[b * (b + 1) / 2 + k], v);
-            Mx[b][a] = v;   // upper storage
+        for (int a = b; a < D; ++a) {
+            double v = G[a][0] * G[b][0];
+#pragma unroll
+            for (int k = 1; k <= b; ++k) v = fma(G[a][k], G[b][k], v);
+            Mx[b][a] = v;
         }
-    }
 }
 
-// Out-of-line slow path of the affine-invariant pair (kept out of the hot loop: ~3 k instructions that would otherwise sit
-// between the fast path's blocks in the instruction cache and inflate its register allocation).  Taken when the
+// Out-of-line slow path of the affine-invariant pair (kept out of the hot loop: ~3 k instructions).  Taken when the
 // mixed-precision eigenvalues do not validate (near-multiple eigenvalues) or the spectrum is wide: all-FP64 QL on the
-// tridiagonal, then cyclic Jacobi (relative accuracy) if lambda_min <= 0.02 lambda_max.  S2 travels by value (packed upper
-// triangle) so that the caller's copy can stay in registers.  Returns sum_k log^2 lambda_k.
+// tridiagonal, then cyclic Jacobi (relative accuracy) if lambda_min <= 0.02 lambda_max.  L_j travels by value (packed)
+// so that the caller's copy can stay in registers.  Returns sum_k log^2 lambda_k.
 template <int D>
-struct SymPacked { double v[D * (D + 1) / 2]; };
+struct TriPacked { double v[D * (D + 1) / 2]; };
 
 template <int D>
-__device__ __noinline__ double ai_sumlog2_slow(const double* __restrict__ wrow, const SymPacked<D> Sp) {
-    double B[D][D];
-#pragma unroll
-    for (int r = 0; r < D; ++r)
-#pragma unroll
-        for (int c = r; c < D; ++c) B[r][c] = Sp.v[r * D - r * (r - 1) / 2 + (c - r)];
+__device__ __noinline__ double ai_sumlog2_slow(const double* __restrict__ wrow, const TriPacked<D> Lp) {
     double Mx[D][D], ev[D];
-    ai_congruence<D>(wrow, B, Mx);
+    ai_congruence<D>(wrow, Lp.v, Mx);
     tridiag_ql_eigvals<D>(Mx, ev);
     double emin = ev[0], emax = ev[0];
 #pragma unroll
     for (int k = 1; k < D; ++k) { emin = fmin(emin, ev[k]); emax = fmax(emax, ev[k]); }
     if (!(emin > 0.02 * emax)) {
-        ai_congruence<D>(wrow, B, Mx);
+        ai_congruence<D>(wrow, Lp.v, Mx);
         double dummy[1][1];
         jacobi_eig<D, false>(Mx, dummy);
 #pragma unroll
@@ -170,8 +175,9 @@ __device__ __noinline__ double ai_sumlog2_slow(const double* __restrict__ wrow, 
     return s2;
 }
 
-template <int D, int KIND>
-__global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_gram_kernel(const SpdGramParams p) {
+// ---- Stein pair kernel: thread = one column j with S_j in registers, 32 rows per CTA -------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_stein_gram_kernel(const SpdGramParams p) {
     constexpr int DD = D * D;
     constexpr int MP = D * (D + 1) / 2;   // packed lower triangle: entry (a,k), k <= a, at a(a+1)/2 + k
     __shared__ double sR[TI][MP];
@@ -181,8 +187,7 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_gram_kernel(const Sp
     const int tid = threadIdx.x;
     const int64_t i0 = p.row0 + (int64_t)blockIdx.y * TI;
     const int64_t j0 = (int64_t)blockIdx.x * TJ;
-    // symmetric modes: blocks strictly above the diagonal are not needed
-    if (p.uplo != GABO_FULL && j0 > i0 + TI - 1) return;
+    if (p.uplo != GABO_FULL && j0 > i0 + TI - 1) return;   // symmetric modes: blocks strictly above the diagonal
     const bool mirror = (p.uplo == GABO_SYMM_MIRROR);
 
     for (int e = tid; e < TI * MP; e += TJ) {
@@ -191,9 +196,9 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_gram_kernel(const Sp
         while ((a + 1) * (a + 2) / 2 <= idx) ++a;
         const int k = idx - a * (a + 1) / 2;
         const int64_t gi = i0 + r;
-        sR[r][idx] = (gi < p.row1) ? p.R[gi * DD + a * D + k] : 0.0;   // lower triangle of W_i, or of the symmetric S_i
+        sR[r][idx] = (gi < p.row1) ? p.R[gi * DD + a * D + k] : 0.0;   // lower triangle of the symmetric S_i
     }
-    if (KIND == GABO_SPD_STEIN && tid < TI) sRld[tid] = (i0 + tid < p.row1) ? p.Rld[i0 + tid] : 0.0;
+    if (tid < TI) sRld[tid] = (i0 + tid < p.row1) ? p.Rld[i0 + tid] : 0.0;
 
     const int64_t j = j0 + tid;
     const bool jok = j < p.n2;
@@ -202,85 +207,49 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_gram_kernel(const Sp
     for (int r = 0; r < D; ++r)
 #pragma unroll
         for (int c = r; c < D; ++c) B[r][c] = jok ? p.Cm[j * DD + r * D + c] : (r == c ? 1.0 : 0.0);
-    double cld = 0.0;
-    if (KIND == GABO_SPD_STEIN && jok) cld = p.Cld[j];
+    const double cld = jok ? p.Cld[j] : 0.0;
     __syncthreads();
 
     const int rows_here = (int)((p.row1 - i0) < (int64_t)TI ? (p.row1 - i0) : (int64_t)TI);
     for (int r = 0; r < rows_here; ++r) {
         const int64_t gi = i0 + r;
-        // in the mirrored mode the strictly upper entries are produced by their transposes
-        const bool skip = mirror && (j > gi);
+        const bool skip = mirror && (j > gi);   // in the mirrored mode the strictly upper entries are produced by their transposes
         double val = 0.0;
         if (jok && !skip) {
-            if (KIND == GABO_SPD_STEIN) {
-                // log det(S_i + S_j) by an LDL^T elimination in registers (no square roots)
-                double A[D][D];
+            // log det(S_i + S_j) by an LDL^T elimination in registers (no square roots)
+            double A[D][D];
 #pragma unroll
-                for (int a = 0; a < D; ++a)
+            for (int a = 0; a < D; ++a)
 #pragma unroll
-                    for (int b = a; b < D; ++b) A[a][b] = sR[r][b * (b + 1) / 2 + a] + B[a][b];
-                double piv[D];
-                double prod = 1.0;
-                bool bad = false;
+                for (int b = a; b < D; ++b) A[a][b] = sR[r][b * (b + 1) / 2 + a] + B[a][b];
+            double piv[D];
+            double prod = 1.0;
+            bool bad = false;
 #pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    piv[k] = A[k][k];
-                    bad = bad || !(piv[k] > 0.0);
-                    prod *= piv[k];
-                    const double rp = 1.0 / piv[k];
+            for (int k = 0; k < D; ++k) {
+                piv[k] = A[k][k];
+                bad = bad || !(piv[k] > 0.0);
+                prod *= piv[k];
+                const double rp = 1.0 / piv[k];
 #pragma unroll
-                    for (int a = k + 1; a < D; ++a) {
-                        const double l = A[k][a] * rp;
+                for (int a = k + 1; a < D; ++a) {
+                    const double l = A[k][a] * rp;
 #pragma unroll
-                        for (int b = a; b < D; ++b) A[a][b] = fma(-l, A[k][b], A[a][b]);
-                    }
-                }
-                double lgdet;
-                if (prod > 1e-280 && prod < 1e280) {
-                    lgdet = log(prod);
-                } else {   // pivot product out of range: sum the logs instead
-                    lgdet = 0.0;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) lgdet += log(piv[k]);
-                }
-                const double ldsum = lgdet - (double)D * 0.69314718055994530942;   // log det((A+B)/2)
-                // kernels_spd_tf.py:104-112: det(X X2)^beta / det((X+X2)/2)^beta
-                val = p.variance * exp(p.beta * (sRld[r] + cld - ldsum));
-                if (bad) val = __longlong_as_double(0x7ff8000000000000LL);
-            } else {
-                if (p.symmetric && gi == j) {
-                    val = p.variance;   // d_AI(X,X) = 0 exactly
-                } else {
-                    // M = W_i S_j W_i^T, Householder (FP64), then FP32 QL + FP64 Newton refinement of the eigenvalues; the
-                    // out-of-line slow path when that does not validate or the spectrum is wide (ai_sumlog2_slow)
-                    double Mx[D][D], ev[D], td[D], te[D];
-                    ai_congruence<D>(sR[r], B, Mx);
-                    householder_tridiag<D>(Mx, td, te);
-                    bool fast = tridiag_eigvals_mixed<D>(td, te, ev);
-                    double emin = ev[0], emax = ev[0];
-#pragma unroll
-                    for (int k = 1; k < D; ++k) { emin = fmin(emin, ev[k]); emax = fmax(emax, ev[k]); }
-                    fast = fast && (emin > 0.02 * emax);
-                    double s2 = 0.0;
-                    if (fast) {
-#pragma unroll
-                        for (int k = 0; k < D; ++k) {
-                            const double lg = log(ev[k]);   // SPD_utils_tf.py:136-139
-                            s2 = fma(lg, lg, s2);
-                        }
-                    } else {
-                        SymPacked<D> Sp;
-#pragma unroll
-                        for (int rr = 0; rr < D; ++rr)
-#pragma unroll
-                            for (int cc = rr; cc < D; ++cc) Sp.v[rr * D - rr * (rr - 1) / 2 + (cc - rr)] = B[rr][cc];
-                        s2 = ai_sumlog2_slow<D>(sR[r], Sp);
-                    }
-                    if (KIND == GABO_SPD_AI_GAUSSIAN) val = p.variance * exp(-p.beta * s2);          // kernels_spd_tf.py:241-248
-                    else val = p.variance * exp(-p.beta * sqrt(s2));                                 // kernels_spd_tf.py:396-400
+                    for (int b = a; b < D; ++b) A[a][b] = fma(-l, A[k][b], A[a][b]);
                 }
             }
+            double lgdet;
+            if (prod > 1e-280 && prod < 1e280) {
+                lgdet = log(prod);
+            } else {   // pivot product out of range: sum the logs instead
+                lgdet = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) lgdet += log(piv[k]);
+            }
+            const double ldsum = lgdet - (double)D * 0.69314718055994530942;   // log det((A+B)/2)
+            // kernels_spd_tf.py:104-112: det(X X2)^beta / det((X+X2)/2)^beta
+            val = p.variance * exp(p.beta * (sRld[r] + cld - ldsum));
+            if (bad) val = __longlong_as_double(0x7ff8000000000000LL);
             st_cs(p.K + (gi - p.row0) * p.ldk + j, val);
         }
         if (mirror) sOut[r][tid] = val;
@@ -296,31 +265,66 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_gram_kernel(const Sp
     }
 }
 
-// ---- affine-invariant pair kernel, second generation ----------------------------------------------------------------------
-// Measured on the first version (profiles/r01_spd_gram_mixed_ncu.txt): issue-bound at 3.3 k warp instructions per pair-warp,
-// 41 % of them the FP32 QL start (rsqrtf()/__fdividef() denormal guards, convergence tests, a 6x unrolled iteration loop)
-// and a 67 KB loop body that does not fit the 32 KB L1.5 instruction cache (stall_no_instruction 1.3 per issue).  Here:
-//   * two rows per trip; their FP32 QL chains share packed FFMA2 instructions (ql_tri_eigvals_start_f32x2);
-//   * the FP64 phases are ROLLED over the two rows (results pass through a per-thread shared-memory stash), the QL
-//     iteration loop is rolled, log/exp are the lean versions of gabo_math.cuh: loop body ~25 KB;
-//   * the mirror transpose buffer holds 8 rows (64 B mirrored segments = whole sectors), 38 KB of shared memory per CTA.
+// ---- affine-invariant pair kernel ----------------------------------------------------------------------------------------
+// History, measured at N = 16384, d = 6 (profiles/r01_spd_gram_mixed_ncu.txt, profiles/r02_spd_ai_*.txt):
+//   v1  one row per trip, scalar FP32 QL (rsqrtf()/__fdividef() denormal guards, six unrolled iterations per level): 3.3 k warp
+//       instructions per pair, a 67 KB loop body that misses the 32 KB L1.5 instruction cache (stall_no_instruction 1.3 per
+//       issue), S_j held in 42 registers: 20.3 ms.
+//   v2  two rows per trip with their QL chains in packed FFMA2 halves, the FP64 phases ROLLED over the rows of a trip (results
+//       pass through a per-thread shared-memory stash), rolled QL iterations, lean log / exp: 2.3 k instructions, 33 KB: 14.3 ms.
+//   v3  four rows per trip (two packed chains for instruction-level parallelism in the QL phase): MUFU latency hidden, but a
+//       46 KB loop body and more local-memory traffic: 14.5 ms.
+//   v4  (this one) two rows per trip; the congruence W_i S_j W_i^T is accumulated as a sum of outer products of the columns of
+//       G = W_i L_j (L_j = chol(S_j), lower: 112 instead of 182 FMA), with the columns of L_j read from L1 / L2 when needed
+//       (transposed layout: coalesced) instead of S_j living in 42 registers through phases that never use it.
+constexpr int AI_NR = 2;           // rows per trip
 constexpr int AI_TH = 8;           // rows per mirror-transpose phase
-constexpr int AI_SLD = TJ + 1;     // padded leading dimension of the transpose buffer
+constexpr int AI_SLD = TJ + 1;     // padded leading dimension of the mirror transpose buffer
 
 template <int D>
 struct AiSmem {
     static constexpr int MP = D * (D + 1) / 2;
-    static constexpr int NST = 2 * D;                       // stash per (row of the pair, thread): ds[D], es[D-1], trace
-    static constexpr size_t w_off = 0;                                              // [TI][MP]
-    static constexpr size_t stash_off = w_off + sizeof(double) * TI * MP;           // [2][NST][TJ]
-    static constexpr size_t out_off = stash_off + sizeof(double) * 2 * NST * TJ;    // [AI_TH][AI_SLD]
-    static constexpr size_t tab_off = out_off + sizeof(double) * AI_TH * AI_SLD;    // [32]
+    static constexpr int NST = 2 * D;                       // stash per (row of the trip, thread): ds[D], es[D-1], trace
+    static constexpr size_t w_off = 0;                                                  // [TI][MP]
+    static constexpr size_t stash_off = w_off + sizeof(double) * TI * MP;               // [AI_NR][NST][TJ]
+    static constexpr size_t out_off = stash_off + sizeof(double) * AI_NR * NST * TJ;    // [AI_TH][AI_SLD]
+    static constexpr size_t tab_off = out_off + sizeof(double) * AI_TH * AI_SLD;        // [32]
     static constexpr size_t bytes = tab_off + sizeof(double) * 32;
 };
 
-// slow path of one pair with S_j handed over as a packed upper triangle (see ai_sumlog2_slow)
+// a load that the compiler may neither hoist out of the row loop nor keep live across it
+__device__ __forceinline__ double ld_global_keep(const double* ptr) {
+    double v;
+    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
+    return v;
+}
+
+// M = (W L)(W L)^T accumulated over the columns g_c of G = W L: M += g_c g_c^T.  w: packed lower W_i in shared memory;
+// lt: entry (k,c) of L_j at lt[(k(k+1)/2 + c) * ldt] (global, L1-resident).  Mx: upper storage.
+template <int D>
+__device__ __forceinline__ void ai_congruence_cols(const double* __restrict__ w, const double* lt, int64_t ldt,
+                                                   double (&Mx)[D][D]) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        double lc[D], g[D];
+#pragma unroll
+        for (int k = c; k < D; ++k) lc[k] = ld_global_keep(lt + (int64_t)(k * (k + 1) / 2 + c) * ldt);
+#pragma unroll
+        for (int a = c; a < D; ++a) {
+            double v = w[a * (a + 1) / 2 + c] * lc[c];
+#pragma unroll
+            for (int k = c + 1; k <= a; ++k) v = fma(w[a * (a + 1) / 2 + k], lc[k], v);
+            g[a] = v;
+        }
+#pragma unroll
+        for (int b = c; b < D; ++b)
+#pragma unroll
+            for (int a = b; a < D; ++a) Mx[b][a] = (c == 0) ? g[a] * g[b] : fma(g[a], g[b], Mx[b][a]);
+    }
+}
+
 template <int D, int KIND>
-__global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_ai_gram_kernel(const SpdGramParams p) {
+__global__ void __launch_bounds__(TJ, (D <= 6) ? 5 : 2) spd_ai_gram_kernel(const SpdGramParams p) {
     constexpr int DD = D * D;
     constexpr int MP = D * (D + 1) / 2;
     constexpr int NST = AiSmem<D>::NST;
@@ -345,50 +349,45 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_ai_gram_kernel(const
         sW[r][idx] = (gi < p.row1) ? p.R[gi * DD + a * D + k] : (a == k ? 1.0 : 0.0);   // W_i (identity past the last row)
     }
     if (tid < 32) sTab[tid] = kExp2Tab[tid] * p.variance;
+    __syncthreads();
 
     const int64_t j = j0 + tid;
     const bool jok = j < p.n2;
-    double B[D][D];   // S2[j], upper storage used
-#pragma unroll
-    for (int r = 0; r < D; ++r)
-#pragma unroll
-        for (int c = r; c < D; ++c) B[r][c] = jok ? p.Cm[j * DD + r * D + c] : (r == c ? 1.0 : 0.0);
-    __syncthreads();
-
+    const double* const ltj = p.Lt + (jok ? j : 0);        // lanes past the last column compute along on column 0
     const double nbeta = -p.beta, variance = p.variance;
     const int rows_here = (int)((p.row1 - i0) < (int64_t)TI ? (p.row1 - i0) : (int64_t)TI);
-    double* const stash0 = sStash + tid;   // entry k of row u of the pair: stash0[(u * NST + k) * TJ]
+    double* const stash0 = sStash + tid;   // entry k of row u of the trip: stash0[(u * NST + k) * TJ]
 
 #pragma unroll 1
     for (int hb = 0; hb < TI; hb += AI_TH) {
         if (hb >= rows_here) break;
 #pragma unroll 1
-        for (int r = hb; r < hb + AI_TH; r += 2) {
+        for (int r = hb; r < hb + AI_TH; r += AI_NR) {
             // lanes that have a pair to evaluate in row r / r + 1 (the rest computes along on benign data and is discarded)
-            bool act[2];
+            bool act[AI_NR];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < AI_NR; ++u) {
                 const int64_t gi = i0 + r + u;
                 act[u] = jok && (r + u < rows_here) && !(mirror && j > gi) && !(p.symmetric && gi == j);
             }
-            double val[2] = {0.0, 0.0};
+            double val[AI_NR] = {0.0, 0.0};
             if (__any_sync(0xffffffffu, act[0] || act[1])) {
                 // phase A (FP64, rolled over the two rows): congruence, Householder, trace normalisation -> stash
 #pragma unroll 1
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < AI_NR; ++u) {
                     double Mx[D][D], td[D], te[D];
-                    ai_congruence<D>(sW[r + u], B, Mx);
+                    ai_congruence_cols<D>(sW[r + u], ltj, p.ldt, Mx);
                     householder_tridiag<D>(Mx, td, te);
-                    double tr = 0.0;
+                    double t = 0.0;
 #pragma unroll
-                    for (int k = 0; k < D; ++k) tr += td[k];
-                    const double rt = rcp_nr2(tr);
+                    for (int k = 0; k < D; ++k) t += td[k];
+                    const double rt = rcp_nr2(t);
                     double* st = stash0 + (size_t)u * NST * TJ;
 #pragma unroll
                     for (int k = 0; k < D; ++k) st[k * TJ] = td[k] * rt;
 #pragma unroll
                     for (int k = 0; k < D - 1; ++k) st[(D + k) * TJ] = te[k] * rt;
-                    st[(2 * D - 1) * TJ] = tr;
+                    st[(2 * D - 1) * TJ] = t;
                 }
                 // phase B (FP32, both rows in packed halves): implicit-shift QL for the starting values
                 f32x2_t dp[D], ep[D];
@@ -399,9 +398,9 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_ai_gram_kernel(const
                 ep[D - 1] = 0ull;
                 ql_tri_eigvals_start_f32x2<D>(dp, ep);
                 // phase C (FP64, rolled): Newton refinement, validation, sum of squared logs
-                double arg[2];
+                double arg[AI_NR];
 #pragma unroll 1
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < AI_NR; ++u) {
                     const double* st = stash0 + (size_t)u * NST * TJ;
                     double ds[D], e2[D], ev[D];
                     float x0[D];
@@ -413,34 +412,34 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_ai_gram_kernel(const
 #pragma unroll
                     for (int k = 0; k < D - 1; ++k) { const double es = st[(D + k) * TJ]; e2[k] = es * es; }
                     e2[D - 1] = 0.0;
-                    const double tr = st[(2 * D - 1) * TJ];
+                    const double t = st[(2 * D - 1) * TJ];
                     bool fast = tridiag_newton_refine<D>(ds, e2, x0, ev);
-                    double emin = ev[0], emax = ev[0];
+                    // every eigenvalue above 1 % of the trace (the refinement is accurate to ~1e-16 of the TRACE; a smaller
+                    // eigenvalue needs the relative accuracy of the slow path); tested on the exponent words
+                    bool wide = false;
 #pragma unroll
-                    for (int k = 1; k < D; ++k) { emin = fmin(emin, ev[k]); emax = fmax(emax, ev[k]); }
-                    fast = fast && (emin > 0.02 * emax) && (tr > 1e-280) && (tr < 1e280);
+                    for (int k = 0; k < D; ++k) wide = wide || (__double2hiint(ev[k]) < 0x3f847ae1);
+                    fast = fast && !wide && (t > 1e-280) && (t < 1e280);
                     double s2 = 0.0;
                     if (fast) {
 #pragma unroll
                         for (int k = 0; k < D; ++k) {
-                            const double lg = log_pos_normal(ev[k] * tr);   // SPD_utils_tf.py:136-139
+                            const double lg = log_pos_normal(ev[k] * t);   // SPD_utils_tf.py:136-139
                             s2 = fma(lg, lg, s2);
                         }
                     } else if (u ? act[1] : act[0]) {
-                        SymPacked<D> Sp;
+                        TriPacked<D> Lp;
 #pragma unroll
-                        for (int rr = 0; rr < D; ++rr)
-#pragma unroll
-                            for (int cc = rr; cc < D; ++cc) Sp.v[rr * D - rr * (rr - 1) / 2 + (cc - rr)] = B[rr][cc];
-                        s2 = ai_sumlog2_slow<D>(sW[r + u], Sp);
+                        for (int idx = 0; idx < MP; ++idx) Lp.v[idx] = ltj[(int64_t)idx * p.ldt];
+                        s2 = ai_sumlog2_slow<D>(sW[r + u], Lp);
                     }
                     const double a = (KIND == GABO_SPD_AI_GAUSSIAN) ? nbeta * s2 : nbeta * sqrt(s2);   // kernels_spd_tf.py:241-248 / 396-400
                     if (u) arg[1] = a; else arg[0] = a;
                 }
-                exp_neg_scaled_fast_n<2>(arg, val, sTab, variance);
+                exp_neg_scaled_fast_n<AI_NR>(arg, val, sTab, variance);
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < AI_NR; ++u) {
                 const int64_t gi = i0 + r + u;
                 if (p.symmetric && gi == j) val[u] = variance;   // d_AI(X,X) = 0 exactly
                 const bool skip = mirror && (j > gi);
@@ -478,11 +477,8 @@ int launch_spd_ai(const SpdGramParams& p, dim3 grid, cudaStream_t stream) {
 template <int D>
 int launch_spd_gram(int kind, const SpdGramParams& p, cudaStream_t stream) {
     dim3 grid((unsigned)ceil_div64(p.n2, TJ), (unsigned)ceil_div64(p.row1 - p.row0, TI));
-    static const bool ai_v1 = (getenv("GABO_SPD_AI_V1") != nullptr);   // A/B switch for profiling: first-generation kernel
     int rc = 0;
-    if (kind == GABO_SPD_STEIN) spd_gram_kernel<D, GABO_SPD_STEIN><<<grid, TJ, 0, stream>>>(p);
-    else if (ai_v1 && kind == GABO_SPD_AI_GAUSSIAN) spd_gram_kernel<D, GABO_SPD_AI_GAUSSIAN><<<grid, TJ, 0, stream>>>(p);
-    else if (ai_v1) spd_gram_kernel<D, GABO_SPD_AI_LAPLACE><<<grid, TJ, 0, stream>>>(p);
+    if (kind == GABO_SPD_STEIN) spd_stein_gram_kernel<D><<<grid, TJ, 0, stream>>>(p);
     else if (kind == GABO_SPD_AI_GAUSSIAN) rc = launch_spd_ai<D, GABO_SPD_AI_GAUSSIAN>(p, grid, stream);
     else rc = launch_spd_ai<D, GABO_SPD_AI_LAPLACE>(p, grid, stream);
     if (rc) return rc;
@@ -500,20 +496,22 @@ __global__ void stein_kdiag_kernel(const double* __restrict__ logdet, int64_t n,
 }  // namespace gabo
 
 extern "C" int gabo_spd_prep_f64(const double* Xmandel, int64_t n, int64_t ldx, int d, double* out_S, double* out_W,
-                                 double* out_logdet, double* out_logm_mandel, int32_t* info, gabo_stream_t stream) {
+                                 double* out_logdet, double* out_logm_mandel, double* out_Lt, int64_t ldt, int32_t* info,
+                                 gabo_stream_t stream) {
     using namespace gabo;
     if (n < 0) return -2;
     if (d < 2 || d > 8) return -4;
     if (ldx < d * (d + 1) / 2) return -3;
+    if (out_Lt != nullptr && ldt < n) return -10;
     if (n == 0) return 0;
     if (Xmandel == nullptr) return -1;
-    if (info == nullptr) return -9;
+    if (info == nullptr) return -11;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int threads = 64;
     const unsigned grid = (unsigned)ceil_div64(n, threads);
 #define GABO_PREP_CASE(DV)                                                                                     \
     case DV:                                                                                                   \
-        spd_prep_kernel<DV><<<grid, threads, 0, s>>>(Xmandel, n, ldx, out_S, out_W, out_logdet, out_logm_mandel, info); \
+        spd_prep_kernel<DV><<<grid, threads, 0, s>>>(Xmandel, n, ldx, out_S, out_W, out_logdet, out_logm_mandel, out_Lt, ldt, info); \
         break;
     switch (d) {
         GABO_PREP_CASE(2) GABO_PREP_CASE(3) GABO_PREP_CASE(4) GABO_PREP_CASE(5)
@@ -525,34 +523,36 @@ extern "C" int gabo_spd_prep_f64(const double* Xmandel, int64_t n, int64_t ldx, 
 }
 
 extern "C" int gabo_spd_gram_f64(int kind, int d, const double* W1, const double* S1, const double* logdet1, int64_t n1,
-                                 const double* S2, const double* logdet2, int64_t n2, int symmetric, double beta,
-                                 double variance, double* K, int64_t ldk, int64_t row0, int64_t row1, int uplo,
-                                 gabo_stream_t stream) {
+                                 const double* S2, const double* L2t, int64_t ldt2, const double* logdet2, int64_t n2,
+                                 int symmetric, double beta, double variance, double* K, int64_t ldk, int64_t row0,
+                                 int64_t row1, int uplo, gabo_stream_t stream) {
     using namespace gabo;
     if (kind < GABO_SPD_AI_GAUSSIAN || kind > GABO_SPD_STEIN) return -1;
     if (d < 2 || d > 8) return -2;
     if (n1 < 0) return -6;
-    if (n2 < 0) return -9;
+    if (n2 < 0) return -11;
     if (kind == GABO_SPD_STEIN) {
         if (S1 == nullptr) return -4;
         if (logdet1 == nullptr) return -5;
-        if (logdet2 == nullptr) return -8;
-    } else if (W1 == nullptr) {
-        return -3;
+        if (S2 == nullptr) return -7;
+        if (logdet2 == nullptr) return -10;
+    } else {
+        if (W1 == nullptr) return -3;
+        if (L2t == nullptr) return -8;
+        if (ldt2 < n2) return -9;
     }
-    if (S2 == nullptr) return -7;
-    if (K == nullptr) return -13;
-    if (ldk < n2) return -14;
-    if (row0 < 0 || row0 > n1 || row0 % 32 != 0) return -15;
-    if (row1 < row0 || row1 > n1) return -16;
-    if (uplo < GABO_FULL || uplo > GABO_SYMM_MIRROR) return -17;
-    if (uplo != GABO_FULL && !symmetric) return -17;
-    if (uplo == GABO_SYMM_MIRROR && !(row0 == 0 && row1 == n1)) return -17;
-    if (symmetric && n1 != n2) return -10;
+    if (K == nullptr) return -15;
+    if (ldk < n2) return -16;
+    if (row0 < 0 || row0 > n1 || row0 % 32 != 0) return -17;
+    if (row1 < row0 || row1 > n1) return -18;
+    if (uplo < GABO_FULL || uplo > GABO_SYMM_MIRROR) return -19;
+    if (uplo != GABO_FULL && !symmetric) return -19;
+    if (uplo == GABO_SYMM_MIRROR && !(row0 == 0 && row1 == n1)) return -19;
+    if (symmetric && n1 != n2) return -12;
     if (row1 == row0 || n2 == 0) return 0;
     SpdGramParams p;
     p.R = (kind == GABO_SPD_STEIN) ? S1 : W1;
-    p.Rld = logdet1; p.Cm = S2; p.Cld = logdet2; p.K = K; p.ldk = ldk; p.n1 = n1; p.n2 = n2;
+    p.Rld = logdet1; p.Cm = S2; p.Lt = L2t; p.ldt = ldt2; p.Cld = logdet2; p.K = K; p.ldk = ldk; p.n1 = n1; p.n2 = n2;
     p.row0 = row0; p.row1 = row1; p.symmetric = symmetric ? 1 : 0; p.uplo = uplo; p.beta = beta; p.variance = variance;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (d) {

@@ -214,45 +214,6 @@ __device__ __forceinline__ void ql_tri_eigvals(T (&d)[D], T (&e)[D]) {
     }
 }
 
-// FP32 QL for STARTING VALUES only (tridiag_eigvals_mixed validates what it is given, so this routine may fail): the
-// sweep always runs over the whole block below l (no search for interior splits, no zero-rotation guard) and only e[l]
-// is tested, against 2^-11 of its neighbours (the eigenvalue error is quadratic in the neglected coupling: ~1e-6); at
-// most 6 iterations per eigenvalue.  About half the instructions of the
-// guarded version above.
-template <int D>
-__device__ __forceinline__ void ql_tri_eigvals_start_f32(float (&d)[D], float (&e)[D]) {
-#pragma unroll
-    for (int l = 0; l < D - 1; ++l) {
-        for (int iter = 0; iter < 6; ++iter) {
-            const int he = __float_as_int(e[l]) & 0x7fffffff;
-            const int ha = __float_as_int(d[l]) & 0x7fffffff, hb = __float_as_int(d[l + 1]) & 0x7fffffff;
-            if (he + (16 << 23) <= (ha > hb ? ha : hb)) break;
-            const float dl = 0.5f * (d[l + 1] - d[l]);
-            const float e2 = e[l] * e[l];
-            const float hh = fmaf(dl, dl, e2);
-            float g = d[D - 1] - d[l] + __fdividef(e2, dl + copysignf(hh * rsqrtf(hh), dl));
-            float s = 1.0f, c = 1.0f, p = 0.0f;
-#pragma unroll
-            for (int i = D - 2; i >= l; --i) {
-                const float f = s * e[i], b = c * e[i];
-                const float h2 = fmaf(f, f, g * g);
-                const float rr = rsqrtf(h2);
-                e[i + 1] = h2 * rr;
-                s = f * rr;
-                c = g * rr;
-                g = d[i + 1] - p;
-                const float r2 = fmaf(d[i] - g, s, 2.0f * c * b);
-                p = s * r2;
-                d[i + 1] = g + p;
-                g = fmaf(c, r2, -b);
-            }
-            d[l] -= p;
-            e[l] = g;
-            e[D - 1] = 0.0f;
-        }
-    }
-}
-
 // Eigenvalues of a symmetric D x D matrix (upper storage of A, destroyed), all in FP64 -- about 4x fewer FP64 pipe slots
 // than cyclic Jacobi for d = 6.  Callers fall back to Jacobi (relative accuracy) for ill-conditioned matrices.
 template <int D>
@@ -267,70 +228,6 @@ __device__ __forceinline__ double rcp_fast40(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     return fma(fma(-x, r, 1.0), r, r);
-}
-
-// Mixed-precision eigenvalues of the symmetric positive-definite tridiagonal (d, e) (both kept): the data-dependent QL
-// iteration runs in FP32 on the FP32 pipe -- it only has to land each eigenvalue inside the basin of its own root -- and
-// FP64 does two Newton steps per eigenvalue on the characteristic polynomial, evaluated with its derivative by the
-// three-term recurrence (no divisions, fixed trip count, three independent chains in flight).  Work is done on T / trace(T)
-// so that neither precision can over- or underflow.  Validation: every second Newton correction must be >= 1000x smaller
-// than the first (quadratic convergence -> remaining error <= 1e-6 of the second correction) and the eigenvalues must sum
-// to the trace to 1e-13 (two starts that fell to the same root would miss it by their gap).  Returns false when either
-// test fails (near-multiple eigenvalues, FP32 non-convergence, non-positive trace, NaN): the caller then runs the FP64 QL.
-template <int D>
-__device__ __forceinline__ bool tridiag_eigvals_mixed(const double (&d)[D], const double (&e)[D], double (&ev)[D]) {
-    double tr = 0.0;
-#pragma unroll
-    for (int k = 0; k < D; ++k) tr += d[k];
-    if (!(tr > 0.0) || !(tr < 1e300)) return false;
-    const double rt = rcp_nr2(tr);
-    double ds[D], e2[D];
-    float df[D], ef[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        ds[k] = d[k] * rt;
-        const double es = e[k] * rt;
-        e2[k] = es * es;
-        df[k] = (float)ds[k];
-        ef[k] = (float)es;
-    }
-    ql_tri_eigvals_start_f32<D>(df, ef);
-    bool ok = true;
-    double sum = 0.0;
-    constexpr int G = 3;   // eigenvalues refined together
-#pragma unroll
-    for (int g0 = 0; g0 < D; g0 += G) {
-        double x[G], d1[G];
-#pragma unroll
-        for (int u = 0; u < G; ++u) x[u] = (g0 + u < D) ? (double)df[g0 + u] : 0.0;
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            double p1[G], p2[G], q1[G], q2[G];   // p_k, p_{k-1} and derivatives
-#pragma unroll
-            for (int u = 0; u < G; ++u) { p2[u] = 1.0; q2[u] = 0.0; p1[u] = ds[0] - x[u]; q1[u] = -1.0; }
-#pragma unroll
-            for (int k = 1; k < D; ++k) {
-#pragma unroll
-                for (int u = 0; u < G; ++u) {
-                    const double t = ds[k] - x[u];
-                    const double pn = fma(t, p1[u], -e2[k - 1] * p2[u]);
-                    const double qn = fma(t, q1[u], fma(-e2[k - 1], q2[u], -p1[u]));
-                    p2[u] = p1[u]; q2[u] = q1[u]; p1[u] = pn; q1[u] = qn;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < G; ++u) {
-                const double dlt = p1[u] * rcp_fast40(q1[u]);
-                x[u] -= dlt;
-                if (it == 0) d1[u] = fabs(dlt);
-                else if (g0 + u < D) ok = ok && (fabs(dlt) <= fmax(1e-3 * d1[u], 1e-15));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < G; ++u)
-            if (g0 + u < D) { ev[g0 + u] = x[u] * tr; sum += x[u]; }
-    }
-    return ok && (fabs(sum - 1.0) <= 1e-13);
 }
 
 // ---- packed FP32 pairs (sm_100a FFMA2 / FADD2: two FP32 operations per issue slot) --------------------------------------
@@ -363,46 +260,92 @@ __device__ __forceinline__ bool f2_negligible16(f32x2_t e, f32x2_t da, f32x2_t d
     return !(f2_lo(t) > 0.0f || f2_hi(t) > 0.0f);
 }
 
-// ql_tri_eigvals_start_f32 for two tridiagonals at once (low / high halves).  Both run the same number of iterations (the
-// maximum of the two); an extra implicit-shift sweep on an already converged block is a valid similarity transform.
-template <int D>
-__device__ __forceinline__ void ql_tri_eigvals_start_f32x2(f32x2_t (&d)[D], f32x2_t (&e)[D]) {
+// One implicit-shift QL iteration (Wilkinson shift, sweep i = D-2 .. l) on the block [l, D-1] of two tridiagonals held in the
+// low / high halves of d, e.  FP32, STARTING VALUES only: no search for interior splits, no zero-rotation guard -- the FP64
+// refinement validates what it is given.
+template <int D, int L>
+__device__ __forceinline__ void ql_sweep_f32x2(f32x2_t (&d)[D], f32x2_t (&e)[D]) {
     const f32x2_t one = f2_pack(1.0f, 1.0f), half = f2_pack(0.5f, 0.5f);
+    const f32x2_t dl = f2_mul(f2_sub(d[L + 1], d[L]), half);
+    const f32x2_t e2 = f2_mul(e[L], e[L]);
+    const f32x2_t hh = f2_fma(dl, dl, e2);
+    const f32x2_t rt = f2_mul(hh, f2_rsq(hh));
+    const f32x2_t den = f2_add(dl, f2_copysign(rt, dl));
+    f32x2_t g = f2_add(f2_sub(d[D - 1], d[L]), f2_mul(e2, f2_rcp(den)));
+    f32x2_t s = one, c = one, p = 0ull;
 #pragma unroll
-    for (int l = 0; l < D - 1; ++l) {
-#pragma unroll 1   // rolled: six unrolled copies per l made a 70 KB loop body, beyond the 32 KB L1.5 instruction cache
-        for (int iter = 0; iter < 6; ++iter) {
-            if (f2_negligible16(e[l], d[l], d[l + 1])) break;
-            const f32x2_t dl = f2_mul(f2_sub(d[l + 1], d[l]), half);
-            const f32x2_t e2 = f2_mul(e[l], e[l]);
-            const f32x2_t hh = f2_fma(dl, dl, e2);
-            const f32x2_t rt = f2_mul(hh, f2_rsq(hh));
-            const f32x2_t den = f2_add(dl, f2_copysign(rt, dl));
-            f32x2_t g = f2_add(f2_sub(d[D - 1], d[l]), f2_mul(e2, f2_rcp(den)));
-            f32x2_t s = one, c = one, p = 0ull;
-#pragma unroll
-            for (int i = D - 2; i >= l; --i) {
-                const f32x2_t f = f2_mul(s, e[i]), b = f2_mul(c, e[i]);
-                const f32x2_t h2 = f2_fma(f, f, f2_mul(g, g));
-                const f32x2_t rr = f2_rsq(h2);
-                e[i + 1] = f2_mul(h2, rr);
-                s = f2_mul(f, rr);
-                c = f2_mul(g, rr);
-                g = f2_sub(d[i + 1], p);
-                const f32x2_t r2 = f2_fma(f2_sub(d[i], g), s, f2_mul(f2_add(c, c), b));
-                p = f2_mul(s, r2);
-                d[i + 1] = f2_add(g, p);
-                g = f2_sub(f2_mul(c, r2), b);
-            }
-            d[l] = f2_sub(d[l], p);
-            e[l] = g;
-            e[D - 1] = 0ull;
-        }
+    for (int i = D - 2; i >= L; --i) {
+        const f32x2_t f = f2_mul(s, e[i]), b = f2_mul(c, e[i]);
+        const f32x2_t h2 = f2_fma(f, f, f2_mul(g, g));
+        const f32x2_t rr = f2_rsq(h2);
+        e[i + 1] = f2_mul(h2, rr);
+        s = f2_mul(f, rr);
+        c = f2_mul(g, rr);
+        g = f2_sub(d[i + 1], p);
+        const f32x2_t r2 = f2_fma(f2_sub(d[i], g), s, f2_mul(f2_add(c, c), b));
+        p = f2_mul(s, r2);
+        d[i + 1] = f2_add(g, p);
+        g = f2_sub(f2_mul(c, r2), b);
     }
+    d[L] = f2_sub(d[L], p);
+    e[L] = g;
+    e[D - 1] = 0ull;
 }
 
-// The FP64 half of tridiag_eigvals_mixed on its own: two Newton steps per eigenvalue of the trace-normalised tridiagonal
-// (ds diagonal, e2 squared off-diagonals) from the starting values x0, with the same validation.  ev = eigenvalues / trace.
+template <int D, int L>
+struct QlLevels {
+    // one packed pair
+    static __device__ __forceinline__ void run(f32x2_t (&da)[D], f32x2_t (&ea)[D]) {
+#pragma unroll 1   // rolled: six unrolled copies per level made a 70 KB loop body, beyond the 32 KB L1.5 instruction cache
+        for (int iter = 0; iter < 6; ++iter) {
+            if (f2_negligible16(ea[L], da[L], da[L + 1])) break;
+            ql_sweep_f32x2<D, L>(da, ea);
+        }
+        QlLevels<D, L + 1>::run(da, ea);
+    }
+    // two packed pairs as two independent dependency chains in one instruction stream
+    static __device__ __forceinline__ void run(f32x2_t (&da)[D], f32x2_t (&ea)[D], f32x2_t (&db)[D], f32x2_t (&eb)[D]) {
+#pragma unroll 1
+        for (int iter = 0; iter < 6; ++iter) {
+            if (f2_negligible16(ea[L], da[L], da[L + 1]) && f2_negligible16(eb[L], db[L], db[L + 1])) break;
+            ql_sweep_f32x2<D, L>(da, ea);
+            ql_sweep_f32x2<D, L>(db, eb);
+        }
+        QlLevels<D, L + 1>::run(da, ea, db, eb);
+    }
+};
+template <int D>
+struct QlLevels<D, D - 1> {
+    static __device__ __forceinline__ void run(f32x2_t (&)[D], f32x2_t (&)[D]) {}
+    static __device__ __forceinline__ void run(f32x2_t (&)[D], f32x2_t (&)[D], f32x2_t (&)[D], f32x2_t (&)[D]) {}
+};
+
+// Eigenvalue STARTS of two tridiagonals (low / high halves), levels l = 0 .. D-2, at most 6 iterations per level.  Both
+// halves run the same number of iterations (the maximum of the two); an extra implicit-shift sweep on an already converged
+// block is a valid similarity transform.
+template <int D>
+__device__ __forceinline__ void ql_tri_eigvals_start_f32x2(f32x2_t (&d)[D], f32x2_t (&e)[D]) {
+    QlLevels<D, 0>::run(d, e);
+}
+// The same for FOUR tridiagonals as two packed pairs that advance together (twice the instruction-level parallelism, twice
+// the code; measured no faster than one pair per trip at four CTAs per SM, kept for reference).
+template <int D>
+__device__ __forceinline__ void ql_tri_eigvals_start_f32x2_dual(f32x2_t (&da)[D], f32x2_t (&ea)[D], f32x2_t (&db)[D],
+                                                                f32x2_t (&eb)[D]) {
+    QlLevels<D, 0>::run(da, ea, db, eb);
+}
+
+// Mixed-precision eigenvalues, FP64 half: refinement of the starting values x0 on the characteristic polynomial of the
+// trace-normalised tridiagonal (ds diagonal, e2 squared off-diagonals), evaluated by the three-term recurrence (no
+// divisions, fixed trip count, three independent chains in flight).  Step 1 is a Newton step (p and p'); step 2 re-evaluates
+// p only and reuses 1/p' of step 1 (the chord step: 3 instead of 5 FP64 operations per recurrence row and no second
+// reciprocal).  With e0 the error of the start and kappa = p''/p', the corrections are dlt1 ~ e0, dlt2 ~ kappa e0^2 / 2 and
+// the error left after step 2 is kappa^2 e0^3 / 2 ~ 2 dlt2^2 / dlt1, which is what gets validated: every eigenvalue must
+// satisfy dlt2^2 <= 1e-15 |dlt1| (error <= 2e-15 of the trace), and the eigenvalues must sum to the trace to 1e-13 (two
+// starts that fell to the same root miss it by their gap).  Returns false otherwise (near-multiple eigenvalues, FP32
+// non-convergence, NaN): the caller then takes the all-FP64 slow path.  ev = eigenvalues / trace.
+// Measured on 4e5 pairs of the C5 workload (tools/spd_newton_emul.py): 6e-5 of the pairs fail the validation; the
+// accepted eigenvalues are within 2e-14 relative of LAPACK's.
 template <int D>
 __device__ __forceinline__ bool tridiag_newton_refine(const double (&ds)[D], const double (&e2)[D], const float (&x0)[D],
                                                       double (&ev)[D]) {
@@ -411,11 +354,10 @@ __device__ __forceinline__ bool tridiag_newton_refine(const double (&ds)[D], con
     constexpr int G = 3;
 #pragma unroll
     for (int g0 = 0; g0 < D; g0 += G) {
-        double x[G], d1[G];
+        double x[G], d1[G], rq[G];
 #pragma unroll
-        for (int u = 0; u < G; ++u) { x[u] = (g0 + u < D) ? (double)x0[g0 + u] : 0.0; d1[u] = 0.0; }
-#pragma unroll 1   // rolled to keep the caller's loop body inside the instruction cache
-        for (int it = 0; it < 2; ++it) {
+        for (int u = 0; u < G; ++u) x[u] = (g0 + u < D) ? (double)x0[g0 + u] : 0.0;
+        {   // step 1: p and p'
             double p1[G], p2[G], q1[G], q2[G];
 #pragma unroll
             for (int u = 0; u < G; ++u) { p2[u] = 1.0; q2[u] = 0.0; p1[u] = ds[0] - x[u]; q1[u] = -1.0; }
@@ -431,10 +373,30 @@ __device__ __forceinline__ bool tridiag_newton_refine(const double (&ds)[D], con
             }
 #pragma unroll
             for (int u = 0; u < G; ++u) {
-                const double dlt = p1[u] * rcp_fast40(q1[u]);
+                rq[u] = rcp_fast40(q1[u]);
+                const double dlt = p1[u] * rq[u];
                 x[u] -= dlt;
-                if (it == 0) d1[u] = fabs(dlt);
-                else if (g0 + u < D) ok = ok && (fabs(dlt) <= fmax(1e-3 * d1[u], 1e-15));
+                d1[u] = fabs(dlt);
+            }
+        }
+        {   // step 2: p only, chord step with the derivative of step 1
+            double p1[G], p2[G];
+#pragma unroll
+            for (int u = 0; u < G; ++u) { p2[u] = 1.0; p1[u] = ds[0] - x[u]; }
+#pragma unroll
+            for (int k = 1; k < D; ++k) {
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    const double t = ds[k] - x[u];
+                    const double pn = fma(t, p1[u], -e2[k - 1] * p2[u]);
+                    p2[u] = p1[u]; p1[u] = pn;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                const double dlt = p1[u] * rq[u];
+                x[u] -= dlt;
+                if (g0 + u < D) ok = ok && (dlt * dlt <= 1e-15 * d1[u]);
             }
         }
 #pragma unroll

@@ -109,24 +109,37 @@ class SpdPrep:
     logdet: Optional[torch.Tensor]   # [n]
     logm: Optional[torch.Tensor]     # [n, m]    Mandel(logm S)
     info: torch.Tensor               # [n] int32
+    Lt: Optional[torch.Tensor] = None   # [m, ldt] packed lower Cholesky factors, transposed (column operand of the AI kernel)
+
+    def check(self) -> 'SpdPrep':
+        """Raise ValueError naming the first input matrix that is not SPD (one host sync)."""
+        if self.n and bool(self.info.any().item()):
+            bad = int(torch.nonzero(self.info)[0].item())
+            raise ValueError(f'input matrix {bad} is not symmetric positive definite '
+                             f'(Cholesky pivot {int(self.info[bad].item())} is not positive)')
+        return self
 
 
-def spd_prep(Xm: torch.Tensor, d: int, want_S=True, want_W=True, want_logdet=True, want_logm=False) -> SpdPrep:
+def spd_prep(Xm: torch.Tensor, d: int, want_S=True, want_W=True, want_logdet=True, want_logm=False, want_Lt=None) -> SpdPrep:
     Xm = _rowmajor2d(_req(Xm, 'Xmandel'))
     n, m = int(Xm.shape[0]), int(Xm.shape[1])
     if m != d * (d + 1) // 2:
         raise ValueError(f'Mandel length {m} does not match matrix_dim {d}')
+    if want_Lt is None:
+        want_Lt = want_W                      # the affine-invariant kinds need both halves of the pair operand
     dev = Xm.device
     S = torch.empty((n, d * d), dtype=torch.float64, device=dev) if want_S else None
     W = torch.empty((n, d * d), dtype=torch.float64, device=dev) if want_W else None
     ld = torch.empty((n,), dtype=torch.float64, device=dev) if want_logdet else None
     lm = torch.empty((n, m), dtype=torch.float64, device=dev) if want_logm else None
+    ldt = ((n + 31) // 32) * 32               # 256 B aligned rows
+    Lt = torch.empty((m, max(ldt, 1)), dtype=torch.float64, device=dev) if want_Lt else None
     info = torch.zeros((max(n, 1),), dtype=torch.int32, device=dev)
     ptr = lambda t: t.data_ptr() if t is not None else None
-    st = _lib.lib().gabo_spd_prep_f64(Xm.data_ptr(), n, _ld(Xm), d, ptr(S), ptr(W), ptr(ld), ptr(lm),
+    st = _lib.lib().gabo_spd_prep_f64(Xm.data_ptr(), n, _ld(Xm), d, ptr(S), ptr(W), ptr(ld), ptr(lm), ptr(Lt), max(ldt, 1),
                                       info.data_ptr(), _stream())
     _lib.check('gabo_spd_prep_f64', st)
-    return SpdPrep(d, n, S, W, ld, lm, info[:n])
+    return SpdPrep(d, n, S, W, ld, lm, info[:n], Lt)
 
 
 def spd_gram(kind: int, p1: SpdPrep, p2: Optional[SpdPrep] = None, beta: float = 1.0, variance: float = 1.0,
@@ -144,8 +157,11 @@ def spd_gram(kind: int, p1: SpdPrep, p2: Optional[SpdPrep] = None, beta: float =
     if out is None:
         out = torch.empty((rows, n2), dtype=torch.float64, device=dev)
     ptr = lambda t: t.data_ptr() if t is not None else None
+    if kind != SPD_STEIN and (p1.W is None or p2.Lt is None):
+        raise ValueError('the affine-invariant kinds need W of the row points and Lt of the column points (spd_prep want_W / want_Lt)')
     st = _lib.lib().gabo_spd_gram_f64(int(kind), p1.d, ptr(p1.W), ptr(p1.S), ptr(p1.logdet), n1,
-                                      ptr(p2.S), ptr(p2.logdet), n2, 1 if symmetric else 0,
+                                      ptr(p2.S), ptr(p2.Lt), int(p2.Lt.stride(0)) if p2.Lt is not None else 0,
+                                      ptr(p2.logdet), n2, 1 if symmetric else 0,
                                       float(beta), float(variance), out.data_ptr(),
                                       _ld(out) if rows > 1 else max(n2, int(out.stride(0))),
                                       int(row0), int(row1), _UPLO[uplo], _stream())

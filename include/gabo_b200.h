@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GABO_ABI_VERSION 1
+#define GABO_ABI_VERSION 2
 #define GABO_ERR_CUDA (-1000)
 #define GABO_MAX_PEERS 8      /* ranks of one NVSwitch node that exchange through peer memory */
 
@@ -92,26 +92,31 @@ int gabo_kdiag_const_f64(int64_t n, double variance, double* out, gabo_stream_t 
  * Replaces vector_to_symmetric_matrix_tf (SPD_utils_tf.py:11-65) and hoists the per-PAIR inverse / sqrtm /
  * logm of the reference (SPD_utils_tf.py:129, kernels_spd_tf.py:634) to once per point:
  *   S[i]      d x d symmetric matrix of Mandel row i                    (out_S, [n,d*d], may be NULL)
- *   W[i]      inverse of the lower Cholesky factor of S[i]              (out_W, [n,d*d], may be NULL)
+ *   W[i]      inverse of the lower Cholesky factor L[i] of S[i]         (out_W, [n,d*d], may be NULL)
  *   logdet[i] log det S[i]                                              (out_logdet, [n], may be NULL)
  *   logm[i]   Mandel vector of the matrix logarithm (Jacobi eigen)      (out_logm_mandel, [n,m], may be NULL)
+ *   Lt        the factors L[i], packed lower (entry (a,k), k <= a, at a(a+1)/2 + k) and TRANSPOSED:
+ *             Lt[(a(a+1)/2 + k)*ldt + i], ldt >= n -- the column operand of the affine-invariant pair kernel, laid
+ *             out so that a warp reads one entry of 32 consecutive points in one 256 B request (out_Lt, may be NULL)
  *   info[i]   0, or k>0 if the k-th Cholesky pivot of S[i] is not positive (outputs for i are NaN)
  * 2 <= d <= 8. */
 int gabo_spd_prep_f64(const double* Xmandel, int64_t n, int64_t ldx, int d,
                       double* out_S, double* out_W, double* out_logdet, double* out_logm_mandel,
-                      int32_t* info, gabo_stream_t stream);
+                      double* out_Lt, int64_t ldt, int32_t* info, gabo_stream_t stream);
 
 /* ---- SPD pair Gram -----------------------------------------------------------------------------------
  * Affine-invariant kinds replace affine_invariant_distance_tf (SPD_utils_tf.py:95-139):
- *   d_AI(i,j)^2 = sum_k log^2 lambda_k( W1[i] S2[j] W1[i]^T ), eigenvalues by cyclic Jacobi in registers.
+ *   d_AI(i,j)^2 = sum_k log^2 lambda_k( W1[i] S2[j] W1[i]^T ), formed as (W1[i] L2[j])(W1[i] L2[j])^T from the triangular
+ *   factors; eigenvalues by Householder + FP32 QL starts + validated FP64 Newton refinement (FP64 QL / cyclic Jacobi
+ *   when the refinement does not validate or the spectrum is wide).
  * Stein replaces kernels_spd_tf.py:98-112: exp(beta*(logdet1[i]+logdet2[j]-logdet((S1[i]+S2[j])/2))).
- * W1 / S1 / logdet1 describe X (rows), S2 / logdet2 describe X2 (columns); `symmetric` != 0 states that
+ * W1 / S1 / logdet1 describe X (rows), S2 / L2t / logdet2 describe X2 (columns); `symmetric` != 0 states that
  * both describe the same point set (enables uplo modes and the exact diagonal for the AI kinds).
- * Unused inputs for a kind may be NULL (AI: S1, logdet1, logdet2; Stein: W1). */
+ * Unused inputs for a kind may be NULL (AI: S1, S2, logdet1, logdet2; Stein: W1, L2t). */
 int gabo_spd_gram_f64(int kind, int d,
                       const double* W1, const double* S1, const double* logdet1, int64_t n1,
-                      const double* S2, const double* logdet2, int64_t n2, int symmetric,
-                      double beta, double variance,
+                      const double* S2, const double* L2t, int64_t ldt2, const double* logdet2, int64_t n2,
+                      int symmetric, double beta, double variance,
                       double* K, int64_t ldk, int64_t row0, int64_t row1, int uplo,
                       gabo_stream_t stream);
 /* SpdSteinGaussianKernel.Kdiag = diag_part(K(X)) (kernels_spd_tf.py:129) = variance*exp(beta*logdet[i]). */
