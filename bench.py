@@ -10,17 +10,26 @@ A step is one pass of the hot path over one synthetic batch (BASELINE.json confi
     potrf  in-place FP64 Cholesky of the leading 32,768 block of K + 1e-2 I            (the metric's Cholesky)
     solve  alpha = L^-1 y, log marginal likelihood (one scalar)
 `value` = Gram entries per second over the gram phase (max over ranks); `ms_per_step` covers the whole step and
-`phases_ms` / `cholesky` split it.  Inputs are synthetic (seeded), already resident in HBM for `value`; `e2e` repeats
-the steps through the public kernel-class / GPR API from pinned HOST buffers with the host<->device copies inside the
-timed region.  The working set (34 GB of K) is >> the 126 MB L2, so no explicit flush is needed between iterations.
+`phases_ms` / `cholesky` split it; `step_entries_per_s` is the whole-step rate.  Inputs are synthetic (seeded), already
+resident in HBM for `value`.  `e2e` repeats the steps from pinned HOST buffers with the host<->device copies inside the timed
+region, at N = 1 through the public classes -- ``SphereGaussianKernel.K`` for the Gram, ``GPR.compute_log_likelihood`` for
+Cholesky + solve + likelihood (GPR forms its own lower Gram of the 32,768 training points, which is part of its time) -- and at
+N > 1 through ``gaboflow_b200.dist``.  The working set (34 GB of K) is >> the 126 MB L2: no flush needed between iterations.
 
-N > 1 (one rank per GPU under torchrun, strong scaling: the same matrix on more GPUs).  K lives in 512-row panels, 1-D
-block-cyclic over the ranks.  gram: lower tiles by the row owner; upper tiles either stored into the owning GPU over
-NVLink from inside the kernel or recomputed by their row owner (hashed split, dist.default_recompute_frac256); completion
-is a stream-ordered flag handshake.  potrf: right-looking over panels with one panel of look-ahead; the block column
-reaches every rank by NVLink stores from the row-solve kernel, the diagonal block by copy engines, ordering by
-cuStreamWaitValue32 flags (no collective inside the loop; GABO_DIST_P2P=0 selects the NCCL broadcast + all-gather
-version).  solve / loglik: 512-vector broadcast per panel, one all-reduce.  Times are CUDA events, max over ranks.
+After the timed sphere steps the same process runs BASELINE.json configs[4] (`spd` in the JSON line): the SPD affine-invariant
+Gaussian Gram at N = 16,384 on S^6_++ (timed, roofline against the declared 2532 flop per pair), the Stein and Log-Euclidean
+Grams, and the Cholesky + log-likelihood of K_AI + 1e-2 I; and it CHECKS its own results outside the timed regions (`checks`):
+the Cholesky info word, sampled Gram rows of every kernel against the NumPy oracle, residuals of the factor and of the solve
+on sampled tiles, and the log-likelihood of a 4096-point sub-problem against the oracle.
+
+N > 1 (one rank per GPU under torchrun, strong scaling: the same matrices on more GPUs).  K lives in 512-row panels, 1-D
+block-cyclic over the ranks.  sphere gram: lower tiles by the row owner; upper tiles either stored into the owning GPU over
+NVLink from inside the kernel or recomputed by their row owner (hashed split, dist.default_recompute_frac256).  SPD gram: the
+lower 32 x 128 blocks are dealt round-robin to the ranks and stored, with their mirror images, straight into the owners' HBM.
+Completion is a stream-ordered flag handshake.  potrf: right-looking over panels with one panel of look-ahead; the block
+column reaches every rank by NVLink stores from the row-solve kernel, the diagonal block by copy engines, ordering by
+cuStreamWaitValue32 flags (no collective inside the loop; GABO_DIST_P2P=0 selects the NCCL broadcast + all-gather version).
+solve / loglik: 512-vector exchange per panel, one all-reduce.  Times are CUDA events, max over ranks.
 """
 from __future__ import annotations
 
@@ -43,6 +52,10 @@ DIM = 51
 FP64_PEAK_TFLOPS = 37.2                # measured on this pool: tools/fp64_probe.cu -> profiles/r01_fp64_probe.txt (DMMA.8x8x4)
 GEMM_DRAM_TRAFFIC_BYTES = 9.41e9        # ncu: dram__bytes_read 5.285 GB + write 4.128 GB for the m=32256, k=512 trailing update
 F_TR = 100                             # declared transcendental flops per sphere Gram entry
+# BASELINE.json configs[4]: N = 16,384 matrices on S^6_++, eigenvalues U[0.5, 2], seed 20242
+SPD_N, SPD_D, SPD_SEED = 16384, 6, 20242
+SPD_BETA_AI, SPD_BETA_LE, SPD_BETA_STEIN = 1.0, 1.0, 3.0
+F_PAIR = 2532                          # declared flops per affine-invariant pair at d = 6
 
 
 def synth_sphere(n, dim, seed):
@@ -98,18 +111,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(n_gram, n_chol_sample=8192, gram_rows=2048, n_chol_metric=32768):
-    """The reference math on the host cores (NumPy/OpenBLAS oracle port), bounded sample of the bench workload."""
-    from oracle import gabo_oracle as orc   # the ONE place bench.py executes oracle/: the CPU baseline
-    # all the host threads the BLAS can use (torchrun exports OMP_NUM_THREADS=1, which would make this arm single-threaded)
+def _host_threads():
+    """All the host threads the BLAS can use (torchrun exports OMP_NUM_THREADS=1, which would make the CPU arm single-threaded)."""
     want = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     try:
         from threadpoolctl import threadpool_info, threadpool_limits
-        _limit = threadpool_limits(limits=want)
+        limit = threadpool_limits(limits=want)
         cores = max([p.get('num_threads', 1) for p in threadpool_info()] + [1])
     except Exception:
-        _limit = None
-        cores = 1
+        limit, cores = None, 1
+    return limit, int(cores)
+
+
+def cpu_reference_sample(n_gram, n_chol_sample=8192, gram_rows=2048, n_chol_metric=32768, spd_rows=48):
+    """The reference math on the host cores (NumPy/OpenBLAS oracle port), bounded sample of the bench workload."""
+    from oracle import gabo_oracle as orc   # the ONE place bench.py executes oracle/ as the thing measured: the CPU baseline
+    _limit, cores = _host_threads()
     X = synth_sphere(n_gram, DIM, SEED_X)
     rows = min(gram_rows, n_gram)
     t0 = time.perf_counter()
@@ -123,26 +140,42 @@ def cpu_reference_sample(n_gram, n_chol_sample=8192, gram_rows=2048, n_chol_metr
     ll = orc.gp_loglik(Kc, y, SIGMA2)
     t_chol = time.perf_counter() - t0
     gflops = nc ** 3 / 3 / t_chol * 1e-9
-    return {
-        'value': rows * n_gram / t_gram, 'unit': 'entries/s', 'cores': int(cores), 'kind': 'port',
+    gram_rate = rows * n_gram / t_gram
+    chol_full = t_chol * (n_chol_metric / nc) ** 3
+    step_s = n_gram * n_gram / gram_rate + chol_full
+    out = {
+        'value': gram_rate, 'unit': 'entries/s', 'cores': int(cores), 'kind': 'port',
         'sample': f'gram rows [0,{rows}) x {n_gram} cols of the same workload in {t_gram:.2f} s; Cholesky+solve+loglik at N={nc} '
                   f'in {t_chol:.2f} s (NumPy/SciPy OpenBLAS oracle port; TF1/GPflow 0.5 not installable)',
         'cholesky': {'n': nc, 'seconds': t_chol, 'gflops': gflops,
-                     'extrapolated_n%d_s' % n_chol_metric: t_chol * (n_chol_metric / nc) ** 3},
+                     'extrapolated_n%d_s' % n_chol_metric: chol_full},
+        'step_seconds_extrapolated': step_s,
+        'step_entries_per_s': n_gram * n_gram / step_s,
+        'step_note': f'whole step on the host cores = full Gram at the sampled rate ({n_gram * n_gram / gram_rate:.1f} s) + Cholesky '
+                     f'extrapolated with N^3 from N={nc} ({chol_full:.1f} s)',
         'loglik_sample': ll,
     }
+    if spd_rows > 0:
+        Xm = orc.synth_spd_mandel(SPD_N, SPD_D, seed=SPD_SEED)
+        t0 = time.perf_counter()
+        orc.spd_ai_gaussian_K(Xm[:spd_rows], Xm, beta=SPD_BETA_AI)
+        t_spd = time.perf_counter() - t0
+        out['spd'] = {'ai_pairs_per_s': spd_rows * SPD_N / t_spd, 'sample': f'{spd_rows} rows x {SPD_N} cols of the affine-invariant '
+                      f'Gram (batched eigvalsh of W_i S_j W_i^T) in {t_spd:.2f} s',
+                      'full_gram_seconds_extrapolated': SPD_N * (SPD_N + 1) / 2 / (spd_rows * SPD_N / t_spd)}
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
-    n_gram, n_chol = args.n_gram, args.n_chol
+    n_gram, n_chol = args.n_gram, min(args.n_chol, args.n_gram)
     times, last = [], None
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         last = cpu_reference_sample(n_gram, n_chol_sample=min(args.ref_chol_n, n_chol), gram_rows=args.ref_gram_rows,
-                                    n_chol_metric=n_chol)
+                                    n_chol_metric=n_chol, spd_rows=args.ref_spd_rows if it == args.warmup + args.steps - 1 else 0)
         if it >= args.warmup:
             times.append((time.perf_counter() - t0, last))
     val = float(np.mean([t[1]['value'] for t in times]))
@@ -152,13 +185,16 @@ def run_reference(args):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean([t[0] for t in times])) * 1e3,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'sphere Gaussian Gram N={n_gram} on S^50 (D=51) + FP64 Cholesky of K+1e-2 I at N={n_chol} + solve + loglik',
-                   'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2,
+                   'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2, 'seeds': [SEED_X, SEED_Y],
                    'note': 'each step is a bounded sample of the workload on the host CPU cores (see cpu_baseline.sample)'},
         'cholesky': chol,
-        'cpu_baseline': {k: last[k] for k in ('unit', 'cores', 'kind', 'sample')} | {'value': val},
+        'step_entries_per_s': last['step_entries_per_s'], 'step_seconds_extrapolated': last['step_seconds_extrapolated'],
+        'cpu_baseline': {k: last[k] for k in ('unit', 'cores', 'kind', 'sample', 'step_seconds_extrapolated', 'step_note')} | {'value': val},
         'e2e': {'value': val, 'unit': 'entries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+    if 'spd' in last:
+        line['spd'] = last['spd']
     print(json.dumps(line), flush=True)
     return 0
 
@@ -167,7 +203,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from gaboflow_b200 import GPR, SphereGaussianKernel, ops, _lib
+    from gaboflow_b200 import GPR, SphereGaussianKernel, SpdAffineInvariantGaussianKernel, ops, _lib
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -186,19 +222,17 @@ def run_ours(args):
     lib = _lib.lib()
 
     N, NC = args.n_gram, min(args.n_chol, args.n_gram)
-    Xh = torch.from_numpy(synth_sphere(N, DIM, SEED_X)).pin_memory()
-    yh = torch.from_numpy(np.random.default_rng(SEED_Y).standard_normal((N, 1))).pin_memory()
+    Xnp = synth_sphere(N, DIM, SEED_X)
+    ynp = np.random.default_rng(SEED_Y).standard_normal((N, 1))
+    Xh = torch.from_numpy(Xnp).pin_memory()
+    yh = torch.from_numpy(ynp).pin_memory()
     X = Xh.to(dev)
     y = yh.to(dev)
     kern = SphereGaussianKernel(DIM, range(DIM), beta_min=0.0, beta=BETA, variance=VARIANCE)
 
-    # N = 1: one GPU holds all of K; lower tiles are computed once and mirror-stored.
-    # N > 1: K is distributed by 512-row panels, 1-D block-cyclic (gaboflow_b200/dist.py): every rank generates the full
-    #        rows of its panels with no exchange (X is replicated), then the leading NC x NC block is factored by the
-    #        distributed right-looking Cholesky (diagonal-block broadcast + block-column all-gather over NCCL).
     from gaboflow_b200.dist import (BlockCyclic, PeerBuffers, gram_block_cyclic_mirrored, potrf_block_cyclic_,
                                     PanelExchange, potrf_block_cyclic_p2p_, default_recompute_frac256,
-                                    solve_lower_block_cyclic_, gp_loglik_block_cyclic)
+                                    solve_lower_block_cyclic_, gp_loglik_block_cyclic, spd_gram_block_cyclic)
     PANEL = 512
     lay = BlockCyclic(N, PANEL, world, rank)
     rows = lay.local_rows
@@ -220,11 +254,12 @@ def run_ours(args):
     ws = torch.empty(int(max(lib.gabo_points_gram_workspace_bytes(N, N, DIM), lib.gabo_points_gram_cyclic_workspace_bytes(N, DIM))),
                      dtype=torch.uint8, device=dev)
     grow = lay.global_rows()
-    sel_fac = (grow < NC).to(dev)
     y_rows = grow[grow < NC].to(dev)
     V = torch.empty((int(y_rows.numel()) if world > 1 else NC, 1), dtype=torch.float64, device=dev)
     ll_val_host = [None]
     ll_dev = torch.zeros((1,), dtype=torch.float64, device=dev)
+    info_last = [None]
+    winv_last = [None]
 
     def barrier():
         if world > 1:
@@ -234,6 +269,7 @@ def run_ours(args):
     dist_phases = [None]
 
     def step(events=None, from_host=False):
+        """One pass of the hot path at the operator level (device-resident inputs unless from_host)."""
         nonlocal ll_dev
         Xd, yd = X, y
         if from_host:
@@ -257,7 +293,7 @@ def run_ours(args):
             events[1].record()
         if world == 1:
             A = K[:NC, :NC]                       # leading block, ld = N, factored in place (K is regenerated next step)
-            ops.potrf_(A, SIGMA2, check=False)
+            info_last[0] = ops.potrf_(A, SIGMA2, check=False)
             if events is not None:
                 events[2].record()
             V.copy_(yd[:NC])
@@ -270,10 +306,12 @@ def run_ours(args):
         else:
             winv = {}
             if xch is not None and dist_phases[0] is None:
-                potrf_block_cyclic_p2p_(K, lay, SIGMA2, xch, n_factor=NC, winv_store=winv)
+                info_last[0] = potrf_block_cyclic_p2p_(K, lay, SIGMA2, xch, n_factor=NC, winv_store=winv)
             else:
-                potrf_block_cyclic_(K, lay, SIGMA2, n_factor=NC, lookahead=os.environ.get('GABO_DIST_LOOKAHEAD', '0') == '1',
-                                    winv_store=winv, phase_ms=dist_phases[0])
+                info_last[0] = potrf_block_cyclic_(K, lay, SIGMA2, n_factor=NC,
+                                                   lookahead=os.environ.get('GABO_DIST_LOOKAHEAD', '0') == '1',
+                                                   winv_store=winv, phase_ms=dist_phases[0])
+            winv_last[0] = winv
             if events is not None:
                 events[2].record()
             V.copy_(yd[y_rows])
@@ -309,37 +347,124 @@ def run_ours(args):
         t_end.record()
         barrier()
     launches = lib.gabo_launch_count() - launches0
-    kern = None
+    kprof = None
     if world == 1:
         import ctypes as C
         kn, kms, kfl, kmx, kmxf = C.c_int64(), C.c_double(), C.c_double(), C.c_double(), C.c_double()
         lib.gabo_profile_trailing_read(C.byref(kn), C.byref(kms), C.byref(kfl), C.byref(kmx), C.byref(kmxf))
         lib.gabo_profile_trailing_updates(0)
         if kn.value > 0 and kms.value > 0:
-            kern = {'launches': kn.value, 'total_ms': kms.value, 'tflops_avg': kfl.value / kms.value * 1e-9,
-                    'largest_ms': kmx.value, 'largest_tflops': kmxf.value / kmx.value * 1e-9 if kmx.value > 0 else None,
-                    'flops_per_launch_avg': kfl.value / kn.value, 'ms_per_launch_avg': kms.value / kn.value}
+            kprof = {'launches': kn.value, 'total_ms': kms.value, 'tflops_avg': kfl.value / kms.value * 1e-9,
+                     'largest_ms': kmx.value, 'largest_tflops': kmxf.value / kmx.value * 1e-9 if kmx.value > 0 else None,
+                     'flops_per_launch_avg': kfl.value / kn.value, 'ms_per_launch_avg': kms.value / kn.value}
     total_ms = t_start.elapsed_time(t_end)
     gram_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     potrf_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
     solve_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
     ll_val = float(ll_dev.item()) if world == 1 else ll_val_host[0]
 
-    # ---- end to end from pinned host buffers through the public API ----
+    # ---- checks of the step's own results (outside every timed region; the factor of the last timed step is still in K) ----
+    checks = {}
+    from oracle import gabo_oracle as orc            # the checker, never the thing measured
+    if world == 1:
+        checks['potrf_info'] = int(info_last[0].item())
+        A = K[:NC, :NC]
+        rs = np.random.default_rng(7)
+        # factor residual |L L^T - (K + s2 I)| on sampled 256 x 256 tiles (K entries recomputed by the oracle)
+        worst = 0.0
+        for _ in range(3):
+            i0 = int(rs.integers(0, NC // 256)) * 256
+            j0 = int(rs.integers(0, i0 // 256 + 1)) * 256
+            Li = A[i0:i0 + 256, :j0 + 256]                       # rows of L (the strictly upper part of A still holds K)
+            if i0 == j0:
+                Li = torch.tril(Li, diagonal=i0)
+            Lj = torch.tril(A[j0:j0 + 256, :j0 + 256], diagonal=j0)
+            prod = (Li @ Lj.t()).cpu().numpy()
+            ref = orc.sphere_gaussian_K(Xnp[i0:i0 + 256], Xnp[j0:j0 + 256], beta=BETA, variance=VARIANCE)
+            if i0 == j0:
+                ref = ref + SIGMA2 * np.eye(256)
+                np.fill_diagonal(ref, VARIANCE + SIGMA2)
+            worst = max(worst, float(np.max(np.abs(prod - ref))))
+        checks['chol_residual_max_abs_sampled_tiles'] = worst
+        # solve residual: L alpha = y on a sampled row block
+        i0 = int(rs.integers(0, NC // 256)) * 256
+        r = (torch.tril(A[i0:i0 + 256, :i0 + 256], diagonal=i0) @ V[:i0 + 256] - y[i0:i0 + 256]).abs().max().item()
+        checks['solve_residual_max_abs'] = float(r)
+    else:
+        checks['potrf_info'] = int(info_last[0])
+    # sampled Gram rows against the oracle: regenerate (the factor overwrote the leading block), compare rows this rank holds
+    if world == 1:
+        ops.points_gram(ops.SPHERE_GAUSSIAN, X, None, beta=BETA, variance=VARIANCE, out=K, uplo='mirror', workspace=ws)
+        loc = np.r_[0:64, N // 2 + 100:N // 2 + 164, N - 64:N]
+        gl = loc
+    else:
+        if p2p_mirror:
+            gram_block_cyclic_mirrored(ops.SPHERE_GAUSSIAN, X, lay, peers, BETA, VARIANCE, workspace=ws, sync=True,
+                                       recompute_frac256=gram_frac, xch=xch)
+        else:
+            step()
+        loc = np.r_[0:64, rows - 64:rows]
+        gl = grow.numpy()[loc]
+    torch.cuda.synchronize()
+    got = K[torch.from_numpy(loc).to(dev)].cpu().numpy()
+    ref = orc.sphere_gaussian_K(Xnp[gl], Xnp, beta=BETA, variance=VARIANCE)
+    ref[np.arange(len(gl)), gl] = VARIANCE           # documented convention: the diagonal of K(X) is exactly `variance`
+    gerr = torch.tensor([float(np.max(np.abs(got - ref) / ref))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(gerr, op=dist.ReduceOp.MAX)
+    checks['gram_rows_max_rel_err_vs_oracle'] = float(gerr.item())
+    checks['gram_rows_checked_per_rank'] = int(len(loc))
+    if world == 1:
+        # log-likelihood of a sub-problem small enough for the oracle (same code path: Gram -> potrf -> trsm -> loglik)
+        ns = min(4096, NC)
+        Ks = torch.empty((ns, ns), dtype=torch.float64, device=dev)
+        ops.points_gram(ops.SPHERE_GAUSSIAN, X[:ns], None, beta=BETA, variance=VARIANCE, out=Ks, uplo='lower')
+        ops.potrf_(Ks, SIGMA2, check=False)
+        Vs = y[:ns].clone()
+        ops.trsm_(Ks, Vs)
+        ll_s = float(ops.gp_loglik(Ks, Vs).item())
+        ll_o = orc.gp_loglik(orc.sphere_gaussian_K(Xnp[:ns], beta=BETA, variance=VARIANCE), ynp[:ns], SIGMA2)
+        checks['loglik_n%d_rel_err_vs_oracle' % ns] = abs(ll_s / ll_o - 1.0)
+        del Ks, Vs
+
+    # ---- end to end from pinned host buffers ----
+    gpr = None
+    if world == 1:
+        gpr = GPR(X[:NC], y[:NC], kern)              # public API object; its data are replaced from the host every step
+        gpr.likelihood.variance = SIGMA2
+
+    def step_e2e(events):
+        if world > 1:
+            return step(events, from_host=True)
+        Xd = Xh.to(dev, non_blocking=True)
+        yd = yh.to(dev, non_blocking=True)
+        events[0].record()
+        kern.K(Xd, uplo='mirror', out=K)                             # SphereGaussianKernel.K: the full dense Gram
+        events[1].record()
+        gpr.set_data(Xd[:NC], yd[:NC])                                # new data: GPR refactorises (Gram of its rows, potrf, solve)
+        ll = gpr.compute_log_likelihood()                             # device -> host read of the result
+        events[3].record()
+        return ll
+
     for _ in range(3):
-        step(from_host=True)
+        step_e2e([torch.cuda.Event(enable_timing=True) for _ in range(4)])
     barrier()
     e_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     pre = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ll_e2e = None
     e0.record()
     for s in range(args.steps):
         pre[s].record()
-        step(e_evs[s], from_host=True)
+        ll_e2e = step_e2e(e_evs[s])
     e1.record()
     barrier()
     e2e_total_ms = e0.elapsed_time(e1)
     e2e_gram_ms = float(np.mean([pre[s].elapsed_time(e_evs[s][1]) for s in range(args.steps)]))   # H2D + pack + gram
+    checks['e2e_loglik_rel_diff_vs_device_resident'] = abs(ll_e2e / ll_val - 1.0)
+    if gpr is not None:
+        gpr._L = gpr._Lbuf = gpr._V = None
+        gpr = None
 
     def reduce_max(v):
         if world == 1:
@@ -356,11 +481,22 @@ def run_ours(args):
     e2e_gram_ms = reduce_max(e2e_gram_ms)
     launches_all = int(reduce_max(float(launches)))
 
+    # ---- BASELINE.json configs[4]: SPD affine-invariant / Stein / Log-Euclidean Grams at N = 16384 on S^6_++ -------------
+    spd = None
+    if not args.no_spd:
+        del K
+        if peers is not None:
+            peers.close()
+            peers = None
+        torch.cuda.empty_cache()
+        spd = run_spd_section(args, torch, dist, ops, orc, dev, world, rank, xch, reduce_max, barrier,
+                              BlockCyclic, PeerBuffers, spd_gram_block_cyclic, potrf_block_cyclic_p2p_, potrf_block_cyclic_,
+                              solve_lower_block_cyclic_, gp_loglik_block_cyclic, SpdAffineInvariantGaussianKernel)
+
     if rank != 0:
         if xch is not None:
             xch.close()
         if peers is not None:
-            del K
             peers.close()
         if world > 1:
             dist.destroy_process_group()
@@ -373,9 +509,10 @@ def run_ours(args):
     potrf_tflops = (NC ** 3 / 3) / potrf_s * 1e-12 if potrf_s > 0 else None
     sym = (world == 1) or p2p_mirror
     gram_flops = entries * (2 * DIM + F_TR) * (0.5 if sym else 1.0)    # symmetric tiles are computed once and mirrored
+    step_ms = total_ms / args.steps
     line = {
         'metric': 'sphere_gram_entries_per_s', 'value': value, 'unit': 'entries/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': warm, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+        'warmup': warm, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'sphere Gaussian Gram N={N} on S^50 (D={DIM}) + FP64 Cholesky of K+1e-2 I at N={NC} + solve + loglik',
                    'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2, 'seeds': [SEED_X, SEED_Y],
@@ -391,50 +528,213 @@ def run_ours(args):
                                    'kernel, diagonal block pushed by copy engines, stream-ordered flags (no collective in the loop)'
                                    if xch is not None else 'diagonal-block broadcast + block-column all-gather over NCCL')},
         'phases_ms': {'gram': gram_ms, 'potrf': potrf_ms, 'solve_loglik': solve_ms},
+        'step_entries_per_s': entries / (step_ms * 1e-3),
         'cholesky': {'n': NC, 'seconds': potrf_s, 'tflops': potrf_tflops,
                      'frac_fp64_tensor_peak': (potrf_tflops / (FP64_PEAK_TFLOPS * world)) if potrf_tflops else None},
         'loglik': ll_val,
+        'checks': checks,
         'gpu_launches': launches_all,
         'clocks': clocks.summary(),
         'e2e': {'value': entries / (e2e_gram_ms * 1e-3), 'unit': 'entries/s',
                 'h2d_bytes_per_step': int(Xh.numel() * 8 + yh.numel() * 8), 'd2h_bytes_per_step': 8,
                 'ms_per_step': e2e_total_ms / args.steps,
-                'api': 'pinned host X,y -> device, ops.points_gram / potrf_ / trsm_ / gp_loglik (C-ABI; gaboflow_b200.dist for N>1), loglik read back'},
+                'step_entries_per_s': entries / (e2e_total_ms / args.steps * 1e-3),
+                'loglik': ll_e2e,
+                'api': ('pinned host X,y -> device; SphereGaussianKernel.K(X) (full dense Gram, the timed numerator of `value`); '
+                        'GPR(X[:n_chol], y[:n_chol], kern).compute_log_likelihood() (own lower Gram + Cholesky + solve + '
+                        'likelihood, result read back)') if world == 1 else
+                       'pinned host X,y -> device; gaboflow_b200.dist (block-cyclic Gram, p2p Cholesky, solve, loglik all-reduce + read back)'},
         'roofline': {'bound': 'tensor',
                      'kernel': 'gemm_nt_tma_kernel (DMMA.8x8x4 fed by UTMALDG): the k=512 trailing updates inside gabo_potrf_f64, '
-                               + ('%.0f%% of the step' % (100.0 * kern['total_ms'] / args.steps / (total_ms / args.steps)) if kern else 'dominant kernel'),
-                     'achieved': kern['tflops_avg'] if kern else potrf_tflops,
+                               + ('%.0f%% of the step' % (100.0 * kprof['total_ms'] / args.steps / step_ms) if kprof else 'dominant kernel'),
+                     'achieved': kprof['tflops_avg'] if kprof else potrf_tflops,
                      'peak': FP64_PEAK_TFLOPS * world, 'unit': 'TFLOP/s',
-                     'frac': ((kern['tflops_avg'] if kern else potrf_tflops) / (FP64_PEAK_TFLOPS * world)) if (kern or potrf_tflops) else None,
-                     'traffic': GEMM_DRAM_TRAFFIC_BYTES if kern else None,
+                     'frac': ((kprof['tflops_avg'] if kprof else potrf_tflops) / (FP64_PEAK_TFLOPS * world)) if (kprof or potrf_tflops) else None,
+                     'traffic': GEMM_DRAM_TRAFFIC_BYTES if kprof else None,
                      'traffic_note': 'dram read+write of ONE launch at m=32256, k=512 (the largest): ncu --set full, '
                                      'profiles/r01_gemm_tma_ncu.txt; algorithmic bytes of that launch 8.49e9',
-                     'flops_per_launch': kern['flops_per_launch_avg'] if kern else NC ** 3 / 3,
-                     'ms_per_launch': kern['ms_per_launch_avg'] if kern else None,
-                     'launches_timed': kern['launches'] if kern else None,
-                     'largest_launch': {'ms': kern['largest_ms'], 'tflops': kern['largest_tflops']} if kern else None,
+                     'flops_per_launch': kprof['flops_per_launch_avg'] if kprof else NC ** 3 / 3,
+                     'ms_per_launch': kprof['ms_per_launch_avg'] if kprof else None,
+                     'launches_timed': kprof['launches'] if kprof else None,
+                     'largest_launch': {'ms': kprof['largest_ms'], 'tflops': kprof['largest_tflops']} if kprof else None,
                      'how': 'CUDA events recorded by the library around every such launch on its stream during the timed steps '
                             '(gabo_profile_trailing_updates); flops = 2*128*64*512 per lower tile',
                      'peak_source': 'FP64 tensor peak is not in MEASURED_PEAKS.json: measured on this pool with tools/fp64_probe.cu '
-                                    '(profiles/r01_fp64_probe.txt, DMMA 37.2 TFLOP/s; cuBLAS DGEMM 36.2)'},
+                                    '(profiles/r01_fp64_probe.txt, DMMA 37.2 TFLOP/s = 148 SM x 64 FMA x 2 x 1.965 GHz; cuBLAS DGEMM 36.2)'},
         'roofline_gram': {'bound': 'fp64', 'kernel': 'points_gram_kernel_1c<52> (DMMA inner products + fused acos/exp epilogue)', 'achieved': gram_flops / (gram_ms * 1e-3) * 1e-12,
                           'peak': FP64_PEAK_TFLOPS * world, 'unit': 'TFLOP/s',
                           'frac': gram_flops / (gram_ms * 1e-3) * 1e-12 / (FP64_PEAK_TFLOPS * world),
                           'hbm_write_gbs_per_gpu': rows * N * 8 / (gram_ms * 1e-3) * 1e-9, 'hbm_peak_gbs': hbm_peak, 'hbm_peak_source': hbm_src,
                           'flops_per_entry_declared': 2 * DIM + F_TR},
     }
+    if spd is not None:
+        line['spd'] = spd
     if world == 1 and not args.no_cpu_baseline:
-        line['cpu_baseline'] = cpu_reference_sample(N, n_chol_sample=min(args.ref_chol_n, NC), gram_rows=args.ref_gram_rows,
-                                                    n_chol_metric=NC)
+        cb = cpu_reference_sample(N, n_chol_sample=min(args.ref_chol_n, NC), gram_rows=args.ref_gram_rows, n_chol_metric=NC,
+                                  spd_rows=0)
+        if spd is not None and 'cpu_ai_pairs_per_s' in spd:
+            cb['spd'] = {'ai_pairs_per_s': spd['cpu_ai_pairs_per_s'], 'sample': spd['cpu_sample']}
+        line['cpu_baseline'] = cb
+        line['e2e']['step_speedup_vs_cpu_step'] = cb['step_seconds_extrapolated'] / (e2e_total_ms / args.steps * 1e-3)
     print(json.dumps(line), flush=True)
     if xch is not None:
         xch.close()
-    if peers is not None:
-        del K
-        peers.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_spd_section(args, torch, dist, ops, orc, dev, world, rank, xch, reduce_max, barrier, BlockCyclic, PeerBuffers,
+                    spd_gram_block_cyclic, potrf_block_cyclic_p2p_, potrf_block_cyclic_, solve_lower_block_cyclic_,
+                    gp_loglik_block_cyclic, SpdAffineInvariantGaussianKernel):
+    """BASELINE.json configs[4]: N = 16,384 SPD matrices on S^6_++ -- affine-invariant (timed, roofline, parity), Stein and
+    Log-Euclidean Grams, then Cholesky + log-likelihood of K_AI + sigma^2 I.  Returns the `spd` object of the JSON line."""
+    n, d = args.n_spd, SPD_D
+    steps = args.steps
+    Xm_np = orc.synth_spd_mandel(n, d, seed=SPD_SEED)
+    ys_np = np.random.default_rng(SEED_Y + 1).standard_normal((n, 1))
+    Xm_h = torch.from_numpy(Xm_np).pin_memory()
+    Xm = Xm_h.to(dev)
+    ys = torch.from_numpy(ys_np).to(dev)
+    PANEL = 512
+    lay = BlockCyclic(n, PANEL, world, rank)
+    rows = lay.local_rows
+    peers = None
+    if world > 1:
+        peers = PeerBuffers(rows, n, dev)
+        K = peers.local
+    else:
+        K = torch.empty((n, n), dtype=torch.float64, device=dev)
+    use_xch = xch if (xch is not None and n <= xch.n and n % PANEL == 0) else None
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        barrier()
+        ts = []
+        for _ in range(reps):
+            a, b = ev(), ev()
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return reduce_max(float(np.mean(ts)))
+
+    t_prep = timed(lambda: ops.spd_prep(Xm, d, want_logm=True), steps)
+    prep = ops.spd_prep(Xm, d, want_logm=True)
+
+    def gram(kind, beta):
+        if world == 1:
+            ops.spd_gram(kind, prep, None, beta=beta, variance=VARIANCE, out=K, uplo='mirror')
+        else:
+            spd_gram_block_cyclic(kind, prep, lay, peers, beta, VARIANCE, sync=True, xch=use_xch)
+
+    def gram_logeuclid():
+        if world == 1:
+            ops.points_gram(ops.SQDIST_GAUSSIAN, prep.logm, None, beta=SPD_BETA_LE, variance=VARIANCE, out=K, uplo='mirror')
+        else:
+            for pnl in lay.my_panels():
+                sl, r0 = lay.slot(pnl) * PANEL, pnl * PANEL
+                r1 = r0 + lay.panel_rows(pnl)
+                ops.points_gram(ops.SQDIST_GAUSSIAN, prep.logm, None, beta=SPD_BETA_LE, variance=VARIANCE,
+                                out=K[sl: sl + (r1 - r0)], row0=r0, row1=r1, uplo='full')
+
+    grow = lay.global_rows()
+    nrow_chk = 48 if world == 1 else 16
+    loc = np.r_[0:nrow_chk // 2, rows - nrow_chk // 2:rows]
+    gl = grow.numpy()[loc]
+    loc_t = torch.from_numpy(loc).to(dev)
+
+    def parity(ref_rows, diag_exact):
+        got = K[loc_t].cpu().numpy()
+        ref = ref_rows.copy()
+        if diag_exact:
+            ref[np.arange(len(gl)), gl] = VARIANCE
+        e = torch.tensor([float(np.max(np.abs(got - ref) / np.abs(ref)))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        return float(e.item())
+
+    out = {'workload': f'SPD Grams, N={n} matrices on S^{d}_++ (Mandel [{n},{d * (d + 1) // 2}], eigenvalues U[0.5,2], seed {SPD_SEED}); '
+                       f'full dense FP64 K, lower blocks computed once and mirror-stored', 'prep_ms': t_prep}
+    # affine-invariant Gaussian: the timed kernel of config 5
+    t_ai = timed(lambda: gram(ops.SPD_AI_GAUSSIAN, SPD_BETA_AI), steps)
+    gram(ops.SPD_AI_GAUSSIAN, SPD_BETA_AI)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    _limit, cores = _host_threads()
+    t0 = time.perf_counter()
+    ref_ai = orc.spd_ai_gaussian_K(Xm_np[gl], Xm_np, beta=SPD_BETA_AI, variance=VARIANCE)
+    t_cpu = time.perf_counter() - t0
+    pairs = n * (n + 1) / 2
+    out['affine_invariant'] = {
+        'ms': t_ai, 'pairs_per_s': pairs / (t_ai * 1e-3), 'entries_per_s': float(n) * n / (t_ai * 1e-3),
+        'roofline': {'bound': 'fp64', 'kernel': 'spd_ai_gram_kernel<6> (congruence + Householder in FP64, packed-FP32 QL starts, '
+                     'validated FP64 Newton refinement, log/exp)', 'flops_per_pair_declared': F_PAIR, 'unique_pairs': pairs,
+                     'achieved': F_PAIR * pairs / (t_ai * 1e-3) * 1e-12, 'peak': FP64_PEAK_TFLOPS * world, 'unit': 'TFLOP/s',
+                     'frac': F_PAIR * pairs / (t_ai * 1e-3) * 1e-12 / (FP64_PEAK_TFLOPS * world),
+                     'hbm_floor_ms': 8.0 * n * n / 6547.5e9 * 1e3 / world},
+        'parity': {'max_rel_err_vs_oracle': parity(ref_ai, True), 'rows_checked_per_rank': int(len(loc))},
+        'beta': SPD_BETA_AI}
+    out['cpu_ai_pairs_per_s'] = len(gl) * n / t_cpu
+    out['cpu_sample'] = f'{len(gl)} rows x {n} cols (batched eigvalsh of W_i S_j W_i^T, {cores} threads) in {t_cpu:.2f} s'
+    # end to end through the kernel class from pinned host Mandel vectors (prepare + Gram), N = 1
+    if world == 1:
+        k_ai = SpdAffineInvariantGaussianKernel(d * (d + 1) // 2, range(d * (d + 1) // 2), beta_min=0.0, beta=SPD_BETA_AI)
+        t_e2e = timed(lambda: k_ai.K(Xm_h.to(dev, non_blocking=True), uplo='mirror', out=K), steps)
+        out['affine_invariant']['e2e'] = {'ms': t_e2e, 'pairs_per_s': pairs / (t_e2e * 1e-3), 'h2d_bytes': int(Xm_h.numel() * 8),
+                                          'api': 'pinned host Mandel vectors -> device; SpdAffineInvariantGaussianKernel.K (prepare + pair Gram)'}
+    # Cholesky + solve + log-likelihood of K_AI + sigma^2 I (config 5: "plus FP64 Cholesky and GP log-likelihood")
+    info = [None]
+    ll = [None]
+
+    def factor_and_loglik():
+        gram(ops.SPD_AI_GAUSSIAN, SPD_BETA_AI)
+        if world == 1:
+            info[0] = ops.potrf_(K, SIGMA2, check=False)
+            Vv = ys.clone()
+            ops.trsm_(K, Vv)
+            ll[0] = ops.gp_loglik(K, Vv)
+        else:
+            winv = {}
+            if use_xch is not None:
+                info[0] = potrf_block_cyclic_p2p_(K, lay, SIGMA2, use_xch, n_factor=n, winv_store=winv)
+            else:
+                info[0] = potrf_block_cyclic_(K, lay, SIGMA2, n_factor=n, winv_store=winv)
+            Vv = ys[grow.to(dev)].clone()
+            solve_lower_block_cyclic_(K, Vv, lay, n_factor=n, winv_store=winv)
+            ll[0] = gp_loglik_block_cyclic(K, Vv, lay, n_factor=n)
+
+    t_fac = timed(factor_and_loglik, max(2, min(steps, 3)))
+    out['cholesky_loglik'] = {'ms_incl_gram': t_fac, 'ms_excl_gram': t_fac - t_ai, 'n': n,
+                              'tflops': (n ** 3 / 3) / max((t_fac - t_ai) * 1e-3, 1e-9) * 1e-12,
+                              'potrf_info': int(info[0].item()) if world == 1 else int(info[0]),
+                              'loglik': float(ll[0].item()) if world == 1 else float(ll[0])}
+    # Stein (as coded in the reference) and Log-Euclidean
+    if world == 1 or True:
+        t_st = timed(lambda: gram(ops.SPD_STEIN, SPD_BETA_STEIN), steps)
+        gram(ops.SPD_STEIN, SPD_BETA_STEIN)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ref_st = orc.spd_stein_K(Xm_np[gl], Xm_np, beta=SPD_BETA_STEIN, variance=VARIANCE)
+        out['stein'] = {'ms': t_st, 'entries_per_s': float(n) * n / (t_st * 1e-3), 'beta': SPD_BETA_STEIN,
+                        'parity': {'max_rel_err_vs_oracle': parity(ref_st, False)}}
+    t_le = timed(gram_logeuclid, steps)
+    gram_logeuclid()
+    torch.cuda.synchronize()
+    ref_le = orc.spd_logeuclid_K(Xm_np[gl], Xm_np, beta=SPD_BETA_LE, variance=VARIANCE)
+    out['log_euclidean'] = {'ms_pair_stage': t_le, 'ms_incl_prep': t_le + t_prep, 'entries_per_s': float(n) * n / (t_le * 1e-3),
+                            'beta': SPD_BETA_LE, 'parity': {'max_rel_err_vs_oracle': parity(ref_le, True)},
+                            'note': 'per-point FP64 logm in prep_ms, then the DMMA squared-distance tile kernel' +
+                                    ('' if world == 1 else ' (N>1: every rank produces the full rows of its panels, no exchange)')}
+    del K
+    if peers is not None:
+        peers.close()
+    return out
 
 
 def main():
@@ -445,8 +745,11 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--n-gram', type=int, default=65536)
     ap.add_argument('--n-chol', type=int, default=32768)
+    ap.add_argument('--n-spd', type=int, default=SPD_N)
+    ap.add_argument('--no-spd', action='store_true', help='skip the SPD section (configs[4])')
     ap.add_argument('--ref-gram-rows', type=int, default=2048)
     ap.add_argument('--ref-chol-n', type=int, default=8192)
+    ap.add_argument('--ref-spd-rows', type=int, default=48)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-p2p', action='store_true', help='N=2: full rows per rank instead of NVLink-mirrored tiles')
     args = ap.parse_args()

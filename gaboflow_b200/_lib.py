@@ -22,6 +22,7 @@ SIGNATURES = {
     'gabo_kdiag_const_f64': (i32, [i64, f64, vp, vp]),
     'gabo_spd_prep_f64': (i32, [vp, i64, i64, i32, vp, vp, vp, vp, vp, i64, vp, vp]),
     'gabo_spd_gram_f64': (i32, [i32, i32, vp, vp, vp, i64, vp, vp, i64, vp, i64, i32, f64, f64, vp, i64, i64, i64, i32, vp]),
+    'gabo_spd_gram_cyclic_f64': (i32, [i32, i32, vp, vp, vp, vp, i64, i64, f64, f64, vp, i64, i32, i32, vp]),
     'gabo_spd_stein_kdiag_f64': (i32, [vp, i64, f64, f64, vp, vp]),
     'gabo_potrf_workspace_bytes': (sz, [i64]),
     'gabo_potrf_f64': (i32, [i64, vp, i64, f64, vp, vp, sz, vp]),

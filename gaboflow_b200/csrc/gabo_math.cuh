@@ -128,15 +128,24 @@ static __device__ __noinline__ double exp_scaled_slow(double x, double scale) {
 }
 
 // exp(x) * scale for x <= 0; `tab` = shared-memory table 2^(j/32) ALREADY multiplied by `scale`.
-// The power of two 2^m is applied by an integer add on the exponent field of v = tab[j] * poly, which is only valid
-// while the result stays a NORMAL number: lanes whose biased exponent would reach 0 (scale * e^x below DBL_MIN -- with a
-// small `scale` that happens for |x| well under 700), as well as |x| >= 700 / NaN / inf, take the libm slow path.
+// The power of two 2^m is applied by an integer add on the exponent field of v = tab[j] * poly, which is only valid while
+// the result stays a NORMAL number.  v carries the exponent of `scale` (or one more), so the result is normal whenever
+// m >= 2 - E with E the biased exponent of scale, i.e. |x| <= (E - 2) ln 2: entries beyond `slow_hi` -- the high word of
+// min(700, (E - 2) ln 2), from exp_slow_threshold_hi(scale), computed once per thread -- take the libm slow path, as do
+// NaN / inf.  (Round 1 tested |x| >= 700 only: with scale = 1e-6 and x = -699 the exponent field wrapped to -8.7e306.)
+__device__ __forceinline__ int exp_slow_threshold_hi(double scale) {
+    const int E = (__double2hiint(scale) >> 20) & 0x7ff;           // 0: zero / subnormal scale, 0x7ff: inf / NaN
+    double lim = (double)(E - 2) * 0.693147180559945;
+    if (E == 0x7ff || !(scale > 0.0)) lim = 0.0;
+    lim = fmin(fmax(lim, 0.0), 700.0);
+    return __double2hiint(lim);                                      // |x| >= lim  <=>  hi_abs(x) >= hi(lim) (conservatively)
+}
+
 template <int N>
 __device__ __forceinline__ void exp_neg_scaled_fast_n(const double (&x)[N], double (&out)[N], const double* __restrict__ tab,
-                                                      double scale) {
+                                                      double scale, int slow_hi) {
     double r[N], p[N];
     int n[N];
-    bool slow[N];
     bool anyslow = false;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -145,7 +154,7 @@ __device__ __forceinline__ void exp_neg_scaled_fast_n(const double (&x)[N], doub
         const double nf = tn - kExpC[0];
         r[i] = fma(nf, kExpC[3], fma(nf, kExpC[2], x[i]));
         p[i] = kExpC[4];
-        slow[i] = (hi_abs(x[i]) >= 0x4085e000);      // |x| >= 700 (or NaN / inf)
+        anyslow = anyslow || (hi_abs(x[i]) >= slow_hi);
     }
 #pragma unroll
     for (int c = 5; c <= 9; ++c)
@@ -155,15 +164,12 @@ __device__ __forceinline__ void exp_neg_scaled_fast_n(const double (&x)[N], doub
     for (int i = 0; i < N; ++i) {
         p[i] = fma(p[i], r[i], kExpC[9]);
         const double v = tab[n[i] & 31] * p[i];
-        const int hv = __double2hiint(v), m = n[i] >> 5;
-        out[i] = __hiloint2double(hv + (m << 20), __double2loint(v));
-        slow[i] = slow[i] || ((hv >> 20) + m <= 0);  // result would be subnormal / underflow: the exponent add wraps
-        anyslow = anyslow || slow[i];
+        out[i] = __hiloint2double(__double2hiint(v) + ((n[i] >> 5) << 20), __double2loint(v));
     }
     if (__any_sync(0xffffffffu, anyslow)) {
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            if (slow[i]) out[i] = exp_scaled_slow(x[i], scale);
+            if (hi_abs(x[i]) >= slow_hi) out[i] = exp_scaled_slow(x[i], scale);
     }
 }
 
@@ -172,7 +178,7 @@ __device__ __forceinline__ void acos_fast_n(const double (&t)[N], double (&out)[
 
 template <int N>
 __device__ __forceinline__ void exp_neg_fast_n(const double (&x)[N], double (&out)[N], const double* __restrict__ tab) {
-    exp_neg_scaled_fast_n<N>(x, out, tab, 1.0);
+    exp_neg_scaled_fast_n<N>(x, out, tab, 1.0, 0x4085e000);
 }
 
 // ---- lean natural logarithm for POSITIVE, NORMAL, finite x (the eigenvalues of an SPD congruence) ------------------------

@@ -25,7 +25,7 @@ __global__ void math_probe_kernel(int which, const double* __restrict__ x, int64
         if (which == 0) {
             acos_clamped_fast_n<4>(in, res);
         } else if (which == 1) {
-            exp_neg_scaled_fast_n<4>(in, res, tab, scale);
+            exp_neg_scaled_fast_n<4>(in, res, tab, scale, exp_slow_threshold_hi(scale));
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) res[k] = log_pos_normal(in[k]);

@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
     const bool vec_ok = p.vec_ok != 0;
     double* const Kbase = p.K;
     if (tid < 32) exptab[tid] = kExp2Tab[tid] * variance;   // variance folded into the exp table: one DMUL less per entry
+    const int exp_slow_hi = exp_slow_threshold_hi(variance);   // beyond it variance * e^x leaves the normal range: libm path
     __syncthreads();
 
     const int64_t my_tiles = (p.ntiles > (int64_t)blockIdx.x) ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
                 for (int j = 0; j < 8; ++j)
                     arg[j] = (kind == GABO_SPHERE_GAUSSIAN) ? (nbeta * dd[j]) * dd[j] : nbeta * dd[j];   // kernels_sphere_tf.py:83-86, 199-202
             }
-            exp_neg_scaled_fast_n<8>(arg, v, exptab, variance);                        // kernels_sphere_tf.py:88, 204
+            exp_neg_scaled_fast_n<8>(arg, v, exptab, variance, exp_slow_hi);                       // kernels_sphere_tf.py:88, 204
             if (diag_tile) {   // K(X,X) diagonal is exactly `variance` (matches Kdiag, kernels_sphere_tf.py:105)
 #pragma unroll
                 for (int j = 0; j < 8; ++j)

@@ -115,7 +115,28 @@ struct SpdGramParams {
     int64_t ldk, ldt, n1, n2, row0, row1;
     int symmetric, uplo;
     double beta, variance;
+    // multi-GPU mode (cyc_world > 0; symmetric, mirrored): K is distributed by 512-row panels, 1-D block-cyclic -- global row
+    // gi lives on rank (gi / 512) % cyc_world at local row (gi / 512 / cyc_world) * 512 + gi % 512 of peer[rank] (this
+    // GPU's own buffer or an NVLink peer mapping).  The lower 32 x 128 blocks are dealt to the ranks round-robin
+    // ((blockIdx.x + blockIdx.y) % cyc_world), so the work is balanced whatever the panel ownership, and every block is
+    // stored -- rows and mirror image -- straight into the HBM of the ranks that own those rows.
+    int cyc_world, cyc_rank;
+    double* peer[GABO_MAX_PEERS];
 };
+
+constexpr int SPD_CYC_NB = 512;   // panel height of the block-cyclic layout (gaboflow_b200/dist.py)
+
+// start of global row gi of K
+__device__ __forceinline__ double* spd_row_ptr(const SpdGramParams& p, int64_t gi) {
+    if (p.cyc_world > 0) {
+        const int64_t P = gi / SPD_CYC_NB;
+        return p.peer[P % p.cyc_world] + ((P / p.cyc_world) * SPD_CYC_NB + (gi - P * SPD_CYC_NB)) * p.ldk;
+    }
+    return p.K + (gi - p.row0) * p.ldk;
+}
+__device__ __forceinline__ bool spd_block_is_mine(const SpdGramParams& p) {
+    return p.cyc_world <= 0 || (int)((blockIdx.x + blockIdx.y) % (unsigned)p.cyc_world) == p.cyc_rank;
+}
 
 // M = (W L)(W L)^T for one pair: W = chol(S_i)^-1 and L = chol(S_j), both lower triangular and packed (entry (a,k), k <= a,
 // at a(a+1)/2 + k).  G = W L is lower triangular again, so the congruence W S_j W^T costs 2 * d(d+1)(d+2)/6 = 112 FMA at
@@ -188,6 +209,7 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_stein_gram_kernel(co
     const int64_t i0 = p.row0 + (int64_t)blockIdx.y * TI;
     const int64_t j0 = (int64_t)blockIdx.x * TJ;
     if (p.uplo != GABO_FULL && j0 > i0 + TI - 1) return;   // symmetric modes: blocks strictly above the diagonal
+    if (!spd_block_is_mine(p)) return;
     const bool mirror = (p.uplo == GABO_SYMM_MIRROR);
 
     for (int e = tid; e < TI * MP; e += TJ) {
@@ -250,7 +272,7 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_stein_gram_kernel(co
             // kernels_spd_tf.py:104-112: det(X X2)^beta / det((X+X2)/2)^beta
             val = p.variance * exp(p.beta * (sRld[r] + cld - ldsum));
             if (bad) val = __longlong_as_double(0x7ff8000000000000LL);
-            st_cs(p.K + (gi - p.row0) * p.ldk + j, val);
+            st_cs(spd_row_ptr(p, gi) + j, val);
         }
         if (mirror) sOut[r][tid] = val;
     }
@@ -260,7 +282,7 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 4 : 2) spd_stein_gram_kernel(co
         for (int jl = warp; jl < TJ; jl += TJ / 32) {
             const int64_t gj = j0 + jl;          // becomes the row of the mirrored entry
             const int64_t gi = i0 + lane;        // becomes the column
-            if (gj < p.n2 && lane < rows_here && gj < gi) st_cs(p.K + gj * p.ldk + gi, sOut[lane][jl]);
+            if (gj < p.n2 && lane < rows_here && gj < gi) st_cs(spd_row_ptr(p, gj) + gi, sOut[lane][jl]);
         }
     }
 }
@@ -338,6 +360,7 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 5 : 2) spd_ai_gram_kernel(const
     const int64_t i0 = p.row0 + (int64_t)blockIdx.y * TI;
     const int64_t j0 = (int64_t)blockIdx.x * TJ;
     if (p.uplo != GABO_FULL && j0 > i0 + TI - 1) return;   // symmetric modes: blocks strictly above the diagonal
+    if (!spd_block_is_mine(p)) return;
     const bool mirror = (p.uplo == GABO_SYMM_MIRROR);
 
     for (int e = tid; e < TI * MP; e += TJ) {
@@ -355,6 +378,7 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 5 : 2) spd_ai_gram_kernel(const
     const bool jok = j < p.n2;
     const double* const ltj = p.Lt + (jok ? j : 0);        // lanes past the last column compute along on column 0
     const double nbeta = -p.beta, variance = p.variance;
+    const int exp_slow_hi = exp_slow_threshold_hi(variance);
     const int rows_here = (int)((p.row1 - i0) < (int64_t)TI ? (p.row1 - i0) : (int64_t)TI);
     double* const stash0 = sStash + tid;   // entry k of row u of the trip: stash0[(u * NST + k) * TJ]
 
@@ -436,14 +460,14 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 5 : 2) spd_ai_gram_kernel(const
                     const double a = (KIND == GABO_SPD_AI_GAUSSIAN) ? nbeta * s2 : nbeta * sqrt(s2);   // kernels_spd_tf.py:241-248 / 396-400
                     if (u) arg[1] = a; else arg[0] = a;
                 }
-                exp_neg_scaled_fast_n<AI_NR>(arg, val, sTab, variance);
+                exp_neg_scaled_fast_n<AI_NR>(arg, val, sTab, variance, exp_slow_hi);
             }
 #pragma unroll
             for (int u = 0; u < AI_NR; ++u) {
                 const int64_t gi = i0 + r + u;
                 if (p.symmetric && gi == j) val[u] = variance;   // d_AI(X,X) = 0 exactly
                 const bool skip = mirror && (j > gi);
-                if (jok && (r + u < rows_here) && !skip) st_cs(p.K + (gi - p.row0) * p.ldk + j, val[u]);
+                if (jok && (r + u < rows_here) && !skip) st_cs(spd_row_ptr(p, gi) + j, val[u]);
                 if (mirror) sOut[r + u - hb][tid] = val[u];
             }
         }
@@ -455,7 +479,7 @@ __global__ void __launch_bounds__(TJ, (D <= 6) ? 5 : 2) spd_ai_gram_kernel(const
             for (int jl = warp * 4 + (lane >> 3); jl < TJ; jl += 16) {
                 const int64_t gj = j0 + jl;          // becomes the row of the mirrored entry
                 const int64_t gi = i0 + hb + cr;     // becomes the column
-                if (gj < p.n2 && hb + cr < rows_here && gj < gi) st_cs(p.K + gj * p.ldk + gi, sOut[cr][jl]);
+                if (gj < p.n2 && hb + cr < rows_here && gj < gi) st_cs(spd_row_ptr(p, gj) + gi, sOut[cr][jl]);
             }
             __syncthreads();
         }
@@ -484,6 +508,20 @@ int launch_spd_gram(int kind, const SpdGramParams& p, cudaStream_t stream) {
     if (rc) return rc;
     GABO_LAUNCH_CHECK();
     return 0;
+}
+
+int dispatch_spd_gram(int kind, int d, const SpdGramParams& p, cudaStream_t s) {
+    switch (d) {
+#ifndef GABO_SPD_ONLY_D6   /* development builds: compile the d = 6 pair kernels only (the full set takes ~100 s) */
+        case 2: return launch_spd_gram<2>(kind, p, s);
+        case 3: return launch_spd_gram<3>(kind, p, s);
+        case 4: return launch_spd_gram<4>(kind, p, s);
+        case 5: return launch_spd_gram<5>(kind, p, s);
+        case 7: return launch_spd_gram<7>(kind, p, s);
+        case 8: return launch_spd_gram<8>(kind, p, s);
+#endif
+        default: return launch_spd_gram<6>(kind, p, s);
+    }
 }
 
 __global__ void stein_kdiag_kernel(const double* __restrict__ logdet, int64_t n, double beta, double variance,
@@ -554,19 +592,49 @@ extern "C" int gabo_spd_gram_f64(int kind, int d, const double* W1, const double
     p.R = (kind == GABO_SPD_STEIN) ? S1 : W1;
     p.Rld = logdet1; p.Cm = S2; p.Lt = L2t; p.ldt = ldt2; p.Cld = logdet2; p.K = K; p.ldk = ldk; p.n1 = n1; p.n2 = n2;
     p.row0 = row0; p.row1 = row1; p.symmetric = symmetric ? 1 : 0; p.uplo = uplo; p.beta = beta; p.variance = variance;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    switch (d) {
-#ifndef GABO_SPD_ONLY_D6   /* development builds: compile the d = 6 pair kernels only (the full set takes ~100 s) */
-        case 2: return launch_spd_gram<2>(kind, p, s);
-        case 3: return launch_spd_gram<3>(kind, p, s);
-        case 4: return launch_spd_gram<4>(kind, p, s);
-        case 5: return launch_spd_gram<5>(kind, p, s);
-        case 7: return launch_spd_gram<7>(kind, p, s);
-        case 8: return launch_spd_gram<8>(kind, p, s);
-#endif
-        default: return launch_spd_gram<6>(kind, p, s);
-    }
+    p.cyc_world = 0; p.cyc_rank = 0;
+    for (int r = 0; r < GABO_MAX_PEERS; ++r) p.peer[r] = nullptr;
+    return gabo::dispatch_spd_gram(kind, d, p, static_cast<cudaStream_t>(stream));
 }
+
+// Multi-GPU symmetric SPD Gram K(X, X), distributed by 512-row panels 1-D block-cyclic over `world` ranks (panel P on rank
+// P % world, local slot P / world).  Every rank calls this with the same per-point data; rank `rank` evaluates its share of
+// the lower 32 x 128 blocks (dealt round-robin, so the triangular work is balanced) and stores each block and its mirror
+// image directly into the buffers of the ranks that own those rows (K_bases_host[r]: base of rank r's [local_rows, ldk]
+// buffer as mapped in this process -- own memory or CUDA IPC peer mappings over NVLink).  No collective; the caller
+// synchronises (stream + barrier, or the flag handshake of gaboflow_b200/dist.py) before the rows are read.
+extern "C" int gabo_spd_gram_cyclic_f64(int kind, int d, const double* W1, const double* S1, const double* logdet1,
+                                        const double* L1t, int64_t ldt, int64_t n, double beta, double variance,
+                                        double* const* K_bases_host, int64_t ldk, int world, int rank, gabo_stream_t stream) {
+    using namespace gabo;
+    if (kind < GABO_SPD_AI_GAUSSIAN || kind > GABO_SPD_STEIN) return -1;
+    if (d < 2 || d > 8) return -2;
+    if (n < 0) return -8;
+    if (kind == GABO_SPD_STEIN) {
+        if (S1 == nullptr) return -4;
+        if (logdet1 == nullptr) return -5;
+    } else {
+        if (W1 == nullptr) return -3;
+        if (L1t == nullptr) return -6;
+        if (ldt < n) return -7;
+    }
+    if (K_bases_host == nullptr) return -11;
+    if (ldk < n) return -12;
+    if (world < 1 || world > GABO_MAX_PEERS) return -13;
+    if (rank < 0 || rank >= world) return -14;
+    if (n == 0) return 0;
+    SpdGramParams p;
+    p.R = (kind == GABO_SPD_STEIN) ? S1 : W1;
+    p.Rld = logdet1; p.Cm = S1; p.Lt = L1t; p.ldt = ldt; p.Cld = logdet1; p.K = K_bases_host[rank]; p.ldk = ldk;
+    p.n1 = n; p.n2 = n; p.row0 = 0; p.row1 = n; p.symmetric = 1; p.uplo = GABO_SYMM_MIRROR; p.beta = beta; p.variance = variance;
+    p.cyc_world = world; p.cyc_rank = rank;
+    for (int r = 0; r < GABO_MAX_PEERS; ++r) {
+        p.peer[r] = (r < world) ? K_bases_host[r] : nullptr;
+        if (r < world && p.peer[r] == nullptr) return -11;
+    }
+    return gabo::dispatch_spd_gram(kind, d, p, static_cast<cudaStream_t>(stream));
+}
+
 
 extern "C" int gabo_spd_stein_kdiag_f64(const double* logdet, int64_t n, double beta, double variance, double* out,
                                         gabo_stream_t stream) {

@@ -457,6 +457,31 @@ def gram_block_cyclic_mirrored(kind: int, X: torch.Tensor, layout: BlockCyclic, 
     return peers.local
 
 
+def spd_gram_block_cyclic(kind: int, prep, layout: BlockCyclic, peers: PeerBuffers, beta: float, variance: float,
+                          group=None, sync: bool = True, xch: Optional['PanelExchange'] = None) -> torch.Tensor:
+    """Symmetric SPD Gram (affine-invariant Gaussian / Laplace, Stein) into the block-cyclic row panels of all ranks: the
+    lower 32 x 128 blocks are dealt round-robin to the ranks (balanced triangular work), and every block and its mirror image
+    are stored from inside the kernel into the HBM of the ranks owning those rows (``gabo_spd_gram_cyclic_f64``).  The pair
+    kernel is compute-bound (8 B per ~2.5 kflop), so the NVLink stores ride for free.  Completion: the stream-ordered flag
+    handshake of ``gram_block_cyclic_mirrored`` when ``xch`` is given, else stream sync + barrier."""
+    from . import ops
+    if layout.nb != 512:
+        raise ValueError('the cyclic SPD Gram uses 512-row panels')
+    ops.spd_gram_cyclic(kind, prep, peers.ptrs, int(peers.local.stride(0)), layout.world, layout.rank, beta, variance)
+    if sync and xch is not None and layout.world > 1:
+        xch.gram_epoch += 1
+        me = layout.rank
+        others = [r for r in range(layout.world) if r != me]
+        ops.flag_signal([xch.flag_ptr(r, 16 + me) for r in others], xch.gram_epoch)
+        for r in others:
+            ops.flag_wait_geq(xch.flag_ptr(me, 16 + r), xch.gram_epoch)
+    elif sync:
+        torch.cuda.synchronize(peers.local.device)
+        if layout.world > 1:
+            dist.barrier(group=group)
+    return peers.local
+
+
 class PanelExchange:
     """Peer-memory exchange area of the distributed factorisation (one NVSwitch node, world <= 8).
 

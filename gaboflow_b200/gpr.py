@@ -55,6 +55,19 @@ class GPR(Parameterized):
         self._L = None
         self._V = None
 
+    def set_data(self, X, Y) -> None:
+        """Replace the training set (what GPflow 0.5 does by assigning ``m.X`` / ``m.Y``) and drop every cached quantity."""
+        self.X = to_device(X)
+        Yd = to_device(Y)
+        if Yd.dim() == 1:
+            Yd = Yd.unsqueeze(1)
+        if Yd.shape[0] != self.X.shape[0]:
+            Yd = Yd.t().contiguous()
+        self.Y = Yd.contiguous()
+        self._cache_key = None
+        self._V = None
+        self._xprep_tag = None
+
     # ---- state ------------------------------------------------------------------------------------
     def _mean_const(self) -> float:
         return float(self.mean_function.c)
@@ -65,14 +78,30 @@ class GPR(Parameterized):
         return (kp, extra, float(self.likelihood.variance), self._mean_const(), self.X.data_ptr(), self.X._version,
                 self.Y.data_ptr(), self.Y._version)
 
+    def _kern_input(self):
+        """What goes into ``kern.K`` for the training set: X itself, or -- for kernels with a per-point preparation (the SPD
+        pair kernels) -- that preparation, computed once per training set instead of on every ``K(X, X*)``."""
+        prepare = getattr(self.kern, 'prepare', None)
+        if prepare is None:
+            return self.X
+        tag = (self.X.data_ptr(), self.X._version, tuple(self.X.shape))
+        if getattr(self, '_xprep_tag', None) != tag:
+            self._xprep = prepare(self.X)             # raises ValueError on a non-SPD input (ops.SpdPrep.check)
+            self._xprep_tag = tag
+        return self._xprep
+
     def _factorise(self):
         key = self._key()
         if self._cache_key == key and self._L is not None:
             return self._L, self._V
+        # the buffer is about to be overwritten: whatever happens below, the old factor is gone (a failed Cholesky must not
+        # leave the previous key pointing at a half-factored matrix)
+        self._cache_key = None
+        self._V = None
         n = int(self.X.shape[0])
         if self._L is None or self._L.shape[0] != n:
             self._L = self._factor_view(n)
-        self.kern.K(self.X, uplo='lower', out=self._L)
+        self.kern.K(self._kern_input(), uplo='lower', out=self._L)
         ops.potrf_(self._L, float(self.likelihood.variance), check=True)
         V = (self.Y - self._mean_const()).contiguous()
         ops.trsm_(self._L, V, trans=False)
@@ -104,7 +133,7 @@ class GPR(Parameterized):
         n, P = int(V.shape[0]), int(V.shape[1])
         xn = to_device(x_new).reshape(1, -1)
         yn = to_device(y_new).reshape(1, P)
-        k = self.kern.K(self.X, xn).contiguous()                      # [n, 1]
+        k = self.kern.K(self._kern_input(), xn).contiguous()          # [n, 1]
         kss = float(self.kern.Kdiag(xn)[0].item()) + float(self.likelihood.variance)
         ops.trsm_(L, k, trans=False)                                  # l
         d2 = kss - float((k * k).sum().item())
@@ -129,7 +158,7 @@ class GPR(Parameterized):
     def build_predict(self, Xnew, full_cov=False):
         L, V = self._factorise()
         Xn = to_device(Xnew)
-        A = self.kern.K(self.X, Xn)                    # [N, M]
+        A = self.kern.K(self._kern_input(), Xn)        # [N, M]
         ops.trsm_(L, A, trans=False)
         kd = self.kern.Kdiag(Xn)
         mean, var = ops.gp_predict(A, V, kd, self._mean_const())
@@ -175,7 +204,7 @@ class GPR(Parameterized):
         bname = self.kern.beta_param_name()
         if bname is not None:
             Kf = Zt                                                    # reuse: noise-free Gram, lower tiles
-            self.kern.K(self.X, uplo='lower', out=Kf)
+            self.kern.K(self._kern_input(), uplo='lower', out=Kf)
             grads['kern.' + bname] = float(ops.gp_grad_beta(Kf, neg_kinv, alpha, v, self.kern.beta_effective()).item())
         return grads
 

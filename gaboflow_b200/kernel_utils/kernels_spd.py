@@ -5,8 +5,9 @@ constructor arguments, Param attributes and methods.  Inputs are Mandel vectors 
 
 Structure (instead of the reference's per-PAIR inverse / sqrtm / SVD / logm on N1 x N2 x d x d tensors):
   per point, once  : Mandel -> S, Cholesky whitening W = L^-1, log det, Mandel(logm S)   (gabo_spd_prep_f64)
-  per pair         : eigenvalues of W_i S_j W_i^T by in-register Jacobi (affine-invariant), a d x d Cholesky of
-                     (S_i+S_j)/2 (Stein), or the DMMA squared-distance tile kernel (Frobenius / Log-Euclidean).
+  per pair         : eigenvalues of W_i S_j W_i^T in registers -- Householder, FP32 QL starts, validated FP64 Newton
+                     refinement, FP64 QL / Jacobi when that does not validate -- (affine-invariant), an LDL^T of
+                     S_i + S_j (Stein), or the DMMA squared-distance tile kernel (Frobenius / Log-Euclidean).
 """
 from __future__ import annotations
 
@@ -39,9 +40,11 @@ class _SpdPairKernel(Kern):
     def _beta_eff(self):
         raise NotImplementedError
 
-    def prepare(self, X):
-        """Per-point preparation; reusable across K calls when X is unchanged (e.g. the training set)."""
-        return ops.spd_prep(to_device(X), self.matrix_dim, **self._need)
+    def prepare(self, X, check=True):
+        """Per-point preparation; reusable across K calls when X is unchanged (e.g. the training set).  With ``check`` (one
+        host sync) a non-SPD input raises ValueError naming the matrix instead of propagating NaN rows into the Gram."""
+        prep = ops.spd_prep(to_device(X), self.matrix_dim, **self._need)
+        return prep.check() if check else prep
 
     def K(self, X, X2=None, uplo='mirror', out=None, row0=0, row1=None):
         p1 = X if isinstance(X, ops.SpdPrep) else self.prepare(X)
@@ -150,8 +153,11 @@ class SpdLogEuclideanGaussianKernel(_SpdSqdistKernel):
     """``variance * exp(-beta * ||logm X - logm X2||_F^2)`` (``kernels_spd_tf.py:561-658``), with logm taken once per
     point in FP64 (the reference recomputes it per pair in complex64, :634)."""
 
+    def prepare(self, X, check=True):
+        prep = ops.spd_prep(to_device(X), self.matrix_dim, want_S=False, want_W=False, want_logdet=False, want_logm=True)
+        return prep.check() if check else prep
+
     def _features(self, X):
         if isinstance(X, ops.SpdPrep):
             return X.logm
-        return ops.spd_prep(to_device(X), self.matrix_dim, want_S=False, want_W=False, want_logdet=False,
-                            want_logm=True).logm
+        return self.prepare(X).logm

@@ -169,6 +169,21 @@ def spd_gram(kind: int, p1: SpdPrep, p2: Optional[SpdPrep] = None, beta: float =
     return out
 
 
+def spd_gram_cyclic(kind: int, p: SpdPrep, bases, ldk: int, world: int, rank: int, beta: float = 1.0,
+                    variance: float = 1.0) -> None:
+    """Block-cyclic symmetric SPD Gram with peer-memory stores (gabo_spd_gram_cyclic_f64).  `bases`: list of `world` device
+    pointers (ints), entry r = base of rank r's local [local_rows, ldk] buffer as mapped in this process."""
+    import ctypes as C
+    if kind != SPD_STEIN and (p.W is None or p.Lt is None):
+        raise ValueError('the affine-invariant kinds need W and Lt (spd_prep want_W / want_Lt)')
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    arr = (C.c_void_p * world)(*[C.c_void_p(int(b)) for b in bases])
+    st = _lib.lib().gabo_spd_gram_cyclic_f64(int(kind), p.d, ptr(p.W), ptr(p.S), ptr(p.logdet), ptr(p.Lt),
+                                             int(p.Lt.stride(0)) if p.Lt is not None else 0, p.n, float(beta), float(variance),
+                                             C.cast(arr, C.c_void_p), int(ldk), int(world), int(rank), _stream())
+    _lib.check('gabo_spd_gram_cyclic_f64', st)
+
+
 def spd_stein_kdiag(p: SpdPrep, beta: float, variance: float) -> torch.Tensor:
     out = torch.empty((p.n,), dtype=torch.float64, device=p.info.device)
     st = _lib.lib().gabo_spd_stein_kdiag_f64(p.logdet.data_ptr(), p.n, float(beta), float(variance), out.data_ptr(), _stream())

@@ -119,6 +119,17 @@ int gabo_spd_gram_f64(int kind, int d,
                       int symmetric, double beta, double variance,
                       double* K, int64_t ldk, int64_t row0, int64_t row1, int uplo,
                       gabo_stream_t stream);
+/* gabo_spd_gram_cyclic_f64: the symmetric SPD Gram K(X, X) of the kinds above, distributed over the GPUs of one node by
+ *   512-row panels, 1-D block-cyclic (panel P on rank P % world, local slot P / world -- the layout the distributed
+ *   Cholesky consumes).  Every rank passes the same per-point data (replicated: 4.7 MB at N = 16384, d = 6); rank `rank`
+ *   evaluates its round-robin share of the lower 32 x 128 blocks -- so the triangular work is balanced whatever the panel
+ *   ownership -- and stores each block AND its mirror image straight into the HBM of the ranks that own those rows
+ *   (K_bases_host: HOST array of `world` device pointers, entry r = base of rank r's [local_rows, ldk] buffer as mapped in
+ *   this process: own memory or CUDA IPC peer mappings, i.e. NVLink stores issued from the epilogue; no collective).
+ *   Callers synchronise (stream + barrier, or a flag handshake) before reading their rows. */
+int gabo_spd_gram_cyclic_f64(int kind, int d, const double* W1, const double* S1, const double* logdet1,
+                             const double* L1t, int64_t ldt, int64_t n, double beta, double variance,
+                             double* const* K_bases_host, int64_t ldk, int world, int rank, gabo_stream_t stream);
 /* SpdSteinGaussianKernel.Kdiag = diag_part(K(X)) (kernels_spd_tf.py:129) = variance*exp(beta*logdet[i]). */
 int gabo_spd_stein_kdiag_f64(const double* logdet, int64_t n, double beta, double variance,
                              double* out, gabo_stream_t stream);

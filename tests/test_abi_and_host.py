@@ -102,7 +102,7 @@ def test_bench_reference_arm_runs_small():
     import subprocess
     import sys
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0',
-                          '--n-gram', '2048', '--n-chol', '1024', '--ref-gram-rows', '256', '--ref-chol-n', '512'],
+                          '--n-gram', '2048', '--n-chol', '1024', '--ref-gram-rows', '256', '--ref-chol-n', '512', '--ref-spd-rows', '2'],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr
     line = json.loads(out.stdout.strip().splitlines()[-1])

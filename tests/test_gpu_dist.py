@@ -92,6 +92,32 @@ def test_cyclic_mirrored_gram_single_process(cuda, world, mod):
         assert torch.equal(bufs[r], full[rows])
 
 
+@pytest.mark.parametrize('kind_name', ['ai_gauss', 'ai_laplace', 'stein'])
+@pytest.mark.parametrize('world', [1, 2, 3, 8])
+def test_cyclic_spd_gram_single_process(cuda, world, kind_name):
+    """gabo_spd_gram_cyclic_f64 with all `world` ranks emulated on one GPU (every 'peer' buffer is local memory): same kernel
+    and addressing as the NVLink run, launched once per rank.  Every entry is written exactly once (NaN pre-fill), with the
+    bits of the single-GPU mirrored Gram; n is not a multiple of the panel (ragged last panel)."""
+    from gaboflow_b200 import ops
+    from gaboflow_b200.dist import BlockCyclic
+    from oracle import gabo_oracle as orc
+    n = 512 * 3 + 200
+    kind, beta = {'ai_gauss': (ops.SPD_AI_GAUSSIAN, 1.0), 'ai_laplace': (ops.SPD_AI_LAPLACE, 0.7), 'stein': (ops.SPD_STEIN, 3.0)}[kind_name]
+    prep = ops.spd_prep(torch.from_numpy(orc.synth_spd_mandel(n, 6, seed=31)).cuda(), 6)
+    lays = [BlockCyclic(n, 512, world, r) for r in range(world)]
+    bufs = [torch.full((max(l.local_rows, 1), n), float('nan'), dtype=torch.float64, device='cuda') for l in lays]
+    ptrs = [b.data_ptr() for b in bufs]
+    for r in range(world):
+        ops.spd_gram_cyclic(kind, prep, ptrs, n, world, r, beta=beta, variance=1.2)
+    torch.cuda.synchronize()
+    full = ops.spd_gram(kind, prep, None, beta=beta, variance=1.2, uplo='mirror')
+    for r in range(world):
+        if lays[r].local_rows == 0:
+            continue
+        rows = lays[r].global_rows().cuda()
+        assert torch.equal(bufs[r][:lays[r].local_rows], full[rows])
+
+
 def test_flag_signal_and_stream_wait(cuda):
     """gabo_flag_signal / gabo_flag_wait_geq: a stream stalled on a flag resumes when another stream raises it."""
     from gaboflow_b200 import ops

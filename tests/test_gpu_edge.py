@@ -102,3 +102,37 @@ def test_empty_and_tiny(cuda):
     ops.potrf_(L, 0.0)
     ops.trsm_(L, b)
     assert abs(float(L.item()) - np.sqrt(2.0)) < 1e-15 and abs(float(b.item()) - 4.0 / np.sqrt(2.0)) < 1e-15
+
+
+def test_gpr_failed_cholesky_does_not_leave_stale_cache(cuda):
+    """factorise(ok) -> factorise(non-PD, raises) -> factorise(first parameters again) must refactorise; the
+    buffer holds a half-factored matrix after the failure and the old cache key may not survive it."""
+    from gaboflow_b200 import GPR, SphereGaussianKernel
+    X = orc.synth_sphere(300, 3, seed=12)
+    y = np.random.default_rng(13).standard_normal((300, 1))
+    k = SphereGaussianKernel(3, range(3), beta_min=6.5, beta=1.0)
+    m = GPR(X, y, kern=k)
+    m.likelihood.variance = 1e-3
+    ll0 = m.compute_log_likelihood()
+    mean0, var0 = m.predict_f(X[:5])
+    k.variance = -1.0                                       # K + s2 I is negative definite: the Cholesky must report it
+    with pytest.raises(np.linalg.LinAlgError):
+        m.compute_log_likelihood()
+    k.variance = 1.0                                        # back to the parameters of the cached factor
+    assert abs(m.compute_log_likelihood() - ll0) <= 1e-12 * abs(ll0)
+    mean1, var1 = m.predict_f(X[:5])
+    assert np.array_equal(mean0, mean1) and np.array_equal(var0, var1)
+
+
+def test_spd_kernel_classes_reject_non_spd_input(cuda):
+    """the per-point Cholesky info is read on the host-facing paths; a non-SPD matrix raises instead of
+    silently producing NaN rows."""
+    from gaboflow_b200 import GPR, SpdAffineInvariantGaussianKernel, SpdLogEuclideanGaussianKernel, SpdSteinGaussianKernel
+    X = orc.synth_spd_mandel(20, 3, seed=1)
+    X[7, :3] = [-1.0, 1.0, 1.0]
+    for k in (SpdAffineInvariantGaussianKernel(6, range(6), beta_min=0.5), SpdLogEuclideanGaussianKernel(6, range(6)),
+              SpdSteinGaussianKernel(6, range(6), beta=1.5)):
+        with pytest.raises(ValueError, match='matrix 7'):
+            k.compute_K_symm(X)
+        with pytest.raises(ValueError, match='matrix 7'):
+            GPR(X, np.zeros((20, 1)), kern=k).compute_log_likelihood()
