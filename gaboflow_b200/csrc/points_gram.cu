@@ -538,10 +538,20 @@ int points_gram_impl(int kind, const Tin* X, int64_t n1, int64_t ldx, const Tin*
 
 }  // namespace gabo
 
+namespace gabo {
+size_t points_gram_f32_tc_workspace_bytes(int64_t n1, int64_t n2, int dim);   // points_gram_f32_tc.cu
+bool points_gram_f32_tc_supported(int dim);
+}
+
 extern "C" size_t gabo_points_gram_workspace_bytes(int64_t n1, int64_t n2, int dim) {
     if (n1 < 0 || n2 < 0 || dim < 1) return 0;
     gabo::PackPlan pl = gabo::make_plan(n1, n2, dim);
-    return pl.bytesA + pl.bytesNorm1 + pl.bytesB + pl.bytesNorm2;
+    size_t need = pl.bytesA + pl.bytesNorm1 + pl.bytesB + pl.bytesNorm2;
+    if (gabo::points_gram_f32_tc_supported(dim)) {        // the FP32 tensor-core path packs hi / lo TF32 planes
+        const size_t tc = gabo::points_gram_f32_tc_workspace_bytes(n1, n2, dim);
+        if (tc > need) need = tc;
+    }
+    return need;
 }
 
 extern "C" int gabo_points_gram_f64(int kind, const double* X, int64_t n1, int64_t ldx, const double* X2, int64_t n2,

@@ -1,10 +1,17 @@
-// FP32 mode of the point-set Gram kernel (north_star: Gram entries within 1e-5 relative in FP32 mode).
-// Same contract as gabo_points_gram_f64 (reference sphere_utils_tf.py:11-60 + kernels_sphere_tf.py:59-88,179-204 and the
-// pair stage of kernels_spd_tf.py:510-533,618-641), with float inputs and outputs: half the HBM write traffic, FP32
-// FFMA inner products (128x128 tile, 8x8 outputs per thread) and the fast FP32 acos/exp in the epilogue.
+// FP32 mode of the point-set Gram kernel (north_star: Gram entries within 1e-5 relative in FP32 mode): entry point and the
+// SIMT fallback.  Same contract as gabo_points_gram_f64 (reference sphere_utils_tf.py:11-60 + kernels_sphere_tf.py:59-88,
+// 179-204 and the pair stage of kernels_spd_tf.py:510-533,618-641), with float inputs and outputs.  Point dimensions up to 56
+// (every configuration of BASELINE.json) run on the tensor cores (points_gram_f32_tc.cu); larger ones, or GABO_F32_SIMT=1, on
+// the FFMA kernel below (128x128 tile, 8x8 outputs per thread, libm acosf / expf).
+#include <cstdlib>
 #include "gabo_common.cuh"
 
 namespace gabo {
+// tensor-core path (points_gram_f32_tc.cu): tcgen05.mma kind::tf32, three-term split, accumulators in TMEM
+bool points_gram_f32_tc_supported(int dim);
+int points_gram_f32_tc(int kind, const float* X, int64_t n1, int64_t ldx, const float* X2, int64_t n2, int64_t ldx2, int dim,
+                       float beta, float variance, float* K, int64_t ldk, int64_t row0, int64_t row1, int uplo, bool symmetric,
+                       void* workspace, size_t workspace_bytes, cudaStream_t stream);
 namespace {
 
 constexpr int FT = 128;     // tile side
@@ -129,7 +136,6 @@ extern "C" int gabo_points_gram_f32(int kind, const float* X, int64_t n1, int64_
                                     int64_t row0, int64_t row1, int uplo, void* workspace, size_t workspace_bytes,
                                     gabo_stream_t stream) {
     using namespace gabo;
-    (void)workspace; (void)workspace_bytes;
     if (kind < GABO_SPHERE_GAUSSIAN || kind > GABO_SQDIST_GAUSSIAN) return -1;
     if (n1 < 0) return -3;
     if (n1 == 0) return 0;
@@ -148,6 +154,10 @@ extern "C" int gabo_points_gram_f32(int kind, const float* X, int64_t n1, int64_
     if (uplo != GABO_FULL && !symmetric) return -15;
     if (uplo == GABO_SYMM_MIRROR && !(row0 == 0 && row1 == n1)) return -15;
     if (row1 == row0 || n2 == 0) return 0;
+    static const bool force_simt = (getenv("GABO_F32_SIMT") != nullptr);
+    if (points_gram_f32_tc_supported(dim) && !force_simt)
+        return points_gram_f32_tc(kind, X, n1, ldx, symmetric ? nullptr : X2, n2, ldx2, dim, beta, variance, K, ldk, row0, row1, uplo,
+                                  symmetric, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     GramParamsF32 p;
     p.X = X; p.ldx = ldx; p.X2 = X2; p.ldx2 = ldx2; p.K = K; p.ldk = ldk; p.n1 = n1; p.n2 = n2; p.row0 = row0; p.row1 = row1;
     p.dim = dim; p.kind = kind; p.uplo = uplo; p.symmetric = symmetric ? 1 : 0;

@@ -348,3 +348,59 @@ def test_spd_non_spd_input_reports(cuda):
     assert info[3] > 0 and np.all(np.delete(info, 3) == 0)
     K = ops.spd_gram(ops.SPD_AI_GAUSSIAN, p).cpu().numpy()
     assert np.all(np.isnan(K[3, [0, 1, 2, 4]])) and np.all(np.isfinite(np.delete(np.delete(K, 3, 0), 3, 1)))
+
+
+# ----------------------------------------------------------------------------------------------- FP32 tensor-core mode
+@pytest.mark.parametrize('kind', ['gauss', 'laplace', 'sqdist'])
+@pytest.mark.parametrize('n1,n2,dim', [(1, 1, 3), (5, 7, 3), (127, 129, 3), (130, 257, 51), (300, 1100, 20), (1500, 1500, 56)])
+def test_fp32_tensor_core_gram_vs_oracle(cuda, kind, n1, n2, dim):
+    """FP32 mode (tcgen05.mma kind::tf32, three-term split, TMEM accumulators): every kind, ragged sizes, cross and symmetric
+    Grams, all uplo modes and row blocks, against the FP64 oracle at the north_star tolerance of this mode (1e-5)."""
+    from gaboflow_b200 import ops
+    if kind == 'sqdist':
+        rng = np.random.default_rng(n1 + dim)
+        X, X2 = rng.standard_normal((n1, dim)) * 0.6, rng.standard_normal((n2, dim)) * 0.6
+        d2 = ((X[:, None, :] - X2[None, :, :]) ** 2).sum(-1)
+        ref = 1.3 * np.exp(-0.7 * d2)
+        refs = 1.3 * np.exp(-0.7 * ((X[:, None, :] - X[None, :, :]) ** 2).sum(-1))
+        code, beta = ops.SQDIST_GAUSSIAN, 0.7
+    else:
+        X, X2 = orc.synth_sphere(n1, dim, seed=3), orc.synth_sphere(n2, dim, seed=4)
+        f = orc.sphere_gaussian_K if kind == 'gauss' else orc.sphere_laplace_K
+        code, beta = (ops.SPHERE_GAUSSIAN, 2.0) if kind == 'gauss' else (ops.SPHERE_LAPLACE, 1.5)
+        ref, refs = f(X, X2, beta=beta, variance=1.3), f(X, beta=beta, variance=1.3)
+    Xd, X2d = torch.from_numpy(X.astype(np.float32)).cuda(), torch.from_numpy(X2.astype(np.float32)).cuda()
+    # the inputs were rounded to FP32: the honest reference is the oracle on those rounded inputs
+    if kind != 'sqdist':
+        Xr, X2r = Xd.cpu().numpy().astype(np.float64), X2d.cpu().numpy().astype(np.float64)
+        f = orc.sphere_gaussian_K if kind == 'gauss' else orc.sphere_laplace_K
+        ref, refs = f(Xr, X2r, beta=beta, variance=1.3), f(Xr, beta=beta, variance=1.3)
+    got = ops.points_gram(code, Xd, X2d, beta=beta, variance=1.3).cpu().numpy().astype(np.float64)
+
+    def tol_of(Xa, Xb):
+        """1e-5, plus what an FP32 inner product (error ~4e-7) does to the entry: |dlog K / dt| = 2 beta d / sin d (Gaussian),
+        beta / sin d (Laplace) -- unbounded towards antipodal (and, for Laplace, coincident) points, in ANY FP32 evaluation."""
+        if kind == 'sqdist':
+            return 1e-5 + 2 * beta * 4e-7 * (np.sum(Xa * Xa, 1)[:, None] + np.sum(Xb * Xb, 1)[None, :])
+        t = np.clip(Xa @ Xb.T, -1, 1)
+        d = np.arccos(t)
+        sens = (2 * beta * d if kind == 'gauss' else beta) / np.maximum(np.sqrt(1 - t * t), 1e-6)
+        return 1e-5 + 4e-7 * sens
+
+    Xa, Xb = Xd.cpu().numpy().astype(np.float64), X2d.cpu().numpy().astype(np.float64)
+    m = ref > 1e-30
+    assert got.shape == ref.shape and np.all((np.abs(got - ref) / np.maximum(ref, 1e-300))[m] < tol_of(Xa, Xb)[m])
+    full = ops.points_gram(code, Xd, None, beta=beta, variance=1.3, uplo='full')
+    mir = ops.points_gram(code, Xd, None, beta=beta, variance=1.3, uplo='mirror')
+    off = offdiag_mask(n1) & (refs > 1e-30)
+    if off.any():
+        assert np.all((np.abs(full.cpu().numpy().astype(np.float64) - refs) / np.maximum(refs, 1e-300))[off] < tol_of(Xa, Xa)[off])
+    assert torch.equal(mir, mir.t()) and torch.equal(torch.tril(mir), torch.tril(full))
+    assert bool((mir.diagonal() == np.float32(1.3)).all())
+    low = torch.full((n1, n1), float('nan'), dtype=torch.float32, device='cuda')
+    ops.points_gram(code, Xd, None, beta=beta, variance=1.3, uplo='lower', out=low)
+    assert torch.equal(torch.tril(low), torch.tril(full))
+    if n1 > 256:
+        parts = [ops.points_gram(code, Xd, None, beta=beta, variance=1.3, uplo='full', row0=r0, row1=min(r0 + 256, n1))
+                 for r0 in range(0, n1, 256)]
+        assert torch.equal(torch.cat(parts, 0), full)
