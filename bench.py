@@ -29,7 +29,7 @@ lower 32 x 128 blocks are dealt round-robin to the ranks and stored, with their 
 Completion is a stream-ordered flag handshake.  potrf: right-looking over panels with one panel of look-ahead; the block
 column reaches every rank by NVLink stores from the row-solve kernel, the diagonal block by copy engines, ordering by
 cuStreamWaitValue32 flags (no collective inside the loop; GABO_DIST_P2P=0 selects the NCCL broadcast + all-gather version).
-solve / loglik: 512-vector exchange per panel, one all-reduce.  Times are CUDA events, max over ranks.
+solve / loglik: each solved 512-block of x is pushed to the peers with a flag (one launch), one all-reduce.  Times are CUDA events, max over ranks.
 """
 from __future__ import annotations
 
@@ -232,7 +232,8 @@ def run_ours(args):
 
     from gaboflow_b200.dist import (BlockCyclic, PeerBuffers, gram_block_cyclic_mirrored, potrf_block_cyclic_,
                                     PanelExchange, potrf_block_cyclic_p2p_, default_recompute_frac256,
-                                    solve_lower_block_cyclic_, gp_loglik_block_cyclic, spd_gram_block_cyclic)
+                                    solve_lower_block_cyclic_, solve_lower_block_cyclic_p2p_, gp_loglik_block_cyclic,
+                                    spd_gram_block_cyclic)
     PANEL = 512
     lay = BlockCyclic(N, PANEL, world, rank)
     rows = lay.local_rows
@@ -315,7 +316,10 @@ def run_ours(args):
             if events is not None:
                 events[2].record()
             V.copy_(yd[y_rows])
-            solve_lower_block_cyclic_(K, V, lay, n_factor=NC, winv_store=winv)
+            if xch is not None:
+                solve_lower_block_cyclic_p2p_(K, V, lay, xch, n_factor=NC, winv_store=winv)
+            else:
+                solve_lower_block_cyclic_(K, V, lay, n_factor=NC, winv_store=winv)
             ll_val_host[0] = gp_loglik_block_cyclic(K, V, lay, n_factor=NC)   # all-reduce + device -> host read
             if events is not None:
                 events[3].record()
@@ -579,6 +583,8 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if xch is not None:
         xch.close()
+    if peers is not None:            # --no-spd: the sphere buffers are still mapped (collective close, as on the other ranks)
+        peers.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -589,6 +595,7 @@ def run_spd_section(args, torch, dist, ops, orc, dev, world, rank, xch, reduce_m
                     gp_loglik_block_cyclic, SpdAffineInvariantGaussianKernel):
     """BASELINE.json configs[4]: N = 16,384 SPD matrices on S^6_++ -- affine-invariant (timed, roofline, parity), Stein and
     Log-Euclidean Grams, then Cholesky + log-likelihood of K_AI + sigma^2 I.  Returns the `spd` object of the JSON line."""
+    from gaboflow_b200.dist import solve_lower_block_cyclic_p2p_
     n, d = args.n_spd, SPD_D
     steps = args.steps
     Xm_np = orc.synth_spd_mandel(n, d, seed=SPD_SEED)
@@ -705,7 +712,10 @@ def run_spd_section(args, torch, dist, ops, orc, dev, world, rank, xch, reduce_m
             else:
                 info[0] = potrf_block_cyclic_(K, lay, SIGMA2, n_factor=n, winv_store=winv)
             Vv = ys[grow.to(dev)].clone()
-            solve_lower_block_cyclic_(K, Vv, lay, n_factor=n, winv_store=winv)
+            if use_xch is not None:
+                solve_lower_block_cyclic_p2p_(K, Vv, lay, use_xch, n_factor=n, winv_store=winv)
+            else:
+                solve_lower_block_cyclic_(K, Vv, lay, n_factor=n, winv_store=winv)
             ll[0] = gp_loglik_block_cyclic(K, Vv, lay, n_factor=n)
 
     t_fac = timed(factor_and_loglik, max(2, min(steps, 3)))

@@ -28,7 +28,8 @@ SIGNATURES = {
     'gabo_potrf_f64': (i32, [i64, vp, i64, f64, vp, vp, sz, vp]),
     'gabo_trsm_workspace_bytes': (sz, [i64, i64]),
     'gabo_trsm_f64': (i32, [i32, i64, i64, vp, i64, vp, i64, vp, sz, vp]),
-    'gabo_trsm_winv_f64': (i32, [i32, i64, i64, vp, i64, vp, vp, i64, vp]),
+    'gabo_trsm_winv_workspace_bytes': (sz, []),
+    'gabo_trsm_winv_f64': (i32, [i32, i64, i64, vp, i64, vp, vp, i64, vp, sz, vp]),
     'gabo_logdet_f64': (i32, [i64, vp, i64, vp, vp]),
     'gabo_gp_loglik_f64': (i32, [i64, i64, vp, i64, vp, i64, vp, vp]),
     'gabo_gp_grad_beta_workspace_bytes': (sz, []),
@@ -56,7 +57,9 @@ SIGNATURES = {
     'gabo_trsm_right_scatter_f64': (i32, [i64, i64, vp, i64, vp, vp, i64, vp, i32, i64, i64, i32, i32, vp, sz, vp]),
     'gabo_flag_signal': (i32, [vp, i32, C.c_uint32, vp]),
     'gabo_flag_wait_geq': (i32, [vp, C.c_uint32, vp]),
+    'gabo_push_signal_f64': (i32, [vp, i64, vp, vp, i32, C.c_uint32, vp]),
     'gabo_copy_async': (i32, [vp, vp, sz, vp]),
+    'gabo_solve_cyclic_p2p_f64': (i32, [i64, i32, i32, i32, vp, i64, vp, i64, i64, vp, vp, vp, C.c_uint32, vp, sz, vp]),
     'gabo_syrk_cyclic_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, i32, vp]),
     'gabo_solve_update_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]),
 }

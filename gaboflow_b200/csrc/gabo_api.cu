@@ -150,6 +150,44 @@ extern "C" int gabo_flag_signal(uint32_t* const* flags_host, int n, uint32_t val
     return 0;
 }
 
+// Small payload + flag in one launch: copies `count` doubles from src into each of the n destination buffers (peers' memory)
+// and then raises the n flags, after a system-scope fence.  The substitution of the distributed solve publishes each solved
+// 512-block this way: one launch on the critical path instead of n copy-engine transfers + a signal kernel.
+namespace {
+struct PushList { double* dst[GABO_MAX_PEERS]; uint32_t* f[GABO_MAX_PEERS]; int n; };
+__global__ void __launch_bounds__(256) push_signal_kernel(const double* __restrict__ src, int64_t count, const PushList pl, uint32_t value) {
+    for (int p = 0; p < pl.n; ++p)
+        for (int64_t i = threadIdx.x; i < count; i += blockDim.x) pl.dst[p][i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < pl.n) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(pl.f[threadIdx.x]), "r"(value) : "memory");
+    }
+}
+}  // namespace
+
+extern "C" int gabo_push_signal_f64(const double* src, int64_t count, double* const* dst_host, uint32_t* const* flags_host, int n,
+                                    uint32_t value, gabo_stream_t stream_) {
+    if (count < 0) return -2;
+    if (n < 0 || n > GABO_MAX_PEERS) return -5;
+    if (n == 0) return 0;
+    if (src == nullptr && count > 0) return -1;
+    if (dst_host == nullptr) return -3;
+    if (flags_host == nullptr) return -4;
+    PushList pl;
+    pl.n = n;
+    for (int i = 0; i < n; ++i) {
+        if (dst_host[i] == nullptr) return -3;
+        if (flags_host[i] == nullptr) return -4;
+        pl.dst[i] = dst_host[i];
+        pl.f[i] = flags_host[i];
+    }
+    push_signal_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream_)>>>(src, count, pl, value);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int gabo_flag_wait_geq(const uint32_t* flag, uint32_t value, gabo_stream_t stream_) {
     if (flag == nullptr) return -1;
     PFN_waitValue32 fn = get_wait_value32();

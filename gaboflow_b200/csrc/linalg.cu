@@ -827,11 +827,20 @@ extern "C" int gabo_potrf_f64(int64_t n, double* A, int64_t lda, double sigma2, 
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
+namespace gabo {
+// one right-hand side: a single persistent kernel (csrc/trsv.cu)
+size_t trsv_persistent_workspace_bytes();
+int trsv_persistent(bool trans, int64_t n, const double* L, int64_t ldl, const double* Winv, double* x, int64_t ldb,
+                    void* scratch, cudaStream_t stream);
+}
+
+// inverses of the 128 x 128 diagonal blocks, then 256 B for the progress counter of the one-right-hand-side kernel
 extern "C" size_t gabo_trsm_workspace_bytes(int64_t n, int64_t nrhs) {
     (void)nrhs;
-    if (n <= 0) return 256;
-    return align256((size_t)ceil_div64(n, NB_IN) * NB_IN * NB_IN * sizeof(double));
+    if (n <= 0) return 512;
+    return align256((size_t)ceil_div64(n, NB_IN) * NB_IN * NB_IN * sizeof(double)) + 256;
 }
+extern "C" size_t gabo_trsm_winv_workspace_bytes(void) { return 256; }
 
 template <int NRHS>
 static int gemv_dispatch(bool trans, const double* Lp, int64_t ldl, int64_t m, int jb, const double* X, int64_t ldx,
@@ -853,9 +862,10 @@ extern "C" int gabo_trsm_f64(int trans, int64_t n, int64_t nrhs, const double* L
 // Same, with the inverses of the 128x128 diagonal blocks of L supplied (Winv_all [ceil(n/128)][128][128], as written by
 // gabo_potrf_diag_f64): no inversion kernel and no workspace.
 extern "C" int gabo_trsm_winv_f64(int trans, int64_t n, int64_t nrhs, const double* L, int64_t ldl, const double* Winv_all,
-                                  double* B, int64_t ldb, gabo_stream_t stream_) {
+                                  double* B, int64_t ldb, void* scratch, size_t scratch_bytes, gabo_stream_t stream_) {
     if (Winv_all == nullptr) return -6;
-    const int rc = trsm_impl(trans, n, nrhs, L, ldl, Winv_all, B, ldb, nullptr, 0, stream_);
+    if (scratch != nullptr && scratch_bytes < 256) return -10;
+    const int rc = trsm_impl(trans, n, nrhs, L, ldl, Winv_all, B, ldb, scratch, scratch_bytes, stream_);
     return (rc <= -6 && rc > GABO_ERR_CUDA) ? rc - 1 : rc;
 }
 
@@ -883,6 +893,14 @@ static int trsm_impl(int trans, int64_t n, int64_t nrhs, const double* L, int64_
         trtri_blocks_kernel<<<(unsigned)nblk, 512, POTF2_SMEM, stream>>>(L, ldl, n, static_cast<double*>(workspace));
         GABO_LAUNCH_CHECK();
         Wall = static_cast<const double*>(workspace);
+    }
+    // one right-hand side: the whole substitution in ONE persistent kernel (csrc/trsv.cu) instead of 2 launches per block
+    {
+        static const bool chain = (getenv("GABO_TRSV_CHAIN") != nullptr);    // A/B switch: the round-1 launch chain
+        void* scratch = nullptr;
+        if (Winv_pre == nullptr) scratch = static_cast<unsigned char*>(workspace) + align256((size_t)nblk * NB_IN * NB_IN * sizeof(double));
+        else if (workspace != nullptr && workspace_bytes >= 256) scratch = workspace;
+        if (nrhs == 1 && scratch != nullptr && !chain) return gabo::trsv_persistent(trans != 0, n, L, ldl, Wall, B, ldb, scratch, stream);
     }
     const unsigned rhs_chunks = (unsigned)ceil_div64(nrhs, CH);
     for (int64_t b = 0; b < nblk; ++b) {
@@ -1201,6 +1219,56 @@ extern "C" int gabo_syrk_cyclic_f64(int64_t m, int64_t n, int64_t k, const doubl
 
 // y[m, nrhs] -= Lp[m, k] * x[k, nrhs]   (forward-substitution update of the rows this rank owns; nrhs <= 4 uses the
 // HBM-bound GEMV kernel, larger nrhs the DMMA core).
+// Y[m, NRHS] -= Lp[m, k] X[k, NRHS] for a handful of right-hand sides: HBM-bound (Lp is read once), warp per row with the
+// lanes along k (coalesced), X staged in shared memory.  The distributed substitution calls this once per panel and rank with
+// m up to N / world and k = 512; through the DMMA GEMM core (tiles of 64 output columns for ONE column) it took ~80 us.
+namespace gabo {
+namespace {
+template <int NRHS>
+__global__ void __launch_bounds__(256) gemv_wide_kernel(const double* __restrict__ Lp, int64_t ldl, int64_t m, int k,
+                                                        const double* __restrict__ X, int64_t ldx, double* __restrict__ Y,
+                                                        int64_t ldy) {
+    extern __shared__ double sx_wide[];      // [k][NRHS]
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int e = tid; e < k * NRHS; e += 256) {
+        const int kk = e / NRHS, c = e - kk * NRHS;
+        sx_wide[e] = X[(int64_t)kk * ldx + c];
+    }
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (tid >> 5); r < m; r += (int64_t)gridDim.x * 8) {
+        double acc[NRHS];
+#pragma unroll
+        for (int c = 0; c < NRHS; ++c) acc[c] = 0.0;
+        const double* row = Lp + r * ldl;
+        for (int kk = lane; kk < k; kk += 32) {
+            const double l = __ldcs(row + kk);
+#pragma unroll
+            for (int c = 0; c < NRHS; ++c) acc[c] = fma(l, sx_wide[kk * NRHS + c], acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NRHS; ++c) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < NRHS; ++c) Y[r * ldy + c] -= acc[c];
+        }
+    }
+}
+template <int NRHS>
+int launch_gemv_wide(int64_t m, int64_t k, const double* Lp, int64_t ldl, const double* X, int64_t ldx, double* Y, int64_t ldy,
+                     cudaStream_t stream) {
+    int64_t grid = ceil_div64(m, 8);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    gemv_wide_kernel<NRHS><<<(unsigned)grid, 256, (size_t)k * NRHS * sizeof(double), stream>>>(Lp, ldl, m, (int)k, X, ldx, Y, ldy);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+}  // namespace
+}  // namespace gabo
+
 extern "C" int gabo_solve_update_f64(int64_t m, int64_t k, int64_t nrhs, const double* Lp, int64_t ldl, const double* X,
                                      int64_t ldx, double* Y, int64_t ldy, gabo_stream_t stream_) {
     if (m < 0) return -1;
@@ -1214,6 +1282,14 @@ extern "C" int gabo_solve_update_f64(int64_t m, int64_t k, int64_t nrhs, const d
     if (Y == nullptr) return -8;
     if (ldy < nrhs) return -9;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (nrhs <= 4 && k * nrhs * (int64_t)sizeof(double) <= 48 * 1024) {
+        switch (nrhs) {
+            case 1: return gabo::launch_gemv_wide<1>(m, k, Lp, ldl, X, ldx, Y, ldy, stream);
+            case 2: return gabo::launch_gemv_wide<2>(m, k, Lp, ldl, X, ldx, Y, ldy, stream);
+            case 3: return gabo::launch_gemv_wide<3>(m, k, Lp, ldl, X, ldx, Y, ldy, stream);
+            default: return gabo::launch_gemv_wide<4>(m, k, Lp, ldl, X, ldx, Y, ldy, stream);
+        }
+    }
     return launch_gemm(true, false, m, nrhs, k, -1.0, Lp, ldl, X, ldx, false, Y, ldy, false, stream);
 }
 

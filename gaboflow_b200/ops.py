@@ -231,9 +231,15 @@ def trsm_(L_: torch.Tensor, B: torch.Tensor, trans: bool = False, winv_all: Opti
     Lh = _lib.lib()
     if winv_all is not None:
         _req(winv_all, 'winv_all')
+        key = (L_.device.index, 'trsm_winv', torch.cuda.current_stream().cuda_stream)
+        ws = _ws_cache.get(key)
+        if ws is None:
+            ws = torch.empty(256, dtype=torch.uint8, device=L_.device)
+            _ws_cache[key] = ws
         st = Lh.gabo_trsm_winv_f64(1 if trans else 0, n, int(B.shape[1]), L_.data_ptr(), _ld(L_) if n > 1 else 1,
                                    winv_all.data_ptr(), B.data_ptr(),
-                                   max(int(B.stride(0)), int(B.shape[1])) if n > 1 else int(B.shape[1]), _stream())
+                                   max(int(B.stride(0)), int(B.shape[1])) if n > 1 else int(B.shape[1]),
+                                   ws.data_ptr(), ws.numel(), _stream())
         _lib.check('gabo_trsm_winv_f64', st)
         return B
     nbytes = int(Lh.gabo_trsm_workspace_bytes(n, int(B.shape[1])))
@@ -394,6 +400,43 @@ def flag_signal(flag_ptrs, value: int) -> None:
 def flag_wait_geq(flag_ptr: int, value: int) -> None:
     """The current stream stalls (no SM occupied) until the 32-bit flag at ``flag_ptr`` (local memory) is >= value."""
     _lib.check('gabo_flag_wait_geq', _lib.lib().gabo_flag_wait_geq(int(flag_ptr), int(value), _stream()))
+
+
+def solve_cyclic_p2p_(A_loc: torch.Tensor, B_loc: torch.Tensor, n: int, nb: int, world: int, rank: int, winv_ptrs, xarea_ptrs,
+                      flag_ptrs, base: int) -> torch.Tensor:
+    """Distributed forward substitution in one host call (gabo_solve_cyclic_p2p_f64).  winv_ptrs: per panel, the device
+    pointer of the block inverses (0 for panels this rank does not own); xarea_ptrs / flag_ptrs: per rank."""
+    import ctypes as C
+    _req(A_loc, 'A_loc'); _req(B_loc, 'B_loc')
+    key = (A_loc.device.index, 'solve_cyclic', torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        ws = torch.empty(256, dtype=torch.uint8, device=A_loc.device)
+        _ws_cache[key] = ws
+    wv = (C.c_void_p * len(winv_ptrs))(*[C.c_void_p(int(q)) if q else None for q in winv_ptrs])
+    xa = (C.c_void_p * world)(*[int(q) for q in xarea_ptrs])
+    fl = (C.c_void_p * world)(*[int(q) for q in flag_ptrs])
+    st = _lib.lib().gabo_solve_cyclic_p2p_f64(int(n), int(nb), int(world), int(rank), A_loc.data_ptr(), _ldm(A_loc), B_loc.data_ptr(),
+                                              max(int(B_loc.stride(0)), int(B_loc.shape[1])), int(B_loc.shape[1]),
+                                              C.cast(wv, C.c_void_p), C.cast(xa, C.c_void_p), C.cast(fl, C.c_void_p), int(base),
+                                              ws.data_ptr(), ws.numel(), _stream())
+    _lib.check('gabo_solve_cyclic_p2p_f64', st)
+    return B_loc
+
+
+def push_signal(src: torch.Tensor, dst_ptrs, flag_ptrs, value: int) -> None:
+    """Copies the contiguous FP64 tensor ``src`` into each raw device pointer of ``dst_ptrs`` (peers' memory) and then raises
+    the 32-bit flags at ``flag_ptrs`` to ``value`` -- one launch (gabo_push_signal_f64)."""
+    import ctypes as C
+    if not dst_ptrs:
+        return
+    _req(src, 'src')
+    if not src.is_contiguous():
+        raise ValueError('push_signal needs a contiguous source')
+    d = (C.c_void_p * len(dst_ptrs))(*[int(q) for q in dst_ptrs])
+    f = (C.c_void_p * len(flag_ptrs))(*[int(q) for q in flag_ptrs])
+    _lib.check('gabo_push_signal_f64', _lib.lib().gabo_push_signal_f64(src.data_ptr(), int(src.numel()), C.cast(d, C.c_void_p),
+                                                                     C.cast(f, C.c_void_p), len(dst_ptrs), int(value), _stream()))
 
 
 def copy_async(dst_ptr: int, src_ptr: int, nbytes: int) -> None:

@@ -150,9 +150,14 @@ size_t gabo_trsm_workspace_bytes(int64_t n, int64_t nrhs);
 int gabo_trsm_f64(int trans, int64_t n, int64_t nrhs, const double* L, int64_t ldl,
                   double* B, int64_t ldb, void* workspace, size_t workspace_bytes, gabo_stream_t stream);
 /* gabo_trsm_winv_f64: the same solve with the inverses of L's 128 x 128 diagonal blocks supplied
- *   (Winv_all [ceil(n/128)][128][128], e.g. from gabo_potrf_diag_f64): no inversion kernel, no workspace. */
+ *   (Winv_all [ceil(n/128)][128][128], e.g. from gabo_potrf_diag_f64): no inversion kernel.  `scratch`: 256 B of device
+ *   memory (gabo_trsm_winv_workspace_bytes) for the progress counter of the one-right-hand-side kernel; may be NULL, in
+ *   which case nrhs == 1 runs as the launch chain.
+ * With nrhs == 1 both entry points run the whole substitution as ONE persistent kernel: each 128-row block of x is owned by a
+ * resident CTA that streams its block row (or column) of L and consumes the earlier blocks as their owners publish them. */
+size_t gabo_trsm_winv_workspace_bytes(void);
 int gabo_trsm_winv_f64(int trans, int64_t n, int64_t nrhs, const double* L, int64_t ldl, const double* Winv_all,
-                       double* B, int64_t ldb, gabo_stream_t stream);
+                       double* B, int64_t ldb, void* scratch, size_t scratch_bytes, gabo_stream_t stream);
 /* out[0] = sum_i log L_ii  (half the log-determinant of K + sigma^2 I). */
 int gabo_logdet_f64(int64_t n, const double* L, int64_t ldl, double* out, gabo_stream_t stream);
 /* out[0] = -0.5*n*p*log(2 pi) - p*sum_i log L_ii - 0.5*||alpha||_F^2, alpha = L^-1 (y - m) already solved,
@@ -264,7 +269,25 @@ int gabo_trsm_right_scatter_f64(int64_t m, int64_t nb, const double* L, int64_t 
  *   `flag` must be in this device's memory.  gabo_copy_async: cudaMemcpyAsync between local / IPC-mapped buffers. */
 int gabo_flag_signal(uint32_t* const* flags_host, int n, uint32_t value, gabo_stream_t stream);
 int gabo_flag_wait_geq(const uint32_t* flag, uint32_t value, gabo_stream_t stream);
+/* gabo_push_signal_f64: payload + flag in one launch -- copies `count` doubles from src into each of the n buffers
+ *   dst_host[i] (peers' memory) and then, after a system-scope fence, stores `value` into the n flags flags_host[i].  Used by
+ *   the distributed substitution to publish each solved 512-block of x. */
+int gabo_push_signal_f64(const double* src, int64_t count, double* const* dst_host, uint32_t* const* flags_host, int n,
+                         uint32_t value, gabo_stream_t stream);
 int gabo_copy_async(void* dst, const void* src, size_t bytes, gabo_stream_t stream);
+/* gabo_solve_cyclic_p2p_f64: the forward substitution L x = b of the block-cyclically distributed factor (panel p of nb rows on
+ *   rank p % world, local slot p / world; A_loc [local_rows, >= n], B_loc [local_rows, nrhs] contiguous, in place) as ONE host
+ *   call per rank, no collective: at step kp the owner solves its block (inverses of the 128-blocks of the diagonal block in
+ *   winv_host[kp], device pointers in a HOST array of ceil(n/nb) entries, only the owner's are read) and publishes it into slot
+ *   kp of every peer's x area (xarea_host[r], HOST array of `world` device pointers; nb * nrhs doubles per slot) together with
+ *   the flag value base + kp + 1 (flag_host[r], one 32-bit word in each rank's memory); the peers' streams wait for the flag.
+ *   The owner of panel kp + 1 updates those rows first, solves and publishes, then updates the rest of its rows.
+ *   scratch: >= 256 B of device memory.  Successive solves must be separated by a rank-wide synchronisation and use
+ *   increasing `base` values. */
+int gabo_solve_cyclic_p2p_f64(int64_t n, int nb, int world, int rank, const double* A_loc, int64_t lda, double* B_loc,
+                              int64_t ldb, int64_t nrhs, const double* const* winv_host, double* const* xarea_host,
+                              uint32_t* const* flag_host, uint32_t base, void* scratch, size_t scratch_bytes,
+                              gabo_stream_t stream);
 /* gabo_syrk_cyclic_f64: C[m,n] -= A[m,k] B[n,k]^T restricted to GLOBAL col <= GLOBAL row, where local row r of C is
  *   global row row_base + ((r / cyc_nb) * cyc_world + cyc_rank) * cyc_nb + r % cyc_nb (cyc_nb == 0: row_base + r) and
  *   local column c is global column col_base + c. */

@@ -11,7 +11,7 @@ import torch.distributed as dist
 sys.path.insert(0, '.')
 from gaboflow_b200 import SphereGaussianKernel, ops  # noqa: E402
 from gaboflow_b200.dist import (BlockCyclic, gram_block_cyclic, potrf_block_cyclic_, solve_lower_block_cyclic_,  # noqa: E402
-                                gp_loglik_block_cyclic, PanelExchange, potrf_block_cyclic_p2p_)
+                                gp_loglik_block_cyclic, PanelExchange, potrf_block_cyclic_p2p_, solve_lower_block_cyclic_p2p_)
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 rank, world, lr = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
@@ -32,15 +32,28 @@ info = potrf_block_cyclic_(A, lay, 1e-2)
 xch = PanelExchange(lay, N, dev)
 A3 = A2.clone()
 info2 = potrf_block_cyclic_p2p_(A2, lay, 1e-2, xch)
-info3 = potrf_block_cyclic_p2p_(A3, lay, 1e-2, xch)
+store = {}
+info3 = potrf_block_cyclic_p2p_(A3, lay, 1e-2, xch, winv_store=store)
 gmask = torch.arange(N, device=dev)[None, :] <= lay.global_rows().to(dev)[:, None]
 p2p_err = max(float(torch.where(gmask, (A2 - A).abs(), torch.zeros_like(A)).max().item()),
               float(torch.where(gmask, (A3 - A).abs(), torch.zeros_like(A)).max().item()))
-xch.close()
 grow = lay.global_rows()
 V = torch.from_numpy(y[grow.numpy()]).to(dev)
 solve_lower_block_cyclic_(A, V, lay)
 ll = gp_loglik_block_cyclic(A, V, lay)
+# the substitution through peer memory (push + flag per block) must reproduce the collective one; twice for the epochs
+for _ in range(2):
+    V2 = torch.from_numpy(y[grow.numpy()]).to(dev)
+    solve_lower_block_cyclic_p2p_(A, V2, lay, xch)
+    ll2 = gp_loglik_block_cyclic(A, V2, lay)
+    p2p_err = max(p2p_err, float((V2 - V).abs().max().item()))     # same kernels, same order per entry: bit-identical
+# ... and as one C call per rank, with the block inverses the factorisation left behind (differs by rounding only)
+V3 = torch.from_numpy(y[grow.numpy()]).to(dev)
+solve_lower_block_cyclic_p2p_(A3, V3, lay, xch, winv_store=store)
+c_err = float((V3 - V).abs().max().item())
+if c_err > 1e-11:
+    p2p_err = max(p2p_err, c_err)
+xch.close()
 # single-GPU reference on every rank (cheap at this size)
 Kf = torch.empty((N, N), dtype=torch.float64, device=dev)
 k.K(Xd, uplo='lower', out=Kf)
