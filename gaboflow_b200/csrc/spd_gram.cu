@@ -524,6 +524,142 @@ int dispatch_spd_gram(int kind, int d, const SpdGramParams& p, cudaStream_t s) {
     }
 }
 
+// ---- candidate gradients of the affine-invariant kernels ------------------------------------------------------
+// For k_i(X) = variance exp(-beta d_i^p), d_i^2 = sum_k log^2 lambda_k(M_i), M_i = W_i X W_i^T = V Lambda V^T  (W_i = chol(A_i)^-1):
+//   d(d_i^2) = 2 tr( log(A_i^-1 X) X^-1 dX )  and  log(A_i^-1 X) X^-1 = W_i^T V diag(log lambda_k / lambda_k) V^T W_i,
+// so the Euclidean gradient of d_i^2 with respect to the symmetric matrix X is  G_i = 2 sum_k (log lambda_k / lambda_k) u_k u_k^T,
+// u_k = W_i^T v_k  (equal to 2 X^-1 Log(X A_i^-1), which is symmetric).  In Mandel coordinates (SPD_utils_tf.py:27-63) the
+// diagonal slots get G_rr and the off-diagonal slots sqrt(2) G_rc.  dk_i/dx = -beta k_i g_i (Gaussian), -beta k_i g_i / (2 d_i)
+// (Laplace).  The posterior gradients are weighted sums over the training points, as for the sphere kernels
+// (gabo_sphere_posterior_grad_f64):  d mean/dx = sum_i alpha_i dk_i/dx,  d var/dx = -2 sum_i (Ky^-1 k)_i dk_i/dx.
+// One CTA per candidate, a thread per training point (cyclic Jacobi WITH eigenvectors in registers), fixed-order reduction.
+// The reference gets these from TensorFlow autodiff and hands them to the manifold optimiser (manifold_optimization.py:260-271).
+template <int D, int KIND>
+__global__ void __launch_bounds__(128) spd_ai_post_grad_kernel(int64_t n, const double* __restrict__ W1, const double* __restrict__ S2,
+                                                               const double* __restrict__ alpha, const double* __restrict__ Bm,
+                                                               int64_t ldb, double beta, double variance,
+                                                               const double* __restrict__ mean, const double* __restrict__ var,
+                                                               double fmin, double* __restrict__ gmean, double* __restrict__ gvar,
+                                                               double* __restrict__ dei) {
+    constexpr int DD = D * D;
+    constexpr int MP = D * (D + 1) / 2;
+    __shared__ double red[2][MP][128 + 1];
+    const int64_t m = blockIdx.x;
+    const int tid = threadIdx.x;
+    double B[D][D];
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) B[r][c] = S2[m * DD + r * D + c];
+    double a1[MP], a2[MP];
+#pragma unroll
+    for (int s = 0; s < MP; ++s) { a1[s] = 0.0; a2[s] = 0.0; }
+    for (int64_t i = tid; i < n; i += 128) {
+        double Wm[D][D];
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+#pragma unroll
+            for (int c = 0; c < D; ++c) Wm[r][c] = (c <= r) ? W1[i * DD + r * D + c] : 0.0;
+        // M = W B W^T (upper storage)
+        double T[D][D], Mx[D][D], V[D][D];
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k <= a; ++k) v = fma(Wm[a][k], B[k][c], v);
+                T[a][c] = v;
+            }
+#pragma unroll
+        for (int b = 0; b < D; ++b)
+#pragma unroll
+            for (int a = b; a < D; ++a) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k <= b; ++k) v = fma(T[a][k], Wm[b][k], v);
+                Mx[b][a] = v;
+            }
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+#pragma unroll
+            for (int c = 0; c < D; ++c) V[r][c] = (r == c) ? 1.0 : 0.0;
+        jacobi_eig<D, true>(Mx, V);
+        double s2 = 0.0, ck[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const double lg = log(Mx[k][k]);
+            s2 = fma(lg, lg, s2);
+            ck[k] = lg / Mx[k][k];
+        }
+        // U = W^T V (column k = u_k)
+        double U[D][D];
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                double v = 0.0;
+#pragma unroll
+                for (int b = a; b < D; ++b) v = fma(Wm[b][a], V[b][k], v);
+                U[a][k] = v;
+            }
+        double kv, scale;
+        if (KIND == GABO_SPD_AI_GAUSSIAN) {
+            kv = variance * exp(-beta * s2);
+            scale = -beta * kv;
+        } else {
+            const double dist = sqrt(s2);
+            kv = variance * exp(-beta * dist);
+            scale = (dist > 0.0) ? -beta * kv / (2.0 * dist) : 0.0;     // not differentiable at d = 0 (as the kernel itself)
+        }
+        const double w1 = alpha[i] * scale, w2 = Bm[i * ldb + m] * scale;
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+#pragma unroll
+            for (int c = r; c < D; ++c) {
+                double g = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) g = fma(ck[k] * U[r][k], U[c][k], g);
+                g *= (r == c) ? 2.0 : 2.0 * 1.41421356237309504880;
+                const int slot = mandel_slot<D>(r, c);
+                a1[slot] = fma(w1, g, a1[slot]);
+                a2[slot] = fma(w2, g, a2[slot]);
+            }
+    }
+#pragma unroll
+    for (int s = 0; s < MP; ++s) { red[0][s][tid] = a1[s]; red[1][s][tid] = a2[s]; }
+    __syncthreads();
+    if (tid < MP) {
+        double g1 = 0.0, g2 = 0.0;
+        for (int t = 0; t < 128; ++t) { g1 += red[0][tid][t]; g2 += red[1][tid][t]; }
+        g2 *= -2.0;
+        gmean[m * MP + tid] = g1;
+        gvar[m * MP + tid] = g2;
+        if (dei != nullptr) {
+            const double v = var[m];
+            const double sd = sqrt(fmax(v, 1e-6));
+            const double z = (fmin - mean[m]) / sd;
+            const double cdf = 0.5 * erfc(-z * 0.70710678118654752440);
+            const double phi = exp(-0.5 * z * z) * 0.39894228040143267794;
+            dei[m * MP + tid] = -cdf * g1 + ((v > 1e-6) ? phi / (2.0 * sd) * g2 : 0.0);   // the variance floor has zero slope
+        }
+    }
+}
+
+template <int D>
+int launch_spd_ai_post_grad(int kind, int64_t n, int64_t M, const double* W1, const double* S2, const double* alpha, const double* Bm,
+                            int64_t ldb, double beta, double variance, const double* mean, const double* var, double fmin,
+                            double* gmean, double* gvar, double* dei, cudaStream_t stream) {
+    if (kind == GABO_SPD_AI_GAUSSIAN)
+        spd_ai_post_grad_kernel<D, GABO_SPD_AI_GAUSSIAN><<<(unsigned)M, 128, 0, stream>>>(n, W1, S2, alpha, Bm, ldb, beta, variance, mean, var,
+                                                                                         fmin, gmean, gvar, dei);
+    else
+        spd_ai_post_grad_kernel<D, GABO_SPD_AI_LAPLACE><<<(unsigned)M, 128, 0, stream>>>(n, W1, S2, alpha, Bm, ldb, beta, variance, mean, var,
+                                                                                        fmin, gmean, gvar, dei);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+
 __global__ void stein_kdiag_kernel(const double* __restrict__ logdet, int64_t n, double beta, double variance,
                                    double* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -635,6 +771,40 @@ extern "C" int gabo_spd_gram_cyclic_f64(int kind, int d, const double* W1, const
     return gabo::dispatch_spd_gram(kind, d, p, static_cast<cudaStream_t>(stream));
 }
 
+
+// Euclidean gradients (Mandel coordinates) of the posterior mean / variance and of Expected Improvement with respect to each of M
+// candidate SPD matrices, affine-invariant kernels.  W1 [n, d*d]: inverse Cholesky factors of the training matrices; S2 [M, d*d]:
+// the candidates; alpha [n] = Ky^-1 (y - m); Bm [n, M] = Ky^-1 K(X, X*); mean / var [M] the posterior (needed for dei only).
+// gmean, gvar, dei: [M, d(d+1)/2]; dei may be NULL.
+extern "C" int gabo_spd_ai_posterior_grad_f64(int kind, int d, int64_t n, int64_t M, const double* W1, const double* S2,
+                                              const double* alpha, const double* Bm, int64_t ldb, double beta, double variance,
+                                              const double* mean, const double* var, double fmin, double* gmean, double* gvar,
+                                              double* dei, gabo_stream_t stream) {
+    using namespace gabo;
+    if (kind != GABO_SPD_AI_GAUSSIAN && kind != GABO_SPD_AI_LAPLACE) return -1;
+    if (d < 2 || d > 6) return -2;        // a thread holds W, M, V and U: d <= 6 (every S^d_++ of the reference examples is d = 2)
+    if (n < 0) return -3;
+    if (M < 0) return -4;
+    if (M == 0) return 0;
+    if (n > 0 && W1 == nullptr) return -5;
+    if (S2 == nullptr) return -6;
+    if (n > 0 && alpha == nullptr) return -7;
+    if (n > 0 && Bm == nullptr) return -8;
+    if (ldb < M) return -9;
+    if (!(beta > 0.0)) return -10;
+    if (!(variance > 0.0)) return -11;
+    if (dei != nullptr && (mean == nullptr || var == nullptr)) return -12;
+    if (gmean == nullptr) return -15;
+    if (gvar == nullptr) return -16;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (d) {
+        case 2: return launch_spd_ai_post_grad<2>(kind, n, M, W1, S2, alpha, Bm, ldb, beta, variance, mean, var, fmin, gmean, gvar, dei, s);
+        case 3: return launch_spd_ai_post_grad<3>(kind, n, M, W1, S2, alpha, Bm, ldb, beta, variance, mean, var, fmin, gmean, gvar, dei, s);
+        case 4: return launch_spd_ai_post_grad<4>(kind, n, M, W1, S2, alpha, Bm, ldb, beta, variance, mean, var, fmin, gmean, gvar, dei, s);
+        case 5: return launch_spd_ai_post_grad<5>(kind, n, M, W1, S2, alpha, Bm, ldb, beta, variance, mean, var, fmin, gmean, gvar, dei, s);
+        default: return launch_spd_ai_post_grad<6>(kind, n, M, W1, S2, alpha, Bm, ldb, beta, variance, mean, var, fmin, gmean, gvar, dei, s);
+    }
+}
 
 extern "C" int gabo_spd_stein_kdiag_f64(const double* logdet, int64_t n, double beta, double variance, double* out,
                                         gabo_stream_t stream) {

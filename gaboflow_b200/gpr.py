@@ -210,16 +210,31 @@ class GPR(Parameterized):
 
     def build_predict_with_gradients(self, Xnew, fmin=None):
         """Posterior mean / variance at the candidates AND their Euclidean gradients w.r.t. the candidates, for the sphere
-        kernels (the reference differentiates through TensorFlow and hands the result to the manifold
+        kernels and the SPD affine-invariant kernels (Mandel coordinates) (the reference differentiates through TensorFlow and hands the result to the manifold
         optimiser, ``BO_utils/manifold_optimization.py:260-271``).  Returns (mean [M,1], var [M], dmean [M,D], dvar [M,D],
         dEI [M,D] or None); with ``fmin`` the EI gradient is formed in the same kernel.  One output column only."""
+        from .kernel_utils.kernels_spd import SpdAffineInvariantGaussianKernel
         kind = getattr(self.kern, '_kind', None)
-        if kind not in (ops.SPHERE_GAUSSIAN, ops.SPHERE_LAPLACE):
-            raise NotImplementedError('candidate gradients are implemented for the sphere kernels')
+        is_ai = isinstance(self.kern, SpdAffineInvariantGaussianKernel)          # Gaussian and (subclass) Laplace
+        if not is_ai and kind not in (ops.SPHERE_GAUSSIAN, ops.SPHERE_LAPLACE):
+            raise NotImplementedError('candidate gradients are implemented for the sphere and the SPD affine-invariant kernels')
         L, V = self._factorise()
         if int(V.shape[1]) != 1:
             raise NotImplementedError('candidate gradients need a single output column')
         Xn = to_device(Xnew)
+        if is_ai:
+            ptrain = self._kern_input()
+            pcand = self.kern.prepare(Xn)
+            Kx = self.kern.K(ptrain, pcand)                # [N, M]
+            A = Kx.clone()
+            ops.trsm_(L, A, trans=False)
+            mean, var = ops.gp_predict(A, V, self.kern.Kdiag(Xn), self._mean_const())
+            ops.trsm_(L, A, trans=True)                    # Ky^-1 Kx
+            alpha = V.clone()
+            ops.trsm_(L, alpha, trans=True)
+            dmean, dvar, dei = ops.spd_ai_posterior_grad(kind, ptrain, pcand, alpha, A, self.kern.beta_effective(),
+                                                         float(self.kern.variance), mean, var, fmin)
+            return mean, var, dmean, dvar, dei
         Kx = self.kern.K(self.X, Xn)                       # [N, M]
         A = Kx.clone()
         ops.trsm_(L, A, trans=False)                       # L^-1 Kx
@@ -230,6 +245,37 @@ class GPR(Parameterized):
         dmean, dvar, dei = ops.sphere_posterior_grad(kind, self.X, Kx, alpha, A, self.kern.beta_effective(),
                                                      float(self.kern.variance), mean, var, fmin)
         return mean, var, dmean, dvar, dei
+
+    # ---- fused acquisition ---------------------------------------------------------------------
+    FUSED_MAX_N = 4096
+
+    def fused_acquisition_available(self) -> bool:
+        return (getattr(self.kern, '_kind', None) in (ops.SPHERE_GAUSSIAN, ops.SPHERE_LAPLACE)
+                and hasattr(self.kern, 'beta_effective') and type(self.kern).__module__.endswith('kernels_sphere')
+                and int(self.X.shape[0]) <= self.FUSED_MAX_N and int(self.Y.shape[1]) == 1 and int(self.X.shape[1]) <= 64)
+
+    def _fused_state(self):
+        """L^-1 and alpha = Ky^-1 (y - m), formed once per factorisation and kept beside the cached factor."""
+        L, V = self._factorise()
+        if getattr(self, '_fused_key', None) != self._cache_key:
+            n = int(L.shape[0])
+            Linv = torch.eye(n, dtype=torch.float64, device=L.device)
+            ops.trsm_(L, Linv, trans=False)
+            alpha = V.clone()
+            ops.trsm_(L, alpha, trans=True)
+            self._Linv, self._alpha, self._fused_key, self._fused_out = Linv, alpha.reshape(-1).contiguous(), self._cache_key, {}
+        return self._Linv, V, self._alpha
+
+    def acquisition_fused(self, Xcand, fmin, with_grad=False):
+        """Posterior mean / variance, Expected Improvement and (optionally) their Euclidean gradients at the candidates in ONE
+        kernel launch (``gabo_sphere_acq_fused_f64``) -- the evaluation ``manifold_optimization.py:250-271,427`` repeats thousands
+        of times per BO iteration.  Sphere kernels, N <= 4096.  Returns (mean [M], var [M], ei [M], dmean, dvar, dei)."""
+        if not self.fused_acquisition_available():
+            raise NotImplementedError('fused acquisition: sphere kernels, one output column, N <= %d' % self.FUSED_MAX_N)
+        Linv, V, alpha = self._fused_state()
+        return ops.sphere_acq_fused(self.kern._kind, self.X, to_device(Xcand), Linv, V.reshape(-1), alpha, self.kern.beta_effective(),
+                                    float(self.kern.variance), self._mean_const(), float(fmin), with_grad=with_grad,
+                                    out=self._fused_out)
 
     # ---- AutoFlow-style NumPy API ---------------------------------------------------------------------
     def compute_log_likelihood(self) -> float:

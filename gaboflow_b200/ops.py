@@ -518,6 +518,68 @@ def sphere_posterior_grad(kind: int, X: torch.Tensor, Kx: torch.Tensor, alpha: t
     return gmean, gvar, dei
 
 
+def spd_ai_posterior_grad(kind: int, p_train: SpdPrep, p_cand: SpdPrep, alpha: torch.Tensor, Bm: torch.Tensor, beta: float,
+                          variance: float, mean: Optional[torch.Tensor] = None, var: Optional[torch.Tensor] = None,
+                          fmin: Optional[float] = None):
+    """Euclidean gradients, in Mandel coordinates, w.r.t. M candidate SPD matrices under the affine-invariant kernels
+    (gabo_spd_ai_posterior_grad_f64): (d mean/dx* [M,m], d var/dx* [M,m], d EI/dx* [M,m] or None).  alpha = Ky^-1 (y-m) [N],
+    Bm = Ky^-1 K(X, X*) [N,M]."""
+    _req(alpha, 'alpha'); _req(Bm, 'Bm')
+    n, M, d = p_train.n, p_cand.n, p_train.d
+    mm = d * (d + 1) // 2
+    al = alpha.reshape(-1).contiguous()
+    if al.numel() != n or tuple(Bm.shape) != (n, M) or p_cand.d != d or p_train.W is None or p_cand.S is None:
+        raise ValueError('shape mismatch in spd_ai_posterior_grad')
+    dev = p_train.info.device
+    gmean = torch.empty((M, mm), dtype=torch.float64, device=dev)
+    gvar = torch.empty((M, mm), dtype=torch.float64, device=dev)
+    dei = None
+    mptr = vptr = dptr = None
+    if fmin is not None:
+        mean_c = _req(mean, 'mean').reshape(-1).contiguous()
+        var_c = _req(var, 'var').reshape(-1).contiguous()
+        dei = torch.empty((M, mm), dtype=torch.float64, device=dev)
+        mptr, vptr, dptr = mean_c.data_ptr(), var_c.data_ptr(), dei.data_ptr()
+    st = _lib.lib().gabo_spd_ai_posterior_grad_f64(int(kind), d, n, M, p_train.W.data_ptr(), p_cand.S.data_ptr(), al.data_ptr(),
+                                                   Bm.data_ptr(), max(int(Bm.stride(0)), M) if n > 1 else M, float(beta),
+                                                   float(variance), mptr, vptr, float(fmin) if fmin is not None else 0.0,
+                                                   gmean.data_ptr(), gvar.data_ptr(), dptr, _stream())
+    _lib.check('gabo_spd_ai_posterior_grad_f64', st)
+    return gmean, gvar, dei
+
+
+def sphere_acq_fused(kind: int, X: torch.Tensor, Xc: torch.Tensor, Linv: torch.Tensor, V: torch.Tensor, alpha: Optional[torch.Tensor],
+                     beta: float, variance: float, mean_const: float, fmin: float, with_grad: bool = False, out=None):
+    """One launch per candidate batch (gabo_sphere_acq_fused_f64): K(X,x*) -> L^-1 -> mean / var -> EI (-> gradients).
+    Returns (mean [M], var [M], ei [M], dmean, dvar, dei) with the last three None unless with_grad.  ``out``: optional dict of
+    preallocated outputs (keys mean, var, ei, dmean, dvar, dei) so that repeated evaluations allocate nothing."""
+    X = _rowmajor2d(_req(X, 'X')); Xc = _rowmajor2d(_req(Xc, 'Xc'))
+    _req(Linv, 'Linv'); _req(V, 'V')
+    n, dim, M = int(X.shape[0]), int(X.shape[1]), int(Xc.shape[0])
+    dev = X.device
+    o = out if out is not None else {}
+
+    def buf(name, shape):
+        t = o.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=torch.float64, device=dev)
+            o[name] = t
+        return t
+
+    mean, var, ei = buf('mean', (M,)), buf('var', (M,)), buf('ei', (M,))
+    gm = gv = ge = None
+    if with_grad:
+        gm, gv, ge = buf('dmean', (M, dim)), buf('dvar', (M, dim)), buf('dei', (M, dim))
+        _req(alpha, 'alpha')
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    st = _lib.lib().gabo_sphere_acq_fused_f64(int(kind), n, M, dim, X.data_ptr(), _ld(X), Xc.data_ptr(), _ld(Xc), Linv.data_ptr(),
+                                              max(int(Linv.stride(0)), n) if n > 1 else 1, V.data_ptr(), ptr(alpha), float(beta),
+                                              float(variance), float(mean_const), float(fmin), mean.data_ptr(), var.data_ptr(),
+                                              ei.data_ptr(), ptr(gm), ptr(gv), ptr(ge), _stream())
+    _lib.check('gabo_sphere_acq_fused_f64', st)
+    return mean, var, ei, gm, gv, ge
+
+
 def expected_improvement(mean: torch.Tensor, var: torch.Tensor, fmin: float) -> torch.Tensor:
     """EI over the candidates (gabo_expected_improvement_f64); mean / var are [M] or [M,1] device tensors."""
     _req(mean, 'mean'); _req(var, 'var')

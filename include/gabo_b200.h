@@ -194,6 +194,28 @@ int gabo_sphere_posterior_grad_f64(int kind, int64_t n, int64_t M, int dim, cons
                                    const double* Kx, int64_t ldk, const double* alpha, const double* Bm, int64_t ldb,
                                    double beta, double variance, const double* mean, const double* var, double fmin,
                                    double* gmean, double* gvar, double* dei, gabo_stream_t stream);
+/* gabo_spd_ai_posterior_grad_f64: the same for candidate SPD matrices under the affine-invariant kernels
+ *   (examples/bo_spd/benchmark_examples/bo_spd_ackley_manifold.py:159-187 through manifold_optimization.py:260-271).  For
+ *   M_i = W1[i] X W1[i]^T = V Lambda V^T the Euclidean gradient of d_AI(A_i, X)^2 with respect to the symmetric matrix X is
+ *   2 sum_k (log lambda_k / lambda_k) u_k u_k^T, u_k = W1[i]^T v_k (= 2 X^-1 Log(X A_i^-1)); Mandel coordinates scale the
+ *   off-diagonal slots by sqrt(2).  W1 [n, d*d] inverse Cholesky factors of the training matrices (gabo_spd_prep_f64), S2
+ *   [M, d*d] the candidates, alpha [n] = Ky^-1 (y - m), Bm [n, M] = Ky^-1 K(X, X*), mean / var [M] the posterior at the
+ *   candidates.  gmean, gvar, dei: [M, d(d+1)/2]; dei may be NULL (then mean / var / fmin are ignored).  2 <= d <= 6. */
+int gabo_spd_ai_posterior_grad_f64(int kind, int d, int64_t n, int64_t M, const double* W1, const double* S2,
+                                   const double* alpha, const double* Bm, int64_t ldb, double beta, double variance,
+                                   const double* mean, const double* var, double fmin, double* gmean, double* gvar,
+                                   double* dei, gabo_stream_t stream);
+/* gabo_sphere_acq_fused_f64: the acquisition evaluation of the reference's optimisers in ONE launch --
+ *   MultistartedOptimizer scores 100-1000 anchors per BO iteration (manifold_optimization.py:402-431) and the manifold CG asks
+ *   for (-EI, -dEI/dx) one candidate at a time (:250-271).  Per candidate: k = K(X, x*) -> a = L^-1 k -> mean = a.V + mean_const,
+ *   var = variance - a.a (GPR.build_predict) -> EI (GPflowOpt) -> optionally the Euclidean gradients of mean / var / EI.
+ *   Linv [n, n] = L^-1 (lower triangular, row-major; e.g. gabo_trsm_f64 on the identity, once per factorisation),
+ *   V [n] = L^-1 (y - m), alpha [n] = Ky^-1 (y - m) (read only with gradients).  mean / var / ei: [M]; gmean / gvar / dei:
+ *   [M, dim], all NULL for values only (dei alone may be NULL).  n <= 9000, dim <= 64, sphere kinds. */
+int gabo_sphere_acq_fused_f64(int kind, int64_t n, int64_t M, int dim, const double* X, int64_t ldx, const double* Xc,
+                              int64_t ldc, const double* Linv, int64_t ldl, const double* V, const double* alpha,
+                              double beta, double variance, double mean_const, double fmin, double* mean, double* var,
+                              double* ei, double* gmean, double* gvar, double* dei, gabo_stream_t stream);
 /* Expected Improvement over M candidates from the posterior mean / variance (GPflowOpt ExpectedImprovement
  * [third party]; consumed by the reference at BO_utils/manifold_optimization.py:250-271,427):
  *   out = (fmin - mean) Phi(z) + var N(fmin; mean, sqrt(var)), var floored at 1e-6, z = (fmin - mean)/sqrt(var). */

@@ -319,8 +319,8 @@ def test_candidate_gradients_vs_oracle_finite_differences(cuda, laplace):
     acq = ExpectedImprovement(m)
     fmin = acq.fmin
     mean, var, dmean, dvar, dei = m.build_predict_with_gradients(Xs, fmin=fmin)
-    ei, dei2 = acq.evaluate_with_gradients(Xs)
-    assert np.array_equal(dei.cpu().numpy(), dei2)
+    ei, dei2 = acq.evaluate_with_gradients(Xs)          # the fused one-launch path (sphere kernels)
+    assert np.max(np.abs(dei.cpu().numpy() - dei2)) < 1e-10 * max(1.0, float(np.max(np.abs(dei2))))
     Kor = Kfun(X)
     np.fill_diagonal(Kor, v)          # K(X) has a diagonal of exactly `variance` here; the reference's carries acos noise
 
@@ -339,3 +339,88 @@ def test_candidate_gradients_vs_oracle_finite_differences(cuda, laplace):
             for got, ref in ((float(dmean[c, j]), (mp - mm) / (2 * h)), (float(dvar[c, j]), (vp - vm) / (2 * h)),
                              (float(dei[c, j]), (ep - em) / (2 * h))):
                 assert abs(got - ref) < 2e-5 * max(1.0, abs(ref)), (laplace, c, j, got, ref)
+
+
+@pytest.mark.parametrize('d,laplace', [(2, False), (2, True), (3, False), (6, False)])
+def test_spd_ai_candidate_gradients_vs_oracle_finite_differences(cuda, d, laplace):
+    """gabo_spd_ai_posterior_grad_f64 (d mean/dx*, d var/dx*, d EI/dx* in Mandel coordinates) against central finite
+    differences of the ORACLE's posterior and EI -- what bo_spd_ackley_manifold.py:159-187 obtains from TensorFlow autodiff and
+    hands to the manifold optimiser (manifold_optimization.py:260-271)."""
+    from gaboflow_b200 import GPR, SpdAffineInvariantGaussianKernel, SpdAffineInvariantLaplaceKernel, ExpectedImprovement
+    n, M = 90, 4
+    mm = d * (d + 1) // 2
+    X = orc.synth_spd_mandel(n, d, seed=61)
+    y = np.log(orc.mandel_to_sym(X)[:, 0, 0])[:, None] + 0.05 * np.random.default_rng(62).standard_normal((n, 1))
+    Xs = orc.synth_spd_mandel(M, d, seed=63)
+    beta, v, s2 = 0.9, 1.2, 0.05
+    if laplace:
+        k = SpdAffineInvariantLaplaceKernel(mm, range(mm), beta=beta, variance=v)
+        Kfun = lambda A, B=None: orc.spd_ai_laplace_K(A, B, beta=beta, variance=v)
+    else:
+        k = SpdAffineInvariantGaussianKernel(mm, range(mm), beta_min=0.4, beta=beta - 0.4, variance=v)
+        Kfun = lambda A, B=None: orc.spd_ai_gaussian_K(A, B, beta=beta, variance=v)
+    m = GPR(X, y, kern=k)
+    m.likelihood.variance = s2
+    acq = ExpectedImprovement(m)
+    fmin = acq.fmin
+    mean, var, dmean, dvar, dei = m.build_predict_with_gradients(Xs, fmin=fmin)
+    ei, dei2 = acq.evaluate_with_gradients(Xs)
+    assert np.array_equal(dei.cpu().numpy(), dei2)
+    Kor = Kfun(X)
+    np.fill_diagonal(Kor, v)
+
+    def post(x):
+        mu, vv = orc.gp_predict(Kor, Kfun(X, x[None, :]), np.full(1, v), y, s2)
+        mu, vv = float(np.ravel(mu)[0]), float(np.ravel(vv)[0])
+        return mu, vv, float(np.ravel(orc.expected_improvement(np.array([mu]), np.array([vv]), fmin))[0])
+
+    h = 1e-6
+    for c in range(M):
+        mu0, v0, e0 = post(Xs[c])
+        assert abs(float(mean[c, 0]) - mu0) < 1e-8 and abs(float(var[c]) - v0) < 1e-8 and abs(float(ei[c, 0]) - e0) < 1e-8
+        for j in range(mm):
+            e = np.zeros(mm); e[j] = h
+            (mp, vp, ep), (mn, vm, em) = post(Xs[c] + e), post(Xs[c] - e)
+            for got, ref in ((float(dmean[c, j]), (mp - mn) / (2 * h)), (float(dvar[c, j]), (vp - vm) / (2 * h)),
+                             (float(dei[c, j]), (ep - em) / (2 * h))):
+                assert abs(got - ref) < 3e-5 * max(1.0, abs(ref)), (d, laplace, c, j, got, ref)
+
+
+@pytest.mark.parametrize('laplace', [False, True])
+@pytest.mark.parametrize('n,D,M', [(5, 3, 1), (30, 3, 100), (500, 3, 7), (3000, 51, 33)])
+def test_fused_acquisition_matches_unfused_path(cuda, laplace, n, D, M):
+    """gabo_sphere_acq_fused_f64 (K(X,x*) -> L^-1 -> mean/var -> EI -> gradients in ONE launch, cached L^-1) against the
+    separate launches (Gram, TRSM, predict, EI, TRSM^T, gradient kernel) and, for the values, against the oracle."""
+    from gaboflow_b200 import GPR, SphereGaussianKernel, SphereLaplaceKernel, ExpectedImprovement
+    X = orc.synth_sphere(n, D, seed=71)
+    y = np.cos(2.0 * X[:, :1]) + 0.1 * np.random.default_rng(72).standard_normal((n, 1))
+    Xs = orc.synth_sphere(M, D, seed=73)
+    beta, v, s2 = 2.2, 0.9, 0.02
+    if laplace:
+        k = SphereLaplaceKernel(D, range(D), beta=beta, variance=v)
+        Kfun = lambda A, B=None: orc.sphere_laplace_K(A, B, beta=beta, variance=v)
+    else:
+        k = SphereGaussianKernel(D, range(D), beta_min=0.7, beta=beta - 0.7, variance=v)
+        Kfun = lambda A, B=None: orc.sphere_gaussian_K(A, B, beta=beta, variance=v)
+    m = GPR(X, y, kern=k)
+    m.likelihood.variance = s2
+    fused, plain = ExpectedImprovement(m, fused=True), ExpectedImprovement(m, fused=False)
+    assert m.fused_acquisition_available() and fused.fmin == plain.fmin
+    e1, g1 = fused.evaluate_with_gradients(Xs)
+    e2, g2 = plain.evaluate_with_gradients(Xs)
+    assert e1.shape == e2.shape == (M, 1) and g1.shape == g2.shape == (M, D)
+    scale = max(1.0, float(np.max(np.abs(g2))))
+    assert np.max(np.abs(e1 - e2)) < 1e-11 and np.max(np.abs(g1 - g2)) < 1e-9 * scale
+    assert np.max(np.abs(fused.evaluate(Xs) - e1)) == 0.0
+    mean, var, ei = [t.cpu().numpy() for t in m.acquisition_fused(Xs, fused.fmin)[:3]]
+    Kor = Kfun(X)
+    np.fill_diagonal(Kor, v)
+    mu_o, var_o = orc.gp_predict(Kor, Kfun(X, Xs), np.full(M, v), y, s2)
+    assert np.max(np.abs(mean - mu_o[:, 0])) < 1e-8 * max(1.0, np.max(np.abs(mu_o)))
+    assert np.max(np.abs(var - var_o[:, 0])) < 1e-8
+    assert np.max(np.abs(ei - orc.expected_improvement(mu_o[:, 0], var_o[:, 0], fused.fmin))) < 1e-8
+    # a new observation invalidates the cached inverse factor
+    m.append(orc.synth_sphere(1, D, seed=74)[0], np.array([0.3]))
+    f2 = ExpectedImprovement(m, fused=True)
+    p2 = ExpectedImprovement(m, fused=False)
+    assert np.max(np.abs(f2.evaluate(Xs) - p2.evaluate(Xs))) < 1e-11
