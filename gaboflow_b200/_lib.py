@@ -61,6 +61,9 @@ SIGNATURES = {
     'gabo_flag_wait_geq': (i32, [vp, C.c_uint32, vp]),
     'gabo_push_signal_f64': (i32, [vp, i64, vp, vp, i32, C.c_uint32, vp]),
     'gabo_copy_async': (i32, [vp, vp, sz, vp]),
+    'gabo_event_create': (i32, [C.POINTER(vp)]),
+    'gabo_event_destroy': (i32, [vp]),
+    'gabo_potrf_cyclic_p2p_f64': (i32, [i64, i32, i32, i32, vp, i64, f64, vp, vp, vp, C.c_uint32, vp, vp, vp, sz, vp, sz, vp, vp, vp, vp]),
     'gabo_solve_cyclic_p2p_f64': (i32, [i64, i32, i32, i32, vp, i64, vp, i64, i64, vp, vp, vp, C.c_uint32, vp, sz, vp]),
     'gabo_syrk_cyclic_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, i32, vp]),
     'gabo_solve_update_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]),

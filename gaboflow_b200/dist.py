@@ -20,6 +20,8 @@ panel" of the symmetric matrix is a row panel here).
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -579,6 +581,14 @@ class PanelExchange:
         self.gram_epoch = 0
         self.solve_epoch = 0
         self.side = torch.cuda.Stream(device=self.device, priority=-1)
+        self._cstate = None
+        import ctypes as _C
+        from . import _lib as _l
+        e1, e2 = _C.c_void_p(), _C.c_void_p()
+        with torch.cuda.device(self.device):
+            _l.check('gabo_event_create', _l.lib().gabo_event_create(_C.byref(e1)))
+            _l.check('gabo_event_create', _l.lib().gabo_event_create(_C.byref(e2)))
+        self.ev_u1, self.ev_side = e1.value, e2.value
         self.peers.local[0, self.flag_off:].zero_()
         self._warm_up()
         torch.cuda.synchronize(self.device)
@@ -626,7 +636,28 @@ class PanelExchange:
         o = self.NBUF * self.p_elems + b * self.bc_elems
         return self.peers.local[0, o: o + self.bc_elems]
 
+    def c_state(self, npan: int, nslots: int, rows: int):
+        """Scratch of the one-call C drivers, allocated once per exchange (no allocation while streams wait on peers' flags)."""
+        from . import _lib
+        L = _lib.lib()
+        st = self._cstate
+        if st is None or st['npan'] < npan or st['nslots'] < nslots or st['rows'] < rows:
+            with torch.cuda.device(self.device):
+                st = {'npan': npan, 'nslots': nslots, 'rows': rows,
+                      'info': torch.zeros((npan,), dtype=torch.int32, device=self.device),
+                      'winv': torch.empty((nslots, self.nwb, 128, 128), dtype=torch.float64, device=self.device),
+                      'ws_diag': torch.empty(int(L.gabo_potrf_workspace_bytes(self.nb)), dtype=torch.uint8, device=self.device),
+                      'ws_trsm': torch.empty(int(L.gabo_trsm_right_workspace_bytes(rows, self.nb)), dtype=torch.uint8, device=self.device)}
+            self._cstate = st
+        return st
+
     def close(self, group=None):
+        from . import _lib
+        if getattr(self, 'ev_u1', None):
+            torch.cuda.synchronize(self.device)
+            _lib.lib().gabo_event_destroy(self.ev_u1)
+            _lib.lib().gabo_event_destroy(self.ev_side)
+            self.ev_u1 = self.ev_side = None
         self.peers.close(group=group)
 
 
@@ -666,6 +697,31 @@ def potrf_block_cyclic_p2p_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: fl
         raise ValueError('layout and PanelExchange disagree on world / rank')
     my = [p for p in layout.my_panels() if p < npan]
     rows_f = sum(min(nb, n - p * nb) for p in my)
+    if os.environ.get('GABO_DIST_PYLOOP', '0') != '1' and nb % 128 == 0 and 128 <= nb <= 512:
+        # the whole loop as ONE C call (gabo_potrf_cyclic_p2p_f64): the Python loop below -- kept as the readable specification --
+        # spends 0.2-0.3 ms of host time per panel, as much as the device needs for a panel step at 8 GPUs
+        import ctypes as C
+        from . import _lib
+        st = xch.c_state(npan, max(len(my), 1), max(rows_f, 1))
+        Ph = (C.c_void_p * (3 * W))(*[xch.p_ptr(r if W > 1 else me, b) for r in range(W) for b in range(3)])
+        Bh = (C.c_void_p * (3 * W))(*[xch.bc_ptr(r if W > 1 else me, b) for r in range(W) for b in range(3)])
+        Fh = (C.c_void_p * W)(*[xch.flag_ptr(r if W > 1 else me, 0) for r in range(W)])
+        rc = _lib.lib().gabo_potrf_cyclic_p2p_f64(n, nb, W, rank, A_loc.data_ptr(), max(int(A_loc.stride(0)), int(A_loc.shape[1])),
+                                                 float(sigma2), C.cast(Ph, C.c_void_p), C.cast(Bh, C.c_void_p), C.cast(Fh, C.c_void_p),
+                                                 base, st['info'].data_ptr(), st['winv'].data_ptr() if winv_store is not None else None,
+                                                 st['ws_diag'].data_ptr(), st['ws_diag'].numel(), st['ws_trsm'].data_ptr(),
+                                                 st['ws_trsm'].numel(), main.cuda_stream, side.cuda_stream, xch.ev_u1, xch.ev_side)
+        _lib.check('gabo_potrf_cyclic_p2p_f64', rc)
+        if winv_store is not None:
+            for p_ in my:                                   # views: valid until the next factorisation through this exchange
+                winv_store[p_] = st['winv'][layout.slot(p_)]
+        info = st['info'][:npan].to(torch.int64)
+        k0s = torch.arange(npan, device=dev, dtype=torch.int64) * nb
+        first_bad = torch.where(info > 0, info + k0s, torch.full_like(info, 2 ** 62)).min().reshape(1)
+        if W > 1:
+            dist.all_reduce(first_bad, op=dist.ReduceOp.MIN, group=group)
+        fb = int(first_bad.item())
+        return 0 if fb >= 2 ** 62 else fb
     first_bad = torch.full((1,), 2 ** 62, dtype=torch.int64, device=dev)
     bc_bytes = 8 * xch.bc_elems
 

@@ -297,6 +297,26 @@ int gabo_flag_wait_geq(const uint32_t* flag, uint32_t value, gabo_stream_t strea
 int gabo_push_signal_f64(const double* src, int64_t count, double* const* dst_host, uint32_t* const* flags_host, int n,
                          uint32_t value, gabo_stream_t stream);
 int gabo_copy_async(void* dst, const void* src, size_t bytes, gabo_stream_t stream);
+/* gabo_potrf_cyclic_p2p_f64: the distributed right-looking Cholesky of the leading n x n block (lower triangle stored
+ *   block-cyclically: global panel p of nb rows on rank p % world, local slot p / world; A_loc [local_rows, >= n]) as ONE host
+ *   call per rank: peer-memory panel exchange, one panel of look-ahead, no collective.  Main stream: wait for the rows of block
+ *   column kp from every rank -> U1(kp) (next block column) -> U2(kp) (rest).  Side stream (released by U1): the owner factors
+ *   diagonal block kp + 1 (gabo_potrf_diag_f64), pushes factor + block inverses to the peers with copy engines and raises their
+ *   flag; every rank solves its rows of block column kp + 1 (gabo_trsm_right_scatter_f64: the result lands in the block-column
+ *   buffer of EVERY rank by NVLink stores) and raises the peers' flags.
+ *   P_host / bc_host: HOST arrays of world * 3 device pointers (buffer b of rank r at [3 r + b]): block-column buffers [n][nb]
+ *   and diagonal-block buffers (factor [nb][nb] + inverses [nb/128][128][128]); flag_host [world]: base of every rank's 32-word
+ *   flag area ([0] diagonal block arrived, [1 + r] rows of rank r arrived); values base + kp + 1.  info_dev [ceil(n/nb)]: LAPACK
+ *   info per diagonal block (owner's entries).  winv_store: NULL or [local slots][nb/128][128][128].  ws_diag
+ *   (gabo_potrf_workspace_bytes(nb)) and ws_trsm (gabo_trsm_right_workspace_bytes(local_rows, nb)) are used on the side
+ *   stream.  ev_u1 / ev_side: events from gabo_event_create.  Same arithmetic, per entry and in order, as the single-GPU
+ *   factorisation of each rank's rows. */
+int gabo_event_create(void** ev);
+int gabo_event_destroy(void* ev);
+int gabo_potrf_cyclic_p2p_f64(int64_t n, int nb, int world, int rank, double* A_loc, int64_t lda, double sigma2,
+                              double* const* P_host, double* const* bc_host, uint32_t* const* flag_host, uint32_t base,
+                              int32_t* info_dev, double* winv_store, void* ws_diag, size_t ws_diag_bytes, void* ws_trsm,
+                              size_t ws_trsm_bytes, gabo_stream_t main_stream, gabo_stream_t side_stream, void* ev_u1, void* ev_side);
 /* gabo_solve_cyclic_p2p_f64: the forward substitution L x = b of the block-cyclically distributed factor (panel p of nb rows on
  *   rank p % world, local slot p / world; A_loc [local_rows, >= n], B_loc [local_rows, nrhs] contiguous, in place) as ONE host
  *   call per rank, no collective: at step kp the owner solves its block (inverses of the 128-blocks of the diagonal block in
