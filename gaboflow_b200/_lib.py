@@ -11,6 +11,8 @@ LIB_PATH = os.environ.get('GABO_LIB_PATH') or os.path.join(_PKG_DIR, 'libgabo_b2
 i32, i64, f64, f32, vp, sz = C.c_int, C.c_int64, C.c_double, C.c_float, C.c_void_p, C.c_size_t
 
 # name -> (restype, argtypes); mirrors include/gabo_b200.h one to one
+ABI_VERSION = 2      # == GABO_ABI_VERSION in include/gabo_b200.h (tests/test_abi_and_host.py pins the two)
+
 SIGNATURES = {
     'gabo_abi_version': (i32, []),
     'gabo_launch_count': (C.c_longlong, []),
@@ -91,7 +93,7 @@ def lib():
             fn = getattr(handle, name)   # AttributeError if the ABI and the header ever diverge
             fn.restype = res
             fn.argtypes = args
-        if handle.gabo_abi_version() != 2:
+        if handle.gabo_abi_version() != ABI_VERSION:
             raise ImportError('libgabo_b200.so ABI version mismatch; rebuild')
         _lib = handle
     return _lib
