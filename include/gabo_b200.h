@@ -222,6 +222,40 @@ int gabo_sphere_acq_fused_f64(int kind, int64_t n, int64_t M, int dim, const dou
 int gabo_expected_improvement_f64(int64_t M, const double* mean, const double* var, double fmin, double* out,
                                   gabo_stream_t stream);
 
+/* ---- SPD exponential / logarithm maps (affine-invariant metric), batched ------------------------------------------
+ * Replace expmap_tf / logmap_tf (SPD_utils_tf.py:142-167, 170-195) and the NumPy / Mandel twins (SPD_utils.py:104-177):
+ *   expmap: out[i] = S_i expm(S_i^-1 U[i]) = L f(W U W^T) L^T with f = exp;   logmap: out[i] = S_i logm(S_i^-1 X[i]), f = log
+ *   (S_i = L L^T, W = L^-1; symmetric eigenproblem in real FP64 -- the reference goes through complex64).
+ * mandel == 0: every matrix is [d*d] row-major (ld >= d*d); mandel != 0: Mandel vectors of length d(d+1)/2 (SPD_utils_tf.py:11-92).
+ * base_stride == 0: one base point for all n inputs (the reference's signature); otherwise base + i*base_stride.
+ * info[i] (may be NULL): 0, k in 1..d if the k-th Cholesky pivot of the base is not positive, d+1+k if (logmap) eigenvalue k of
+ * W X W^T is not positive; the outputs of such points are NaN.  2 <= d <= 8. */
+int gabo_spd_expmap_f64(int d, const double* U, int64_t ldu, const double* base, int64_t base_stride, int64_t n, int mandel,
+                        double* out, int64_t ldo, int32_t* info, gabo_stream_t stream);
+int gabo_spd_logmap_f64(int d, const double* X, int64_t ldx, const double* base, int64_t base_stride, int64_t n, int mandel,
+                        double* out, int64_t ldo, int32_t* info, gabo_stream_t stream);
+
+/* ---- beta sweeps: extreme eigenvalues of K_beta for a grid of beta (csrc/eig_sweep.cu) ----------------------------------
+ * Device-side form of examples/kernels/sphere/sphere_gaussian_kernel_parameters.py:83-104 and
+ * examples/kernels/spd/spd_gaussian_kernel_parameters.py:108-117 (Gram + numpy.linalg.eig minimum per beta and trial).
+ * Every kernel of the path is variance*exp(-beta*g), so K_beta = variance*exp(ratio*G) with G = log(K_beta0/variance) and
+ * ratio = beta/beta0: ONE Gram per point set serves the whole beta grid.
+ * gabo_log_gram_f64: G = min(0, log(K/variance)) elementwise (in place allowed).
+ * gabo_lanczos_sweep_f64: for each of n_mat log-Grams (G + t*g_stride, [n, ldg]) and each of n_ratios ratios (device array),
+ *   one CTA runs Lanczos with full reorthogonalisation on the operator v -> K v (entries re-formed on the fly, no second
+ *   n x n matrix), at most m_max steps (clamped to n; m_max == n gives dense-eigensolver accuracy, O(eps*||K||)), then takes
+ *   the extreme eigenvalues of the tridiagonal matrix by Sturm-count multisection.
+ *   out [n_mat*n_ratios, 4] (matrix-major): lambda_min estimate (an upper bound when the run stopped early), lambda_max
+ *   estimate, residual estimate of the minimal Ritz pair (0 if exact), steps taken.  tol > 0 enables an early exit (checked
+ *   every 32 steps) once that residual <= tol*||T||.  alpha_out / beta_out: optional [n_mat*n_ratios, m_max] tridiagonal
+ *   coefficients (both or neither).  n <= 16384, m_max <= 2048.  workspace: gabo_lanczos_sweep_workspace_bytes. */
+int gabo_log_gram_f64(const double* K, int64_t ldk, double* G, int64_t ldg, int64_t n1, int64_t n2, double variance,
+                      gabo_stream_t stream);
+size_t gabo_lanczos_sweep_workspace_bytes(int64_t n, int n_mat, int n_ratios, int m_max);
+int gabo_lanczos_sweep_f64(const double* G, int64_t ldg, int64_t g_stride, int64_t n, int n_mat, const double* ratios,
+                           int n_ratios, double variance, int m_max, double tol, unsigned long long seed, double* out,
+                           double* alpha_out, double* beta_out, void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+
 /* Diagnostic: element-wise evaluation of the lean device math that the Gram epilogues inline (csrc/gabo_math.cuh), through
  * the same batched code paths: which = 0 acos(clamp(x,-1,1)) (sphere_utils_tf.py:59-60), 1 scale*exp(x) for x <= 0
  * (kernels_sphere_tf.py:88), 2 log(x) for positive normal x (SPD_utils_tf.py:136).  For accuracy tests only. */
