@@ -41,6 +41,12 @@ SIGNATURES = {
     'gabo_spd_ai_posterior_grad_f64': (i32, [i32, i32, i64, i64, vp, vp, vp, vp, i64, f64, f64, vp, vp, f64, vp, vp, vp, vp]),
     'gabo_sphere_acq_fused_f64': (i32, [i32, i64, i64, i32, vp, i64, vp, i64, vp, i64, vp, vp, f64, f64, f64, f64, vp, vp, vp, vp, vp, vp, vp]),
     'gabo_expected_improvement_f64': (i32, [i64, vp, vp, f64, vp, vp]),
+    'gabo_spd_expmap_f64': (i32, [i32, vp, i64, vp, i64, i64, i32, vp, i64, vp, vp]),
+    'gabo_spd_logmap_f64': (i32, [i32, vp, i64, vp, i64, i64, i32, vp, i64, vp, vp]),
+    'gabo_sym_to_mandel_f64': (i32, [i32, vp, i64, i64, vp, i64, vp]),
+    'gabo_log_gram_f64': (i32, [vp, i64, vp, i64, i64, i64, f64, f64, vp]),
+    'gabo_lanczos_sweep_workspace_bytes': (sz, [i64, i32, i32, i32]),
+    'gabo_lanczos_sweep_f64': (i32, [vp, i64, i64, i64, i32, vp, i32, f64, i32, f64, C.c_ulonglong, vp, vp, vp, vp, sz, vp]),
     'gabo_math_probe_f64': (i32, [i32, vp, i64, f64, vp, vp]),
     'gabo_profile_trailing_updates': (i32, [i32]),
     'gabo_profile_trailing_read': (i32, [C.POINTER(i64), C.POINTER(f64), C.POINTER(f64), C.POINTER(f64), C.POINTER(f64)]),

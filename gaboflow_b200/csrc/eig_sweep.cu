@@ -25,12 +25,12 @@ constexpr int LZ_THREADS = 512;
 constexpr int LZ_WARPS = LZ_THREADS / 32;
 
 __global__ void log_ratio_kernel(const double* __restrict__ K, int64_t ldk, double* __restrict__ G, int64_t ldg, int64_t n1,
-                                 int64_t n2, double inv_variance) {
+                                 int64_t n2, double inv_variance, double scale) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n2) return;
     for (int64_t i = blockIdx.y; i < n1; i += gridDim.y) {
         const double g = log(K[i * ldk + j] * inv_variance);
-        G[i * ldg + j] = g > 0.0 ? 0.0 : g;          // K <= variance for every kind of the path; rounding may leave +1 ulp
+        G[i * ldg + j] = g > 0.0 ? 0.0 : scale * g;  // K <= variance for every kind of the path; rounding may leave +1 ulp
     }
 }
 
@@ -286,9 +286,9 @@ inline size_t lanczos_smem_bytes(int n, int m_max) {
 }  // namespace
 }  // namespace gabo
 
-// G = log(K / variance), clamped to <= 0.  In place allowed (G == K, ldg == ldk).
+// G = scale * min(0, log(K / variance)).  In place allowed (G == K, ldg == ldk).
 extern "C" int gabo_log_gram_f64(const double* K, int64_t ldk, double* G, int64_t ldg, int64_t n1, int64_t n2, double variance,
-                                 gabo_stream_t stream) {
+                                 double scale, gabo_stream_t stream) {
     if (n1 < 0) return -5;
     if (n2 < 0) return -6;
     if (n1 == 0 || n2 == 0) return 0;
@@ -298,7 +298,7 @@ extern "C" int gabo_log_gram_f64(const double* K, int64_t ldk, double* G, int64_
     if (ldg < n2) return -4;
     if (!(variance > 0.0)) return -7;
     dim3 grid((unsigned)gabo::ceil_div64(n2, 256), (unsigned)(n1 < 32768 ? n1 : 32768));
-    gabo::log_ratio_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(K, ldk, G, ldg, n1, n2, 1.0 / variance);
+    gabo::log_ratio_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(K, ldk, G, ldg, n1, n2, 1.0 / variance, scale);
     GABO_LAUNCH_CHECK();
     return 0;
 }

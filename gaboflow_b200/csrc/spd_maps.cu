@@ -112,6 +112,20 @@ __global__ void spd_map_kernel(const double* __restrict__ Y, int64_t ldy, const 
     if (info) info[i] = bad;
 }
 
+template <int D>
+__global__ void sym_to_mandel_kernel(const double* __restrict__ S, int64_t lds, int64_t n, double* __restrict__ out, int64_t ldo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double sqrt2 = 1.41421356237309504880;
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = r; c < D; ++c) {
+            const double v = S[i * lds + r * D + c];
+            out[i * ldo + mandel_slot<D>(r, c)] = (c != r) ? v * sqrt2 : v;     // SPD_utils_tf.py:87-89
+        }
+}
+
 template <bool IS_LOG>
 int launch_spd_map(int d, const double* Y, int64_t ldy, const double* base, int64_t base_stride, int64_t n, int mandel,
                    double* out, int64_t ldo, int32_t* info, cudaStream_t s) {
@@ -167,4 +181,27 @@ extern "C" int gabo_spd_logmap_f64(int d, const double* X, int64_t ldx, const do
     const int c = gabo::check_map_args(d, X, ldx, base, base_stride, n, mandel, out, ldo);
     if (c <= 0) return c;
     return gabo::launch_spd_map<true>(d, X, ldx, base, base_stride, n, mandel, out, ldo, info, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gabo_sym_to_mandel_f64(int d, const double* S, int64_t lds, int64_t n, double* out, int64_t ldo, gabo_stream_t stream) {
+    if (d < 2 || d > 8) return -1;
+    if (n < 0) return -4;
+    if (n == 0) return 0;
+    if (S == nullptr) return -2;
+    if (lds < (int64_t)d * d) return -3;
+    if (out == nullptr) return -5;
+    if (ldo < (int64_t)d * (d + 1) / 2) return -6;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)gabo::ceil_div64(n, 128);
+    switch (d) {
+        case 2: gabo::sym_to_mandel_kernel<2><<<grid, 128, 0, s>>>(S, lds, n, out, ldo); break;
+        case 3: gabo::sym_to_mandel_kernel<3><<<grid, 128, 0, s>>>(S, lds, n, out, ldo); break;
+        case 4: gabo::sym_to_mandel_kernel<4><<<grid, 128, 0, s>>>(S, lds, n, out, ldo); break;
+        case 5: gabo::sym_to_mandel_kernel<5><<<grid, 128, 0, s>>>(S, lds, n, out, ldo); break;
+        case 6: gabo::sym_to_mandel_kernel<6><<<grid, 128, 0, s>>>(S, lds, n, out, ldo); break;
+        case 7: gabo::sym_to_mandel_kernel<7><<<grid, 128, 0, s>>>(S, lds, n, out, ldo); break;
+        default: gabo::sym_to_mandel_kernel<8><<<grid, 128, 0, s>>>(S, lds, n, out, ldo); break;
+    }
+    GABO_LAUNCH_CHECK();
+    return 0;
 }

@@ -191,6 +191,85 @@ def spd_stein_kdiag(p: SpdPrep, beta: float, variance: float) -> torch.Tensor:
     return out
 
 
+def _spd_map(fn_name: str, Y: torch.Tensor, base: torch.Tensor, d: int, mandel: bool, want_info: bool):
+    Y = _req(Y, 'input')
+    base = _req(base, 'base')
+    w = d * (d + 1) // 2 if mandel else d * d
+    single = (Y.dim() == 1) if mandel else (Y.dim() == 2)
+    Y2 = Y.reshape(1, w) if single else Y.reshape(Y.shape[0], w)
+    Y2 = _rowmajor2d(Y2)
+    n = int(Y2.shape[0])
+    b2 = base.reshape(-1, w).contiguous()
+    if b2.shape[0] not in (1, n):
+        raise ValueError('base must be one matrix or one per input')
+    out = torch.empty((n, w), dtype=torch.float64, device=Y.device)
+    info = torch.zeros((max(n, 1),), dtype=torch.int32, device=Y.device)
+    st = getattr(_lib.lib(), fn_name)(int(d), Y2.data_ptr(), _ld(Y2), b2.data_ptr(), 0 if b2.shape[0] == 1 else w, n,
+                                     1 if mandel else 0, out.data_ptr(), w, info.data_ptr(), _stream())
+    _lib.check(fn_name, st)
+    out = out.reshape(Y.shape)
+    return (out, info[:n]) if want_info else out
+
+
+def spd_expmap(U: torch.Tensor, S: torch.Tensor, d: int, mandel: bool = False, want_info: bool = False):
+    """Expmap_S(U) = S expm(S^-1 U), batched (gabo_spd_expmap_f64).  U [n,d,d] / [d,d] matrices, or Mandel vectors [n,m] / [m]
+    with mandel=True; S one base point (same layout) or one per input."""
+    return _spd_map('gabo_spd_expmap_f64', U, S, d, mandel, want_info)
+
+
+def spd_logmap(X: torch.Tensor, S: torch.Tensor, d: int, mandel: bool = False, want_info: bool = False):
+    """Logmap_S(X) = S logm(S^-1 X), batched (gabo_spd_logmap_f64); layouts as spd_expmap."""
+    return _spd_map('gabo_spd_logmap_f64', X, S, d, mandel, want_info)
+
+
+def sym_to_mandel(S: torch.Tensor, d: int) -> torch.Tensor:
+    """[n, d, d] (or [d, d]) symmetric matrices -> Mandel vectors [n, m] (or [m]) (gabo_sym_to_mandel_f64)."""
+    S = _req(S, 'S')
+    single = S.dim() == 2
+    S2 = _rowmajor2d(S.reshape(-1, d * d))
+    n, m = int(S2.shape[0]), d * (d + 1) // 2
+    out = torch.empty((n, m), dtype=torch.float64, device=S.device)
+    st = _lib.lib().gabo_sym_to_mandel_f64(int(d), S2.data_ptr(), _ld(S2), n, out.data_ptr(), m, _stream())
+    _lib.check('gabo_sym_to_mandel_f64', st)
+    return out[0] if single else out
+
+
+def log_gram_(K: torch.Tensor, variance: float = 1.0, scale: float = 1.0) -> torch.Tensor:
+    """In place: K <- scale * min(0, log(K / variance)) (gabo_log_gram_f64); scale=1: the shared operand of lanczos_sweep,
+    scale=-1: the (squared) distance matrix behind a beta = 1 Gram."""
+    K = _req(K, 'K')
+    if K.dim() != 2 or (K.stride(1) != 1 and K.shape[1] > 1):
+        raise ValueError('K must be a row-major 2-D tensor')
+    st = _lib.lib().gabo_log_gram_f64(K.data_ptr(), _ld(K), K.data_ptr(), _ld(K), int(K.shape[0]), int(K.shape[1]), float(variance),
+                                      float(scale), _stream())
+    _lib.check('gabo_log_gram_f64', st)
+    return K
+
+
+def lanczos_sweep(G: torch.Tensor, ratios: torch.Tensor, variance: float = 1.0, m_max: Optional[int] = None, tol: float = 0.0,
+                  seed: int = 1234, want_tridiag: bool = False):
+    """Extreme eigenvalues of variance*exp(ratio*G) for every ratio and every log-Gram in G ([n,n] or [n_mat,n,n], contiguous).
+    Returns a [n_mat, n_ratios, 4] tensor: lambda_min, lambda_max, residual estimate, steps (gabo_lanczos_sweep_f64)."""
+    G = _req(G, 'G')
+    G3 = G.reshape(1, *G.shape) if G.dim() == 2 else G
+    if G3.dim() != 3 or G3.shape[1] != G3.shape[2] or not G3.is_contiguous():
+        raise ValueError('G must be a contiguous [n, n] or [n_mat, n, n] tensor')
+    ratios = _req(ratios, 'ratios').contiguous().reshape(-1)
+    n_mat, n, nb = int(G3.shape[0]), int(G3.shape[1]), int(ratios.numel())
+    m_max = min(n, 2048) if m_max is None else min(int(m_max), n, 2048)
+    lib = _lib.lib()
+    need = int(lib.gabo_lanczos_sweep_workspace_bytes(n, n_mat, nb, m_max))
+    ws = torch.empty((need,), dtype=torch.uint8, device=G.device)
+    out = torch.empty((n_mat, nb, 4), dtype=torch.float64, device=G.device)
+    al = torch.empty((n_mat, nb, m_max), dtype=torch.float64, device=G.device) if want_tridiag else None
+    be = torch.empty((n_mat, nb, m_max), dtype=torch.float64, device=G.device) if want_tridiag else None
+    st = lib.gabo_lanczos_sweep_f64(G3.data_ptr(), n, n * n, n, n_mat, ratios.data_ptr(), nb, float(variance), m_max, float(tol),
+                                    int(seed), out.data_ptr(), al.data_ptr() if al is not None else None,
+                                    be.data_ptr() if be is not None else None, ws.data_ptr(), need, _stream())
+    _lib.check('gabo_lanczos_sweep_f64', st)
+    return (out, al, be) if want_tridiag else out
+
+
 # --------------------------------------------------------------------------------------------------
 _ws_cache = {}
 

@@ -234,13 +234,19 @@ int gabo_spd_expmap_f64(int d, const double* U, int64_t ldu, const double* base,
                         double* out, int64_t ldo, int32_t* info, gabo_stream_t stream);
 int gabo_spd_logmap_f64(int d, const double* X, int64_t ldx, const double* base, int64_t base_stride, int64_t n, int mandel,
                         double* out, int64_t ldo, int32_t* info, gabo_stream_t stream);
+/* symmetric_matrix_to_vector_tf (SPD_utils_tf.py:68-92; NumPy twin SPD_utils.py:57-76): [n, d*d] matrices -> Mandel vectors
+ * [n, d(d+1)/2] (diagonal first, then super-diagonals in order, off-diagonal slots times sqrt(2)); the upper triangle is read.
+ * (The inverse, vector_to_symmetric_matrix_tf, is gabo_spd_prep_f64's out_S.) */
+int gabo_sym_to_mandel_f64(int d, const double* S, int64_t lds, int64_t n, double* out, int64_t ldo, gabo_stream_t stream);
 
 /* ---- beta sweeps: extreme eigenvalues of K_beta for a grid of beta (csrc/eig_sweep.cu) ----------------------------------
  * Device-side form of examples/kernels/sphere/sphere_gaussian_kernel_parameters.py:83-104 and
  * examples/kernels/spd/spd_gaussian_kernel_parameters.py:108-117 (Gram + numpy.linalg.eig minimum per beta and trial).
  * Every kernel of the path is variance*exp(-beta*g), so K_beta = variance*exp(ratio*G) with G = log(K_beta0/variance) and
  * ratio = beta/beta0: ONE Gram per point set serves the whole beta grid.
- * gabo_log_gram_f64: G = min(0, log(K/variance)) elementwise (in place allowed).
+ * gabo_log_gram_f64: G = scale * min(0, log(K/variance)) elementwise (in place allowed): scale = 1 gives the operand of the
+ *   sweep; scale = -1 (Laplace kinds, beta = 1) or -1 (Gaussian kinds: squared distance) recovers the distance matrix of
+ *   sphere_distance_tf (sphere_utils_tf.py:11-60) / affine_invariant_distance_tf (SPD_utils_tf.py:95-139) from a Gram.
  * gabo_lanczos_sweep_f64: for each of n_mat log-Grams (G + t*g_stride, [n, ldg]) and each of n_ratios ratios (device array),
  *   one CTA runs Lanczos with full reorthogonalisation on the operator v -> K v (entries re-formed on the fly, no second
  *   n x n matrix), at most m_max steps (clamped to n; m_max == n gives dense-eigensolver accuracy, O(eps*||K||)), then takes
@@ -250,7 +256,7 @@ int gabo_spd_logmap_f64(int d, const double* X, int64_t ldx, const double* base,
  *   every 32 steps) once that residual <= tol*||T||.  alpha_out / beta_out: optional [n_mat*n_ratios, m_max] tridiagonal
  *   coefficients (both or neither).  n <= 16384, m_max <= 2048.  workspace: gabo_lanczos_sweep_workspace_bytes. */
 int gabo_log_gram_f64(const double* K, int64_t ldk, double* G, int64_t ldg, int64_t n1, int64_t n2, double variance,
-                      gabo_stream_t stream);
+                      double scale, gabo_stream_t stream);
 size_t gabo_lanczos_sweep_workspace_bytes(int64_t n, int n_mat, int n_ratios, int m_max);
 int gabo_lanczos_sweep_f64(const double* G, int64_t ldg, int64_t g_stride, int64_t n, int n_mat, const double* ratios,
                            int n_ratios, double variance, int m_max, double tol, unsigned long long seed, double* out,

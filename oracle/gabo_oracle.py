@@ -250,6 +250,70 @@ def spd_logeuclid_K(X, X2=None, beta=1.0, variance=1.0):
 
 
 # --------------------------------------------------------------------------- #
+# SPD exponential / logarithm maps, beta sweeps  
+# --------------------------------------------------------------------------- #
+def spd_expmap(U, S):
+    """``Expmap_S(U) = S expm(S^-1 U)`` (``SPD_utils_tf.py:142-167``; NumPy twin ``SPD_utils.py:104-120``), evaluated
+    literally with ``scipy.linalg.expm`` in FP64.  U [n,d,d] or [d,d]; S [d,d]."""
+    U = np.asarray(U, dtype=np.float64)
+    if U.ndim == 2:
+        return np.real(S @ sla.expm(np.linalg.solve(S, U)))
+    return np.stack([np.real(S @ sla.expm(np.linalg.solve(S, u))) for u in U])
+
+
+def spd_logmap(X, S):
+    """``Logmap_S(X) = S logm(S^-1 X)`` (``SPD_utils_tf.py:170-195``; twin ``SPD_utils.py:123-139``) with
+    ``scipy.linalg.logm`` in FP64."""
+    X = np.asarray(X, dtype=np.float64)
+    if X.ndim == 2:
+        return np.real(S @ sla.logm(np.linalg.solve(S, X)))
+    return np.stack([np.real(S @ sla.logm(np.linalg.solve(S, x))) for x in X])
+
+
+def min_eig_sweep(K_of_beta, betas):
+    """Minimum (and maximum) eigenvalue of the Gram for each beta of a grid, as
+    ``examples/kernels/sphere/sphere_gaussian_kernel_parameters.py:83-97`` does (build the Gram, take the extreme eigenvalue;
+    the reference calls the non-symmetric ``numpy.linalg.eig`` and keeps the real parts -- ``eigvalsh`` is the symmetric
+    solver for the same spectrum).  ``K_of_beta``: callable beta -> [n,n] Gram."""
+    lo, hi = [], []
+    for b in betas:
+        w = np.linalg.eigvalsh(K_of_beta(float(b)))
+        lo.append(w[0])
+        hi.append(w[-1])
+    return np.asarray(lo), np.asarray(hi)
+
+
+def sweep_trial_sphere(dim=4, nb_samples=500, nb_sources=10, fact_cov=1.0, seed=0):
+    """One trial point set of ``sphere_gaussian_kernel_parameters.py:57-77``: samples of ``nb_sources`` isotropic Gaussians
+    around random unit means, projected to the unit sphere of R^dim."""
+    rng = np.random.RandomState(seed)
+    mean = rng.randn(nb_sources, dim)
+    mean /= np.linalg.norm(mean, axis=1)[:, None]
+    per = nb_samples // nb_sources
+    pts = [rng.multivariate_normal(mean[i], fact_cov * np.eye(dim), per) for i in range(nb_sources)]
+    X = np.concatenate(pts, axis=0)
+    return X / np.linalg.norm(X, axis=1)[:, None]
+
+
+def sweep_trial_spd(dim=2, nb_samples=500, nb_sources=10, fact_cov=1.0, seed=0):
+    """One trial of ``spd_gaussian_kernel_parameters.py:57-106``: tangent-space Gaussian samples mapped to the manifold with
+    the exponential map at ``nb_sources`` random base points (Mandel vectors), +1e-6 on the diagonal, ill-conditioned /
+    far-away samples removed (norm of the Mandel vector > 1000).  Returns Mandel vectors [n', m]."""
+    rng = np.random.RandomState(seed)
+    m = dim * (dim + 1) // 2
+    eye = np.eye(dim)
+    means = [spd_expmap(mandel_to_sym(rng.randn(1, m), dim)[0], eye) + 1e-6 * eye for _ in range(nb_sources)]
+    per = nb_samples // nb_sources
+    out = []
+    for i in range(nb_sources):
+        tang = rng.multivariate_normal(np.zeros(m), fact_cov * np.eye(m), per)
+        S = spd_expmap(mandel_to_sym(tang, dim), means[i]) + 1e-6 * eye
+        out.append(sym_to_mandel(0.5 * (S + np.swapaxes(S, -1, -2))))
+    V = np.concatenate(out, axis=0)
+    return V[np.linalg.norm(V, axis=1) <= 1000.0]
+
+
+# --------------------------------------------------------------------------- #
 # GP linear algebra  (GPflow 0.5 GPR.build_likelihood / build_predict;  [3P])
 # --------------------------------------------------------------------------- #
 def gp_cholesky(K, sigma2):

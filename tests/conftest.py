@@ -20,6 +20,13 @@ def golden():
 
 
 @pytest.fixture(scope='session')
+def mp_truth():
+    """60-digit mpmath values of the SPD kernels on the golden inputs (tests/golden/make_mp_truth.py)."""
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, 'spd_truth_mp.npz')))
+
+
+@pytest.fixture(scope='session')
 def cuda():
     import torch
     if not torch.cuda.is_available():

@@ -145,10 +145,54 @@ def spd6_fixture():
              Kai=np.exp(-Dai * Dai), Klogeuc=np.exp(-Dle * Dle), Kstein=Kst)
 
 
+def spd_maps_fixture():
+    """Exponential / logarithm maps through the reference's NumPy twins (SPD_utils.py:104-177: expmap, logmap,
+    expmap_mandel_vector, logmap_mandel_vector) for d = 2, 3, 6 -- random symmetric tangent matrices at a random SPD base
+    (legacy RNG seed 4321) -- and one beta-sweep trial of examples/kernels/sphere/sphere_gaussian_kernel_parameters.py:57-97
+    (dim = 4, 500 samples, seed 0; minimum numpy.linalg.eig value of the Gram assembled from the reference sphere_distance)."""
+    np.random.seed(4321)
+    out = {}
+    for d in (2, 3, 6):
+        n = 40
+        A = np.random.randn(d, d)
+        S = A @ A.T + 0.5 * np.eye(d)
+        U = np.random.randn(n, d, d)
+        U = 0.5 * (U + np.swapaxes(U, 1, 2))
+        X = np.stack([np.real(ref_spd.expmap(U[i], S)) for i in range(n)])
+        Uback = np.stack([np.real(ref_spd.logmap(X[i], S)) for i in range(n)])
+        s_m = ref_spd.symmetric_matrix_to_vector_mandel(S)
+        u_m = np.stack([ref_spd.symmetric_matrix_to_vector_mandel(U[i]) for i in range(n)])
+        x_m = np.stack([np.real(ref_spd.expmap_mandel_vector(u_m[i], s_m)) for i in range(n)])
+        ub_m = np.stack([np.real(ref_spd.logmap_mandel_vector(x_m[i], s_m)) for i in range(n)])
+        out.update({f'd{d}_S': S, f'd{d}_U': U, f'd{d}_exp': X, f'd{d}_log_of_exp': Uback, f'd{d}_s_mandel': s_m,
+                    f'd{d}_u_mandel': u_m, f'd{d}_exp_mandel': x_m, f'd{d}_log_of_exp_mandel': ub_m})
+    # one sweep trial, sphere_gaussian_kernel_parameters.py:57-97 with dim = 4
+    np.random.seed(0)
+    dim, nb_samples, nb_sources = 4, 500, 10
+    mean = np.array([np.random.randn(dim) for _ in range(nb_sources)])
+    mean = mean / np.linalg.norm(mean, axis=1)[:, None]
+    data = [np.random.multivariate_normal(mean[i], np.eye(dim), nb_samples // nb_sources).T for i in range(nb_sources)]
+    pts = np.array([data[i][:, n] / np.linalg.norm(data[i][:, n]) for i in range(nb_sources) for n in range(nb_samples // nb_sources)])
+    D = np.zeros((nb_samples, nb_samples))
+    for i in range(nb_samples):
+        for j in range(i + 1, nb_samples):
+            D[i, j] = D[j, i] = float(np.squeeze(ref_sphere.sphere_distance(pts[i], pts[j])))
+    betas = np.logspace(0, 2, 30)                                    # :50 (dim == 4)
+    mins = []
+    for b in betas:
+        eigvals, _ = np.linalg.eig(np.exp(-b * D * D))                # kernels_sphere_tf.py:79-88 + :93-96 of the script
+        mins.append(np.min(np.real(eigvals)))
+    out.update(sweep_x=pts, sweep_betas=betas, sweep_min_eig=np.array(mins))
+    np.savez(os.path.join(HERE, 'spd_maps_sweep.npz'), **out)
+    return out
+
+
 if __name__ == '__main__':
     s = sphere_fixture()
     print('sphere: x_man[0] =', s['x_man'][0].tolist(), ' K[0,1] =', s['Kgauss11'][0, 1])
     p = spd_fixture()
     print('spd: X[0] =', p['x_man'][0].tolist(), ' Kai[0,40] =', p['Kai11'][0, 40])
     spd6_fixture()
+    m = spd_maps_fixture()
+    print('sweep: min eig at beta[0], beta[-1] =', m['sweep_min_eig'][0], m['sweep_min_eig'][-1])
     print('wrote', sorted(f for f in os.listdir(HERE) if f.endswith('.npz')))

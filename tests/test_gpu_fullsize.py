@@ -107,5 +107,5 @@ def test_spd_gram_n16384_sampled_blocks(cuda):
         assert np.max(np.abs(got - ref)[~same] / ref[~same]) < 1e-12
         refle = orc.spd_logeuclid_K(Xm[r0:r0 + 64], Xm[cols], beta=1.0)
         gotle = Kle[r0:r0 + 64][:, torch.from_numpy(cols).cuda()].cpu().numpy()
-        assert np.max(np.abs(gotle - refle)[~same] / refle[~same]) < 2e-12
+        assert np.max(np.abs(gotle - refle)[~same] / refle[~same]) < 1e-12
     assert torch.equal(K, K.t()) and bool(torch.all(torch.diagonal(K) == 1.0))
