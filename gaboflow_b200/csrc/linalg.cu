@@ -17,6 +17,7 @@
 // Triangular solves use the same trick: the 128x128 diagonal blocks of L are inverted once (one CTA each, all in
 // parallel), after which forward/backward substitution is a chain of DMMA products (or of HBM-bound GEMV updates when
 // there are at most 4 right-hand sides).
+#include <mutex>
 #include <vector>
 #include <cstdlib>
 #include "dgemm_core.cuh"
@@ -69,7 +70,41 @@ namespace prof {
 struct Rec { cudaEvent_t e0, e1; double flops; };
 static bool g_enabled = false;
 static std::vector<Rec> g_recs;
+static std::mutex g_mutex;   // guards g_recs / g_enabled (diagnostic state, the only process-wide state besides the launch counter)
 }  // namespace prof
+
+// ---- per-device pool of (high-priority side stream, two events) for the look-ahead of gabo_potrf_f64 ------------------------
+// Thread-safe: concurrent calls on one device each take their own entry; entries are created on first use and reused.
+struct AuxCtx { int dev = -1; cudaStream_t aux = nullptr; cudaEvent_t e_main = nullptr, e_aux = nullptr; };
+static std::mutex g_aux_mutex;
+static std::vector<AuxCtx> g_aux_free;
+
+static int aux_acquire(AuxCtx* out) {
+    int dev = 0;
+    GABO_CUDA_TRY(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lk(g_aux_mutex);
+        for (size_t i = 0; i < g_aux_free.size(); ++i)
+            if (g_aux_free[i].dev == dev) {
+                *out = g_aux_free[i];
+                g_aux_free.erase(g_aux_free.begin() + (long)i);
+                return 0;
+            }
+    }
+    int least = 0, greatest = 0;
+    GABO_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    AuxCtx c;
+    c.dev = dev;
+    GABO_CUDA_TRY(cudaStreamCreateWithPriority(&c.aux, cudaStreamNonBlocking, greatest));
+    GABO_CUDA_TRY(cudaEventCreateWithFlags(&c.e_main, cudaEventDisableTiming));
+    GABO_CUDA_TRY(cudaEventCreateWithFlags(&c.e_aux, cudaEventDisableTiming));
+    *out = c;
+    return 0;
+}
+static void aux_release(const AuxCtx& c) {
+    std::lock_guard<std::mutex> lk(g_aux_mutex);
+    g_aux_free.push_back(c);
+}
 
 namespace {
 
@@ -767,15 +802,14 @@ extern "C" int gabo_potrf_f64(int64_t n, double* A, int64_t lda, double sigma2, 
 
     // Right-looking with one block column of look-ahead.  Main stream: the big trailing updates.  Auxiliary high-priority
     // stream: the factorisation of the NEXT block column, started as soon as that column alone has been updated (U1), so it
-    // runs while the rest of the trailing matrix is updated (U2).  The streams and events live only for this call.
-    int least = 0, greatest = 0;
-    GABO_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    cudaStream_t aux;
-    cudaEvent_t e_main, e_aux;
-    GABO_CUDA_TRY(cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, greatest));
-    GABO_CUDA_TRY(cudaEventCreateWithFlags(&e_main, cudaEventDisableTiming));
-    GABO_CUDA_TRY(cudaEventCreateWithFlags(&e_aux, cudaEventDisableTiming));
-    auto cleanup = [&]() { cudaEventDestroy(e_main); cudaEventDestroy(e_aux); cudaStreamDestroy(aux); };
+    // runs while the rest of the trailing matrix is updated (U2).  The auxiliary stream and the two events come from a
+    // per-device pool (created on first use, never inside later calls), so the call allocates nothing and can be captured
+    // into a CUDA graph: the auxiliary stream forks from and joins back into the caller's stream through the events.
+    AuxCtx ctx;
+    if ((rc = aux_acquire(&ctx))) return rc;
+    cudaStream_t aux = ctx.aux;
+    cudaEvent_t e_main = ctx.e_main, e_aux = ctx.e_aux;
+    auto cleanup = [&]() { aux_release(ctx); };
 #define GABO_TRY_CLEAN(expr)                                           \
     do {                                                               \
         cudaError_t e__ = (expr);                                      \
@@ -816,7 +850,7 @@ extern "C" int gabo_potrf_f64(int64_t n, double* A, int64_t lda, double sigma2, 
                 int64_t tiles = 0;   // 128 x 64 tiles on or below the diagonal
                 for (int64_t bi = 0; bi < tm; ++bi) { const int64_t c = (bi * GTM + GTM - 1) / GTN + 1; tiles += c < tn ? c : tn; }
                 rec.flops = 2.0 * (double)tiles * GTM * GTN * NB_OUT;
-                prof::g_recs.push_back(rec);
+                { std::lock_guard<std::mutex> lk(prof::g_mutex); prof::g_recs.push_back(rec); }
             }
         }
     }
@@ -1434,6 +1468,7 @@ extern "C" int gabo_expected_improvement_f64(int64_t M, const double* mean, cons
 
 // ---- profiling hook (see namespace prof above) ---------------------------------------------------------------------
 extern "C" int gabo_profile_trailing_updates(int enable) {
+    std::lock_guard<std::mutex> lk(gabo::prof::g_mutex);
     for (auto& r : gabo::prof::g_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     gabo::prof::g_recs.clear();
     gabo::prof::g_enabled = (enable != 0);
@@ -1444,6 +1479,7 @@ extern "C" int gabo_profile_trailing_updates(int enable) {
 extern "C" int gabo_profile_trailing_read(int64_t* launches, double* total_ms, double* total_flops, double* max_ms,
                                           double* max_flops) {
     int64_t n = 0; double ms = 0.0, fl = 0.0, mx = 0.0, mxf = 0.0;
+    std::lock_guard<std::mutex> lk(gabo::prof::g_mutex);
     for (auto& r : gabo::prof::g_recs) {
         GABO_CUDA_TRY(cudaEventSynchronize(r.e1));
         float t = 0.f;

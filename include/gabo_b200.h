@@ -11,9 +11,12 @@
  *   - points are rows; SPD inputs arrive as Mandel vectors [n, d(d+1)/2]
  *     (SPD_utils_tf.py:11-65 ordering: main diagonal, then super-diagonals 1..d-1, off-diagonal
  *     slots scaled by sqrt(2));
- *   - no internal allocation: scratch is passed in, sized by the matching *_workspace_bytes();
- *   - stream is a cudaStream_t passed as void*; calls are asynchronous on that stream, re-entrant,
- *     and keep no global state;
+ *   - no internal DEVICE-MEMORY allocation: scratch is passed in, sized by the matching *_workspace_bytes();
+ *   - stream is a cudaStream_t passed as void*; calls are asynchronous on that stream and thread-safe.
+ *     Process-wide state, all of it mutex- or atomic-guarded: the diagnostic launch counter, the optional
+ *     trailing-update profiler (gabo_profile_trailing_*), and a per-device pool of one high-priority side
+ *     stream + two events per concurrent gabo_potrf_f64 call (created on first use, reused afterwards, so
+ *     that call creates no CUDA objects in steady state and can be captured into a CUDA graph);
  *   - return value: 0 ok; -k = argument k (1-based) is invalid; GABO_ERR_CUDA-e = CUDA runtime
  *     error e at launch.  Numerical failures (non-SPD input, failed Cholesky pivot) are reported
  *     LAPACK-style through device-side info words, never by aborting (the reference's TF ops raise
