@@ -41,6 +41,7 @@ SIGNATURES = {
     'gabo_spd_ai_posterior_grad_f64': (i32, [i32, i32, i64, i64, vp, vp, vp, vp, i64, f64, f64, vp, vp, f64, vp, vp, vp, vp]),
     'gabo_sphere_acq_fused_f64': (i32, [i32, i64, i64, i32, vp, i64, vp, i64, vp, i64, vp, vp, f64, f64, f64, f64, vp, vp, vp, vp, vp, vp, vp]),
     'gabo_expected_improvement_f64': (i32, [i64, vp, vp, f64, vp, vp]),
+    'gabo_gp_small_batch_f64': (i32, [i64, i64, vp, i64, vp, i64, i64, vp, i32, vp, vp, vp, i64, i64, vp, vp]),
     'gabo_spd_expmap_f64': (i32, [i32, vp, i64, vp, i64, i64, i32, vp, i64, vp, vp]),
     'gabo_spd_logmap_f64': (i32, [i32, vp, i64, vp, i64, i64, i32, vp, i64, vp, vp]),
     'gabo_sym_to_mandel_f64': (i32, [i32, vp, i64, i64, vp, i64, vp]),

@@ -277,6 +277,62 @@ class GPR(Parameterized):
                                     float(self.kern.variance), self._mean_const(), float(fmin), with_grad=with_grad,
                                     out=self._fused_out)
 
+    # ---- small-N fused path (BASELINE configs 1-3: N = 5..160) ------------------------------------------------------------
+    def small_path_available(self) -> bool:
+        """One-launch evaluation (``gabo_gp_small_batch_f64``): N <= 160 points, <= 8 output columns, and a kernel of the form
+        variance * exp(-beta g) with g(x, x) = 0 -- every kernel of the path except Stein 'as coded'."""
+        from .kernel_utils.kernels_spd import SpdSteinGaussianKernel
+        n, p = int(self.X.shape[0]), int(self.Y.shape[1])
+        if isinstance(self.kern, SpdSteinGaussianKernel) or self.kern.beta_param_name() is None:
+            return False
+        return 1 <= n <= ops.GP_SMALL_MAX_N and 1 <= p <= ops.GP_SMALL_MAX_P and (n + p) * (n | 1) + (p + 2) * n + 32 <= 227 * 128
+
+    def _log_gram(self):
+        """G = log(K_beta0 / variance) of the training set, computed ONCE per training set (beta0 = the kernel's effective beta
+        at that moment): every other beta is the elementwise power exp((beta/beta0) G) formed inside the fused kernel, so the
+        pairwise geometry -- acos, or a generalised eigenproblem per pair -- is not repeated during hyper-parameter search."""
+        tag = (self.X.data_ptr(), self.X._version, tuple(self.X.shape), id(self.kern))
+        if getattr(self, '_g_tag', None) != tag:
+            beta0 = float(self.kern.beta_effective())
+            K = self.kern.K(self._kern_input()).clone()
+            ops.log_gram_(K, float(self.kern.variance))
+            if not bool(torch.isfinite(K).all().item()):
+                raise ValueError('log-Gram is not finite: entries of K underflow at beta = %g; start from a smaller beta' % beta0)
+            self._G, self._G_beta0, self._g_tag = K, beta0, tag
+        return self._G, self._G_beta0
+
+    def log_likelihood_batch(self, beta=None, variance=None, noise_variance=None, mean_const=None, with_grad=True) -> dict:
+        """Log marginal likelihood (and its gradients) for B hyper-parameter sets in ONE kernel launch -- multi-start, grid or
+        line-search candidates of the hyper-parameter fit the reference runs per BO iteration (``GPR.optimize``,
+        ``examples/kernels/sphere/sphere_kernels.py:133``).  Each argument is a scalar or an array of length B (EFFECTIVE beta,
+        kernel variance, noise variance, constant mean); omitted ones keep the model's current value.  Returns NumPy arrays:
+        ``loglik`` [B], ``info`` [B] (0, or the index of the failing Cholesky pivot: loglik is NaN there), and with ``with_grad``
+        ``grad`` = {'kern.<beta name>', 'kern.variance', 'likelihood.variance', 'mean_function.c'} -> [B] (derivatives w.r.t. the
+        parameter VALUES, as ``loglik_gradients``)."""
+        if not self.small_path_available():
+            raise NotImplementedError('log_likelihood_batch: N <= %d, <= %d output columns, non-Stein kernels'
+                                      % (ops.GP_SMALL_MAX_N, ops.GP_SMALL_MAX_P))
+        G, beta0 = self._log_gram()
+        cur = [self.kern.beta_effective(), float(self.kern.variance), float(self.likelihood.variance), self._mean_const()]
+        cols = [np.atleast_1d(np.asarray(c if a is None else a, dtype=np.float64)) for a, c in
+                zip((beta, variance, noise_variance, mean_const), cur)]
+        B = max(c.size for c in cols)
+        theta = np.empty((B, 4), dtype=np.float64)
+        for k, c in enumerate(cols):
+            if c.size not in (1, B):
+                raise ValueError('hyper-parameter arrays must have one common length')
+            theta[:, k] = c
+        theta[:, 0] /= beta0
+        out, info = ops.gp_small_batch(G, self.Y, torch.from_numpy(theta).to(G.device), want_grad=with_grad)
+        o = out.cpu().numpy()
+        # a failed set has NaN outputs, so the info words cost a second device->host read only when something failed
+        res = {'loglik': o[:, 0].copy(),
+               'info': info.cpu().numpy() if np.isnan(o[:, 0]).any() else np.zeros(B, dtype=np.int32)}
+        if with_grad:
+            res['grad'] = {'kern.' + self.kern.beta_param_name(): o[:, 1] / beta0, 'kern.variance': o[:, 2].copy(),
+                           'likelihood.variance': o[:, 3].copy(), 'mean_function.c': o[:, 4].copy()}
+        return res
+
     # ---- AutoFlow-style NumPy API ---------------------------------------------------------------------
     def compute_log_likelihood(self) -> float:
         return float(self.build_likelihood().item())
@@ -302,12 +358,14 @@ class GPR(Parameterized):
             ps.append(('mean_function.c', self.mean_function.c))
         return ps
 
-    def optimize(self, method='L-BFGS-B', maxiter=1000, analytic_grad=True, **kwargs):
+    def optimize(self, method='L-BFGS-B', maxiter=1000, analytic_grad=True, fused_small=True, **kwargs):
         """Maximise the log marginal likelihood over the free hyper-parameters, as ``GPR.optimize()`` of GPflow 0.5 does
         with SciPy L-BFGS-B in the unconstrained (softplus) space (reference call sites: ``sphere_kernels.py:133``,
         ``spd_kernels.py:155-187``).  Every objective evaluation runs on the GPU (Gram -> Cholesky -> solve -> log-lik);
         gradients are analytic (``loglik_gradients``, chained through the softplus transform); ``analytic_grad=False``
-        falls back to SciPy's finite differences.  Returns the SciPy result."""
+        falls back to SciPy's finite differences.  For N <= 160 (``small_path_available``) value and gradient come from ONE
+        fused launch per evaluation (``log_likelihood_batch``; ``fused_small=False`` keeps the tiled path).  Returns the SciPy
+        result."""
         from scipy.optimize import minimize
         ps = self._free_params()
         if not ps:
@@ -349,9 +407,22 @@ class GPR(Parameterized):
                 out[i] = -g[name] * dval
             return f, out
 
+        def objective_and_grad_small(x):     # N <= 160: value and gradient in one fused launch
+            set_all(x)
+            r = self.log_likelihood_batch(with_grad=True)
+            if int(r['info'][0]) != 0:
+                return 1e25, np.zeros_like(x)
+            out = np.empty_like(x)
+            for i, (name, p) in enumerate(ps):
+                dval = 1.0 if p.transform != 'positive' else -np.expm1(-float(p))
+                out[i] = -r['grad'][name][0] * dval
+            return -float(r['loglik'][0]), out
+
         x0 = np.array([to_free(p) for _, p in ps], dtype=np.float64)
         known = {'likelihood.variance', 'kern.variance', 'mean_function.c', 'kern.' + str(self.kern.beta_param_name())}
-        if analytic_grad and all(name in known for name, _ in ps):
+        if analytic_grad and fused_small and all(name in known for name, _ in ps) and self.small_path_available():
+            res = minimize(objective_and_grad_small, x0, method=method, jac=True, options={'maxiter': maxiter}, **kwargs)
+        elif analytic_grad and all(name in known for name, _ in ps):
             res = minimize(objective_and_grad, x0, method=method, jac=True, options={'maxiter': maxiter}, **kwargs)
         else:
             res = minimize(objective, x0, method=method, options={'maxiter': maxiter}, **kwargs)

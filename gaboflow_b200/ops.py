@@ -369,6 +369,39 @@ def gp_grad_beta(K: torch.Tensor, neg_kinv: torch.Tensor, alpha: torch.Tensor, v
     return out
 
 
+GP_SMALL_MAX_N, GP_SMALL_MAX_P = 160, 8     # GABO_GP_SMALL_MAX_N / _P of include/gabo_b200.h
+
+
+def gp_small_batch(G: torch.Tensor, Y: torch.Tensor, theta: torch.Tensor, want_grad: bool = True,
+                   Lout: Optional[torch.Tensor] = None, Vout: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                   info: Optional[torch.Tensor] = None):
+    """B fused small-N GP evaluations in one launch (gabo_gp_small_batch_f64): Ky_b = v_b exp(r_b G) + s2_b I.
+    G [n, n] log-Gram (log_gram_), Y [n, p], theta [B, 4] = (r, v, s2, c).  Returns (out [B, 5] = loglik, d/dr, d/dv, d/ds2,
+    d/dc; info [B]).  Lout [B, n, n] / Vout [B, n, p]: optional factor / whitened residual outputs."""
+    G = _req(G, 'G')
+    Y = _rowmajor2d(_req(Y, 'Y'))
+    theta = _req(theta, 'theta').contiguous()
+    if G.dim() != 2 or G.shape[0] != G.shape[1] or (G.shape[1] > 1 and G.stride(1) != 1):
+        raise ValueError('G must be a square row-major matrix')
+    n, p = int(G.shape[0]), int(Y.shape[1])
+    if Y.shape[0] != n or theta.dim() != 2 or theta.shape[1] != 4:
+        raise ValueError('Y must be [n, p] and theta [B, 4]')
+    B = int(theta.shape[0])
+    if out is None:
+        out = torch.empty((B, 5), dtype=torch.float64, device=G.device)
+    if info is None:
+        info = torch.empty((B,), dtype=torch.int32, device=G.device)
+    if Lout is not None and (Lout.shape != (B, n, n) or not Lout.is_contiguous()):
+        raise ValueError('Lout must be a contiguous [B, n, n] tensor')
+    if Vout is not None and (Vout.shape != (B, n, p) or not Vout.is_contiguous()):
+        raise ValueError('Vout must be a contiguous [B, n, p] tensor')
+    st = _lib.lib().gabo_gp_small_batch_f64(n, p, G.data_ptr(), _ld(G), Y.data_ptr(), _ld(Y), B, theta.data_ptr(), int(bool(want_grad)),
+                                            out.data_ptr(), info.data_ptr(), Lout.data_ptr() if Lout is not None else None, n, n * n,
+                                            Vout.data_ptr() if Vout is not None else None, _stream())
+    _lib.check('gabo_gp_small_batch_f64', st)
+    return out, info
+
+
 def gp_predict(A: torch.Tensor, V: torch.Tensor, kdiag: torch.Tensor, mean_const: float = 0.0):
     """mean[M,p] = A^T V + mean_const, var[M] = kdiag - colsum(A*A) from A = L^-1 K(X,X*) and V = L^-1 (y-m)."""
     _req(A, 'A'); _req(V, 'V'); _req(kdiag, 'kdiag')

@@ -35,6 +35,8 @@ extern "C" {
 
 #define GABO_ABI_VERSION 2
 #define GABO_ERR_CUDA (-1000)
+#define GABO_GP_SMALL_MAX_N 160 /* gabo_gp_small_batch_f64: training points per model */
+#define GABO_GP_SMALL_MAX_P 8   /* ... and output columns */
 #define GABO_MAX_PEERS 8      /* ranks of one NVSwitch node that exchange through peer memory */
 
 typedef void* gabo_stream_t; /* cudaStream_t */
@@ -224,6 +226,21 @@ int gabo_sphere_acq_fused_f64(int kind, int64_t n, int64_t M, int dim, const dou
  *   out = (fmin - mean) Phi(z) + var N(fmin; mean, sqrt(var)), var floored at 1e-6, z = (fmin - mean)/sqrt(var). */
 int gabo_expected_improvement_f64(int64_t M, const double* mean, const double* var, double fmin, double* out,
                                   gabo_stream_t stream);
+
+/* ---- small-N batched GP evaluation (csrc/gp_small.cu) -----------------------------------------------------------------
+ * The reference's small configurations (examples/kernels/sphere/sphere_kernels.py:125-139, examples/bo_sphere/benchmark_examples/
+ * bo_sphere_ackley_manifold.py:137-160, examples/bo_spd/benchmark_examples/bo_spd_ackley_manifold.py:159-187) evaluate GPflow 0.5's
+ * GPR.build_likelihood [third party] and its gradient hundreds of times per BO iteration at N = 5..100+.  This entry point
+ * evaluates B hyper-parameter sets in ONE launch (one CTA per set, Gram -> Cholesky -> solve -> log-density -> gradients fused
+ * in shared memory):   Ky_b = v_b exp(r_b G) + s2_b I,   G [n, ldg] = log(K_beta0 / variance0) (gabo_log_gram_f64, G_ii = 0),
+ * theta [B, 4] = {r = beta/beta0, v, s2, constant mean c};  Y [n, ldy], p columns.
+ *   out [B, 5] = { log marginal likelihood, d/dr, d/dv, d/ds2, d/dc } (the derivatives are NaN unless want_grad);
+ *   info [B]   = 0, or k if the k-th pivot of Ky_b is not positive (out[b] is then NaN);
+ *   Lout (may be NULL): lower Cholesky factor of set b at Lout + b*l_stride, row stride ldl;  Vout (may be NULL): [B, n, p] L^-1 (Y - c).
+ * 1 <= n <= GABO_GP_SMALL_MAX_N, 1 <= p <= GABO_GP_SMALL_MAX_P (and (n + p)(n | 1) + (p + 2) n + 32 doubles <= 227 KB). */
+int gabo_gp_small_batch_f64(int64_t n, int64_t p, const double* G, int64_t ldg, const double* Y, int64_t ldy, int64_t B,
+                            const double* theta, int want_grad, double* out, int32_t* info, double* Lout, int64_t ldl,
+                            int64_t l_stride, double* Vout, gabo_stream_t stream);
 
 /* ---- SPD exponential / logarithm maps (affine-invariant metric), batched ------------------------------------------
  * Replace expmap_tf / logmap_tf (SPD_utils_tf.py:142-167, 170-195) and the NumPy / Mandel twins (SPD_utils.py:104-177):
