@@ -241,11 +241,20 @@ def run_ours(args):
     # either stored into the owning GPU's HBM over NVLink from inside the kernel or recomputed by their row owner -- the
     # split (a hashed share of the cross-GPU panel pairs) balances the FP64 pipe against NVLink (dist.default_recompute_frac256).
     p2p_mirror = (world >= 2 and N % PANEL == 0 and not args.no_p2p)
-    gram_frac = int(os.environ.get('GABO_GRAM_RECOMPUTE_FRAC256', str(default_recompute_frac256(world))))
+    # GABO_GRAM_MODE=staged (default): the mirror blocks for other ranks are staged in local HBM and moved by copy engine while
+    # the kernel computes on (no SM stalls on remote stores); =direct: the kernel stores them into the peers' HBM itself.
+    gram_mode = os.environ.get('GABO_GRAM_MODE', 'staged')
+    from gaboflow_b200.dist import default_staged_frac256, make_staged_gram_state
+    gram_frac = int(os.environ.get('GABO_GRAM_RECOMPUTE_FRAC256',
+                                   str(default_staged_frac256(world) if gram_mode == 'staged' else default_recompute_frac256(world))))
+    gram_staged = None
     peers = None
     if p2p_mirror:
         peers = PeerBuffers(rows, N, dev)
         K = peers.local
+        if gram_mode == 'staged':
+            gram_staged = make_staged_gram_state(N, lay, dev, recompute_frac256=gram_frac,
+                                                 split=int(os.environ.get('GABO_GRAM_SPLIT', '1')))
     else:
         K = torch.empty((rows, N), dtype=torch.float64, device=dev)
     # panel exchange of the distributed factorisation through peer memory (GABO_DIST_P2P=0: NCCL broadcast + all-gather)
@@ -282,7 +291,7 @@ def run_ours(args):
             ops.points_gram(ops.SPHERE_GAUSSIAN, Xd, None, beta=BETA, variance=VARIANCE, out=K, uplo='mirror', workspace=ws)
         elif p2p_mirror:
             gram_block_cyclic_mirrored(ops.SPHERE_GAUSSIAN, Xd, lay, peers, BETA, VARIANCE, workspace=ws, sync=True,
-                                       recompute_frac256=gram_frac, xch=xch)
+                                       recompute_frac256=gram_frac, xch=xch, staged=gram_staged)
         else:
             for pnl in lay.my_panels():
                 sl = lay.slot(pnl) * PANEL
@@ -404,7 +413,7 @@ def run_ours(args):
     else:
         if p2p_mirror:
             gram_block_cyclic_mirrored(ops.SPHERE_GAUSSIAN, X, lay, peers, BETA, VARIANCE, workspace=ws, sync=True,
-                                       recompute_frac256=gram_frac, xch=xch)
+                                       recompute_frac256=gram_frac, xch=xch, staged=gram_staged)
         else:
             step()
         loc = np.r_[0:64, rows - 64:rows]
@@ -522,8 +531,10 @@ def run_ours(args):
                    'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2, 'seeds': [SEED_X, SEED_Y],
                    'gram_mode': 'lower tiles computed once, mirror-stored (full dense K)' if world == 1 else
                                 (f'{PANEL}-row panels block-cyclic over {world} ranks; lower tiles computed by the row owner; upper tiles: '
-                                 f'{gram_frac}/256 of the cross-GPU panel pairs recomputed by their row owner, the rest stored into the '
-                                 f'owning GPU over NVLink from inside the kernel (full dense K)' if p2p_mirror else
+                                 f'{gram_frac}/256 of the cross-GPU panel pairs recomputed by their row owner, the rest ' +
+                                 ('staged (transposed) in local HBM by the kernel and moved to the owning GPU by copy-engine 2-D '
+                                  'copies released per chunk by device flags, overlapping the kernel' if gram_staged is not None else
+                                  'stored into the owning GPU over NVLink from inside the kernel') + ' (full dense K)' if p2p_mirror else
                                  f'full rows of the dense K in {PANEL}-row panels, 1-D block-cyclic over {world} ranks'),
                    'l2': f'no flush: {rows * N * 8 / 1e9:.1f} GB of K per GPU >> 126 MB L2',
                    'parallelism': 'single GPU' if world == 1 else

@@ -17,6 +17,7 @@
 //     registers; the epilogue (clamp, acos, square, scale, exp, variance) runs on those registers and stores
 //     with streaming 128-bit writes; the symmetric mode computes lower tiles only and mirror-stores them
 //     (both stores fill whole 32-byte sectors: 64 B per quad row / per 8-lane column group).
+#include <mutex>
 #include <vector>
 #include "gabo_common.cuh"
 #include "gabo_math.cuh"
@@ -27,6 +28,8 @@ namespace {
 constexpr int BT = 128;         // output tile side
 constexpr int NTHREADS = 512;   // 16 warps, 4 x 4, 32x32 outputs each
 constexpr int NSTAGE = 2;
+
+struct StageEnt { int64_t off; int32_t first_slot; int32_t nrows; };   // staging block of (chunk, destination rank)
 
 struct GramParams {
     const double* Ap;      // packed X   [nchunks][n1_pad][KLD]
@@ -57,6 +60,16 @@ struct GramParams {
     int cyc_frac;
     int64_t cyc_lower_tiles;
     const int32_t* cyc_extra;
+    // staged mode (points_gram_kernel_1c<KLD, 2>): mirror images bound for OTHER ranks are written, transposed, into a local
+    // staging buffer laid out so that everything a chunk of row tiles owes one peer is a single dense 2-D block; per-chunk
+    // arrival counters raise a flag when the chunk is complete and copy-engine transfers (waiting on that flag on their own
+    // streams) move the block over NVLink while the kernel computes on -- the SMs never issue a remote store.
+    int cyc_nslots, cyc_split;      // local panel slots; the last cyc_split slots are chunked per row tile, the others per panel
+    double* stage;
+    const StageEnt* stage_tab;      // [chunk][8]
+    uint32_t* prog_cnt;             // [chunks] arrival counters (zeroed before the launch)
+    uint32_t* prog_flag;            // [chunks] completion flags (value = epoch)
+    uint32_t epoch;
 };
 
 constexpr int CYC_PT = 4;   // tiles per 512-row panel
@@ -69,6 +82,35 @@ __host__ __device__ __forceinline__ bool cyclic_recompute(int64_t PI, int64_t PJ
     uint32_t h = (uint32_t)PI * 0x9E3779B1u ^ (uint32_t)PJ * 0x85EBCA77u;
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
     return (int)(h & 255u) < frac256;
+}
+
+// Staged mode: the recomputed pairs of (row panel PI, destination rank rJ) are the LOWEST slots of rJ below PI, so that the
+// mirrored remainder is one contiguous row range on both sides of the copy: slots [first, count) with
+// count = slots of rJ whose panel precedes PI, first = round(count * frac256 / 256).
+__host__ __device__ __forceinline__ int64_t staged_slot_count(int64_t PI, int rJ, int world) {
+    return PI / world + ((rJ < (int)(PI % world)) ? 1 : 0);
+}
+__host__ __device__ __forceinline__ int64_t staged_first_slot(int64_t PI, int rJ, int world, int frac256) {
+    return (staged_slot_count(PI, rJ, world) * frac256 + 128) >> 8;
+}
+__host__ __device__ __forceinline__ bool staged_recompute(int64_t PI, int64_t PJ, int world, int frac256) {
+    if (PI % world == PJ % world) return false;
+    return PJ / world < staged_first_slot(PI, (int)(PJ % world), world, frac256);
+}
+template <int CYC>
+__host__ __device__ __forceinline__ bool cyclic_recompute_m(int64_t PI, int64_t PJ, int world, int frac256) {
+    return CYC == 2 ? staged_recompute(PI, PJ, world, frac256) : cyclic_recompute(PI, PJ, world, frac256);
+}
+// chunk of local row tile lt (staged mode) and the number of lower tiles it holds
+__device__ __forceinline__ int staged_chunk(const GramParams& p, int64_t lt, int64_t gbi, uint32_t& total, int& col_off,
+                                            int& width) {
+    const int64_t s = lt / CYC_PT;
+    const int rr = (int)(lt % CYC_PT);
+    const int64_t whole = p.cyc_nslots - p.cyc_split;
+    const int64_t g0 = gbi - rr;                      // first global row tile of the panel
+    if (s < whole) { total = (uint32_t)(4 * g0 + 10); col_off = rr * BT; width = CYC_PT * BT; return (int)s; }
+    total = (uint32_t)(gbi + 1); col_off = 0; width = BT;
+    return (int)(whole + (s - whole) * CYC_PT + rr);
 }
 
 // u-th tile owned by this rank -> local row tile lt, global row tile gbi, column tile bj; extra = recomputed upper tile.
@@ -286,7 +328,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel(const GramPara
 // ROLLED loop: 4 DMMA accumulators live at once instead of 16, so the epilogue needs no register rotation, indexes nothing
 // dynamically and has 8 independent entries in flight; the B fragments are re-read from shared memory per strip
 // (260 instead of 104 LDS per warp and tile, ~20 % of the shared-memory bandwidth).
-template <int KLD, bool CYC>
+template <int KLD, int CYC>
 __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr uint32_t TILE_BYTES = BT * KLD * sizeof(double);
@@ -330,9 +372,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
     };
     if (tid == 0 && my_tiles > 0) issue(0);
 
+    int prev_chunk = -1;          // staged mode: chunk of the tile this CTA finished last (-1: none to announce)
+    uint32_t prev_total = 0;
+    auto announce = [&]() {       // thread 0, after a CTA barrier that follows the tile's last store
+        __threadfence();
+        const uint32_t old = atomicAdd(p.prog_cnt + prev_chunk, 1u);
+        if (old + 1u == prev_total) {
+            __threadfence();
+            asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p.prog_flag + prev_chunk), "r"(p.epoch) : "memory");
+        }
+    };
     for (int64_t tl = 0; tl < my_tiles; ++tl) {
         const int s = (int)(tl & 1);
         __syncthreads();   // every warp is done with stage s^1 (tile tl-1): refill it while this tile computes
+        if (CYC == 2 && tid == 0 && prev_chunk >= 0) announce();
         if (tid == 0 && tl + 1 < my_tiles) issue(tl + 1);
         const int64_t t = (int64_t)blockIdx.x + tl * gridDim.x;
         int64_t bi, bj, gbi;
@@ -343,16 +396,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
         bool mirror = (p.uplo == GABO_SYMM_MIRROR) && (gcol_tile != grow_tile);
         if (CYC) {   // hybrid: recomputed upper tiles have no mirror image to write, and their lower twins do not send one
             const int64_t PI = gbi / CYC_PT, PJ = bj / CYC_PT;
-            if (extra || cyclic_recompute(PI, PJ, p.cyc_world, p.cyc_frac)) mirror = false;
+            if (extra || cyclic_recompute_m<CYC>(PI, PJ, p.cyc_world, p.cyc_frac)) mirror = false;
         }
         const bool diag_tile = p.symmetric && (gcol_tile == grow_tile);
         // where the tile and its mirror image are stored: rows of K are local rows of this rank (CYC: local row tile bi),
         // the mirror image belongs to the rank that owns global row panel bj / CYC_PT
         const int64_t lrow_tile = CYC ? bi * BT : grow_tile - p.row0;
         double* kmir_base = p.K;
+        int64_t mir_ld = ldk;            // mirror image: entry (col jj, row) at kmir_base + jj * mir_ld + global row
         if (CYC) {
             const int64_t pj = bj / CYC_PT;
-            kmir_base = p.peer[pj % p.cyc_world] + ((pj / p.cyc_world) * CYC_PT + (bj % CYC_PT)) * BT * p.ldk;
+            const int rj = (int)(pj % p.cyc_world);
+            kmir_base = p.peer[rj] + ((pj / p.cyc_world) * CYC_PT + (bj % CYC_PT)) * BT * p.ldk;
+            if (CYC == 2) {
+                prev_chunk = -1;
+                if (!extra) {
+                    int col_off, width;
+                    const int c = staged_chunk(p, bi, gbi, prev_total, col_off, width);
+                    prev_chunk = c;
+                    if (mirror && rj != p.cyc_rank) {   // bound for another rank: into this chunk's staging block for that rank
+                        const StageEnt e = p.stage_tab[c * 8 + rj];
+                        mir_ld = width;
+                        kmir_base = p.stage + e.off + ((pj / p.cyc_world - e.first_slot) * (CYC_PT * BT) + (bj % CYC_PT) * BT) * mir_ld
+                                    + col_off - grow_tile;
+                    }
+                }
+            }
         } else {
             kmir_base = p.K + gcol_tile * p.ldk;
         }
@@ -411,13 +480,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
                         if (gcol + 1 < n2) st_cs(krow + gcol + 1, v[2 * ni + 1]);
                     }
                     if (mirror) {   // K[col][row] = K[row][col]; 8 lanes of equal q write 64 contiguous bytes (own HBM or a peer's over NVLink)
-                        double* km = kmir_base + (int64_t)(wn * 32 + ni * 8 + 2 * q) * ldk + grow;
+                        double* km = kmir_base + (int64_t)(wn * 32 + ni * 8 + 2 * q) * (CYC == 2 ? mir_ld : ldk) + grow;
                         st_cs(km, v[2 * ni]);
-                        st_cs(km + ldk, v[2 * ni + 1]);
+                        st_cs(km + (CYC == 2 ? mir_ld : ldk), v[2 * ni + 1]);
                     }
                 }
             }
         }
+    }
+    if (CYC == 2) {
+        __syncthreads();
+        if (tid == 0 && prev_chunk >= 0) announce();
     }
 }
 
@@ -425,12 +498,14 @@ template <int KLD>
 int launch_points_gram(const GramParams& p, cudaStream_t stream) {
     constexpr size_t smem = (size_t)NSTAGE * 2 * BT * KLD * sizeof(double);
     GABO_CUDA_TRY(cudaFuncSetAttribute(points_gram_kernel<KLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GABO_CUDA_TRY(cudaFuncSetAttribute(points_gram_kernel_1c<KLD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GABO_CUDA_TRY(cudaFuncSetAttribute(points_gram_kernel_1c<KLD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GABO_CUDA_TRY(cudaFuncSetAttribute(points_gram_kernel_1c<KLD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GABO_CUDA_TRY(cudaFuncSetAttribute(points_gram_kernel_1c<KLD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GABO_CUDA_TRY(cudaFuncSetAttribute(points_gram_kernel_1c<KLD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = p.ntiles < (int64_t)sm_count() ? p.ntiles : (int64_t)sm_count();
     if (grid <= 0) return 0;
-    if (p.cyc_world > 0) points_gram_kernel_1c<KLD, true><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
-    else if (p.nchunks == 1) points_gram_kernel_1c<KLD, false><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
+    if (p.cyc_world > 0 && p.stage != nullptr) points_gram_kernel_1c<KLD, 2><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
+    else if (p.cyc_world > 0) points_gram_kernel_1c<KLD, 1><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
+    else if (p.nchunks == 1) points_gram_kernel_1c<KLD, 0><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
     else points_gram_kernel<KLD><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
     GABO_LAUNCH_CHECK();
     return 0;
@@ -525,6 +600,7 @@ int points_gram_impl(int kind, const Tin* X, int64_t n1, int64_t ldx, const Tin*
     p.vec_ok = ((ldk % 2) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0) ? 1 : 0;
     p.beta = beta; p.variance = variance;
     p.cyc_world = 0; p.cyc_rank = 0; p.cyc_frac = 0; p.cyc_lower_tiles = 0; p.cyc_extra = nullptr;
+    p.cyc_nslots = 0; p.cyc_split = 0; p.stage = nullptr; p.stage_tab = nullptr; p.prog_cnt = nullptr; p.prog_flag = nullptr; p.epoch = 0;
     for (int r = 0; r < 8; ++r) p.peer[r] = nullptr;
     p.tile_r0 = row0 / BT;
     p.tiles_m = ceil_div64(row1 - row0, BT);
@@ -577,7 +653,8 @@ extern "C" int gabo_points_gram_cyclic_f64(int kind, const double* X, int64_t n,
 extern "C" size_t gabo_points_gram_cyclic_workspace_bytes(int64_t n, int dim) {
     if (n <= 0 || dim <= 0) return 0;
     const int64_t npanels = (n + 511) / 512;
-    return gabo_points_gram_workspace_bytes(n, n, dim) + (size_t)(npanels * npanels + 64) * sizeof(int32_t);
+    return gabo_points_gram_workspace_bytes(n, n, dim) + (size_t)(npanels * npanels + 64) * sizeof(int32_t)
+           + (size_t)(npanels + 16) * 8 * sizeof(gabo::StageEnt) + 256;      // recompute list + staging table
 }
 
 // Same, with part of the upper triangle RECOMPUTED instead of mirrored: recompute_frac256 / 256 of the panel pairs owned
@@ -644,8 +721,178 @@ extern "C" int gabo_points_gram_cyclic_hybrid_f64(int kind, const double* X, int
         p.cyc_extra = dlist;
     }
     p.ntiles = p.cyc_lower_tiles + 16 * extra_pairs;
+    p.cyc_nslots = (int)nslots; p.cyc_split = 0; p.stage = nullptr; p.stage_tab = nullptr; p.prog_cnt = nullptr; p.prog_flag = nullptr;
+    p.epoch = 0;
     if (p.K == nullptr) return -8;
     if (pl.kld == 4) return launch_points_gram<4>(p, stream);
     if (pl.kld == 20) return launch_points_gram<20>(p, stream);
     return launch_points_gram<52>(p, stream);
+}
+
+// ---- staged mirror: the cross-GPU half of the symmetric Gram moves by copy engine, not by remote stores -------------------
+namespace gabo {
+namespace {
+struct StagePlan {
+    int64_t nslots, whole, nchunks;
+    std::vector<StageEnt> tab;      // [nchunks][8]
+    std::vector<int64_t> chunk_col0; // first global column of the chunk's block
+    std::vector<int> chunk_width;
+    size_t stage_doubles;
+};
+StagePlan make_stage_plan(int64_t n, int world, int rank, int frac256, int split) {
+    StagePlan sp;
+    const int64_t npanels = n / (BT * CYC_PT);
+    sp.nslots = (npanels > rank) ? (npanels - 1 - rank) / world + 1 : 0;
+    if (split > sp.nslots) split = (int)sp.nslots;
+    sp.whole = sp.nslots - split;
+    sp.nchunks = sp.whole + (int64_t)split * CYC_PT;
+    sp.tab.assign((size_t)sp.nchunks * 8, StageEnt{0, 0, 0});
+    sp.chunk_col0.resize((size_t)sp.nchunks);
+    sp.chunk_width.resize((size_t)sp.nchunks);
+    int64_t off = 0;
+    for (int64_t c = 0; c < sp.nchunks; ++c) {
+        const int64_t s = c < sp.whole ? c : sp.whole + (c - sp.whole) / CYC_PT;
+        const int rr0 = c < sp.whole ? 0 : (int)((c - sp.whole) % CYC_PT);
+        const int width = c < sp.whole ? CYC_PT * BT : BT;
+        const int64_t PI = s * world + rank;
+        sp.chunk_col0[(size_t)c] = PI * CYC_PT * BT + rr0 * BT;
+        sp.chunk_width[(size_t)c] = width;
+        for (int r = 0; r < world; ++r) {
+            if (r == rank) continue;
+            const int64_t count = staged_slot_count(PI, r, world), first = staged_first_slot(PI, r, world, frac256);
+            StageEnt e;
+            e.off = off; e.first_slot = (int32_t)first; e.nrows = (int32_t)((count - first) * CYC_PT * BT);
+            sp.tab[(size_t)c * 8 + r] = e;
+            off += (int64_t)e.nrows * width;
+        }
+    }
+    sp.stage_doubles = (size_t)off;
+    return sp;
+}
+
+// per-device copy streams (one per destination rank) and their join events: created on first use, reused afterwards
+struct CopyCtx { int dev; cudaStream_t st[GABO_MAX_PEERS]; cudaEvent_t ev[GABO_MAX_PEERS]; };
+std::mutex g_copy_mutex;
+std::vector<CopyCtx> g_copy_ctx;
+int copy_ctx_get(CopyCtx* out) {
+    int dev = 0;
+    GABO_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_copy_mutex);
+    for (auto& c : g_copy_ctx)
+        if (c.dev == dev) { *out = c; return 0; }
+    CopyCtx c;
+    c.dev = dev;
+    for (int i = 0; i < GABO_MAX_PEERS; ++i) {
+        GABO_CUDA_TRY(cudaStreamCreateWithFlags(&c.st[i], cudaStreamNonBlocking));
+        GABO_CUDA_TRY(cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming));
+    }
+    g_copy_ctx.push_back(c);
+    *out = c;
+    return 0;
+}
+}  // namespace
+}  // namespace gabo
+
+extern "C" size_t gabo_points_gram_cyclic_stage_bytes(int64_t n, int world, int rank, int recompute_frac256, int split) {
+    if (n <= 0 || world < 1 || world > 8 || rank < 0 || rank >= world || n % 512 != 0 || split < 0) return 0;
+    return gabo::make_stage_plan(n, world, rank, recompute_frac256, split).stage_doubles * sizeof(double) + 256;
+}
+
+extern "C" int gabo_points_gram_cyclic_staged_f64(int kind, const double* X, int64_t n, int64_t ldx, int dim, double beta,
+                                                  double variance, double* const* K_bases_host, int64_t ldk, int world,
+                                                  int rank, int recompute_frac256, int split, double* stage, size_t stage_bytes,
+                                                  uint32_t* progress, int64_t progress_words, uint32_t epoch, void* workspace,
+                                                  size_t workspace_bytes, gabo_stream_t stream_) {
+    using namespace gabo;
+    if (recompute_frac256 < 0 || recompute_frac256 > 256) return -12;
+    if (kind < GABO_SPHERE_GAUSSIAN || kind > GABO_SQDIST_GAUSSIAN) return -1;
+    if (n < 0) return -3;
+    if (n == 0) return 0;
+    if (X == nullptr) return -2;
+    if (ldx < dim) return -4;
+    if (dim < 1 || dim > 52) return -5;
+    if (K_bases_host == nullptr) return -8;
+    if (ldk < n) return -9;
+    if (world < 1 || world > 8) return -10;
+    if (rank < 0 || rank >= world) return -11;
+    if (n % (BT * CYC_PT) != 0) return -3;
+    if (split < 0) return -13;
+    for (int r = 0; r < world; ++r)
+        if (K_bases_host[r] == nullptr) return -8;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    StagePlan sp = make_stage_plan(n, world, rank, recompute_frac256, split);
+    if (sp.stage_doubles > 0 && (stage == nullptr || stage_bytes < sp.stage_doubles * sizeof(double))) return -14;
+    if (progress == nullptr || progress_words < 2 * sp.nchunks) return -16;
+    PackPlan pl = make_plan(n, n, dim);
+    const size_t pack_bytes = align256(pl.bytesA + pl.bytesNorm1);
+    if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return -19;
+    if (workspace_bytes < gabo_points_gram_cyclic_workspace_bytes(n, dim)) return -20;
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    double* Ap = reinterpret_cast<double*>(ws);
+    double* nA = reinterpret_cast<double*>(ws + pl.bytesA);
+    const bool want_norm = (kind == GABO_SQDIST_GAUSSIAN);
+    int rc = pack_dispatch<double>(pl.kld, X, n, ldx, dim, Ap, pl.n1_pad, pl.nchunks, want_norm ? nA : nullptr, stream);
+    if (rc) return rc;
+    const int64_t npanels = n / (BT * CYC_PT);
+    const int64_t nslots = sp.nslots;
+    GramParams p;
+    p.Ap = Ap; p.Bp = Ap; p.normA = want_norm ? nA : nullptr; p.normB = p.normA;
+    p.K = K_bases_host[rank]; p.ldk = ldk; p.n1_pad = pl.n1_pad; p.n2_pad = pl.n2_pad;
+    p.row0 = 0; p.row1 = n; p.n2 = n; p.nchunks = 1; p.kind = kind; p.uplo = GABO_SYMM_MIRROR; p.symmetric = 1;
+    p.vec_ok = ((ldk % 2) == 0 && (reinterpret_cast<uintptr_t>(p.K) & 15) == 0) ? 1 : 0;
+    p.beta = beta; p.variance = variance;
+    p.tile_r0 = 0; p.tiles_m = nslots * CYC_PT; p.tiles_n = n / BT;
+    p.cyc_world = world; p.cyc_rank = rank;
+    for (int r = 0; r < 8; ++r) p.peer[r] = (r < world) ? K_bases_host[r] : nullptr;
+    p.cyc_lower_tiles = 8 * (int64_t)world * nslots * (nslots - 1) + (16 * (int64_t)rank + 10) * nslots;
+    p.cyc_frac = recompute_frac256;
+    // upper blocks this rank recomputes: for every later panel PI of another rank, my lowest slots (staged_recompute)
+    std::vector<int32_t> list;
+    for (int64_t sl = 0; sl < nslots; ++sl) {
+        const int64_t PJ = sl * world + rank;
+        for (int64_t PI = PJ + 1; PI < npanels; ++PI)
+            if (staged_recompute(PI, PJ, world, recompute_frac256)) { list.push_back((int32_t)sl); list.push_back((int32_t)PI); }
+    }
+    const int64_t extra_pairs = (int64_t)list.size() / 2;
+    int32_t* dlist = reinterpret_cast<int32_t*>(ws + pack_bytes);
+    const size_t list_bytes = align256(list.size() * sizeof(int32_t) + 16);
+    StageEnt* dtab = reinterpret_cast<StageEnt*>(ws + pack_bytes + list_bytes);
+    if (pack_bytes + list_bytes + sp.tab.size() * sizeof(StageEnt) > workspace_bytes) return -20;
+    if (!list.empty())
+        GABO_CUDA_TRY(cudaMemcpyAsync(dlist, list.data(), list.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    if (!sp.tab.empty())
+        GABO_CUDA_TRY(cudaMemcpyAsync(dtab, sp.tab.data(), sp.tab.size() * sizeof(StageEnt), cudaMemcpyHostToDevice, stream));
+    p.cyc_extra = dlist;
+    p.ntiles = p.cyc_lower_tiles + 16 * extra_pairs;
+    p.cyc_nslots = (int)nslots; p.cyc_split = (int)(nslots - sp.whole);
+    p.stage = stage != nullptr ? stage : reinterpret_cast<double*>(ws);   // non-null selects the staged kernel (world == 1: unused)
+    p.stage_tab = dtab; p.prog_cnt = progress; p.prog_flag = progress + sp.nchunks; p.epoch = epoch;
+    if (sp.nchunks > 0) GABO_CUDA_TRY(cudaMemsetAsync(progress, 0, (size_t)sp.nchunks * sizeof(uint32_t), stream));
+    if (pl.kld == 4) rc = launch_points_gram<4>(p, stream);
+    else if (pl.kld == 20) rc = launch_points_gram<20>(p, stream);
+    else rc = launch_points_gram<52>(p, stream);
+    if (rc) return rc;
+    if (world == 1) return 0;
+    // copy streams: per destination rank, chunk by chunk as the kernel completes them
+    CopyCtx cc;
+    if ((rc = copy_ctx_get(&cc))) return rc;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        bool any = false;
+        for (int64_t c = 0; c < sp.nchunks; ++c) {
+            const StageEnt& e = sp.tab[(size_t)c * 8 + r];
+            if (e.nrows <= 0) continue;
+            if ((rc = gabo_flag_wait_geq(p.prog_flag + c, epoch, cc.st[r]))) return rc;
+            const int width = sp.chunk_width[(size_t)c];
+            double* dst = K_bases_host[r] + (int64_t)e.first_slot * CYC_PT * BT * ldk + sp.chunk_col0[(size_t)c];
+            GABO_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ldk * sizeof(double), stage + e.off, (size_t)width * sizeof(double),
+                                            (size_t)width * sizeof(double), (size_t)e.nrows, cudaMemcpyDefault, cc.st[r]));
+            any = true;
+        }
+        if (any) {
+            GABO_CUDA_TRY(cudaEventRecord(cc.ev[r], cc.st[r]));
+            GABO_CUDA_TRY(cudaStreamWaitEvent(stream, cc.ev[r], 0));
+        }
+    }
+    return 0;
 }

@@ -493,18 +493,43 @@ def default_recompute_frac256(world: int) -> int:
     return {1: 0, 2: 80, 3: 128}.get(int(world), 152 if int(world) == 4 else 160)
 
 
+def default_staged_frac256(world: int) -> int:
+    """Recomputed share (of 256) for the STAGED Gram (copy-engine mirror blocks): the SMs no longer stall on remote stores, so
+    the balance point is FP64 pipe vs NVLink bandwidth alone -- lower-tile time (1 + 0.88 f) against (1 - f) x cross-rank bytes
+    per rank / ~750 GB/s.  Measured on B200 / NVSwitch at N = 65536, D = 51 (tools/dist_gram_check.py, GABO_GRAM_MODE=staged)."""
+    return {1: 0, 2: 0, 3: 16, 4: 32}.get(int(world), 48)
+
+
+def make_staged_gram_state(n: int, layout: BlockCyclic, device, recompute_frac256: Optional[int] = None, split: int = 1):
+    """Scratch of the staged Gram for this rank (ops.StagedGramState): allocate once, reuse for every Gram of that size."""
+    from . import ops
+    f = default_staged_frac256(layout.world) if recompute_frac256 is None else int(recompute_frac256)
+    return ops.StagedGramState(n, layout.world, layout.rank, f, split, device)
+
+
 def gram_block_cyclic_mirrored(kind: int, X: torch.Tensor, layout: BlockCyclic, peers: PeerBuffers, beta: float,
                                variance: float, workspace=None, group=None, sync: bool = True,
-                               recompute_frac256: int = 0, xch: Optional['PanelExchange'] = None) -> torch.Tensor:
+                               recompute_frac256: int = 0, xch: Optional['PanelExchange'] = None, staged=None) -> torch.Tensor:
     """Symmetric Gram K(X,X) into the block-cyclic row panels of all ranks: each rank computes the lower tiles of its own
     panels once and writes their mirror images into the owning peers' memory from inside the kernel.  With
     ``recompute_frac256 = f``, f/256 of the panel pairs owned by different ranks are recomputed by the row owner instead of
-    mirrored, which balances the FP64 pipe against NVLink."""
+    mirrored, which balances the FP64 pipe against NVLink.  ``staged`` (``make_staged_gram_state``): the mirror blocks for other
+    ranks are staged locally and moved by copy engine instead of being stored remotely by the SMs.
+
+    Contract between successive Grams into the same buffers: a rank may start writing the next K into a peer while that peer
+    still reads the previous one -- callers must end every use of K with a rank-wide synchronisation (bench.py: the all-reduce
+    and host read of the log-likelihood)."""
     from . import ops
     if layout.nb != 512:
         raise ValueError('the mirrored Gram uses 512-row panels')
-    ops.points_gram_cyclic(kind, X, peers.ptrs, int(peers.local.stride(0)), layout.world, layout.rank, beta, variance, workspace,
-                           recompute_frac256=recompute_frac256)
+    if staged is not None:
+        # mirror blocks for other ranks leave through a local staging buffer + copy engines (``recompute_frac256`` is the one
+        # the state was built with); on return the stream already waits for this rank's outgoing copies
+        ops.points_gram_cyclic_staged(kind, X, peers.ptrs, int(peers.local.stride(0)), layout.world, layout.rank, staged, beta,
+                                      variance, workspace)
+    else:
+        ops.points_gram_cyclic(kind, X, peers.ptrs, int(peers.local.stride(0)), layout.world, layout.rank, beta, variance,
+                               workspace, recompute_frac256=recompute_frac256)
     if sync and xch is not None and layout.world > 1:
         # stream-ordered handshake instead of a host barrier: tell every peer that this rank's mirror stores are out, and
         # make the stream wait for the same message from every peer (flags 16 + source rank of the exchange area).  The

@@ -599,6 +599,44 @@ def points_gram_cyclic(kind: int, X: torch.Tensor, bases, ldk: int, world: int, 
     _lib.check('gabo_points_gram_cyclic_hybrid_f64', st)
 
 
+class StagedGramState:
+    """Device scratch of the staged block-cyclic Gram (gabo_points_gram_cyclic_staged_f64), allocated once per (n, world, rank,
+    share, split): the local staging buffer for the mirror blocks bound for other ranks, the per-chunk progress words and the
+    epoch counter."""
+
+    def __init__(self, n: int, world: int, rank: int, recompute_frac256: int, split: int, device):
+        L = _lib.lib()
+        self.key = (int(n), int(world), int(rank), int(recompute_frac256), int(split))
+        nbytes = int(L.gabo_points_gram_cyclic_stage_bytes(*self.key))
+        self.stage = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        npanels = n // 512
+        nslots = (npanels - 1 - rank) // world + 1 if npanels > rank else 0
+        self.progress = torch.zeros(2 * (nslots + 3 * split) + 8, dtype=torch.int32, device=device)
+        self.epoch = 0
+
+
+def points_gram_cyclic_staged(kind: int, X: torch.Tensor, bases, ldk: int, world: int, rank: int, state: StagedGramState,
+                              beta: float = 1.0, variance: float = 1.0, workspace: Optional[torch.Tensor] = None) -> None:
+    """Block-cyclic symmetric Gram whose cross-GPU mirror blocks travel by copy engine from a local staging buffer
+    (gabo_points_gram_cyclic_staged_f64); same result, bit for bit, as points_gram_cyclic."""
+    import ctypes as C
+    L = _lib.lib()
+    X = _rowmajor2d(_req(X, 'X'))
+    n, dim = int(X.shape[0]), int(X.shape[1])
+    if state.key[:3] != (n, int(world), int(rank)):
+        raise ValueError('StagedGramState was built for another (n, world, rank)')
+    nbytes = int(L.gabo_points_gram_cyclic_workspace_bytes(n, dim))
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=X.device)
+    arr = (C.c_void_p * world)(*[C.c_void_p(int(b)) for b in bases])
+    state.epoch += 1
+    st = L.gabo_points_gram_cyclic_staged_f64(int(kind), X.data_ptr(), n, _ld(X), dim, float(beta), float(variance),
+                                              C.cast(arr, C.c_void_p), int(ldk), int(world), int(rank), state.key[3], state.key[4],
+                                              state.stage.data_ptr(), state.stage.numel(), state.progress.data_ptr(),
+                                              state.progress.numel(), state.epoch, workspace.data_ptr(), workspace.numel(), _stream())
+    _lib.check('gabo_points_gram_cyclic_staged_f64', st)
+
+
 def sphere_posterior_grad(kind: int, X: torch.Tensor, Kx: torch.Tensor, alpha: torch.Tensor, Bm: torch.Tensor, beta: float,
                           variance: float, mean: Optional[torch.Tensor] = None, var: Optional[torch.Tensor] = None,
                           fmin: Optional[float] = None):

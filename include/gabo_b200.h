@@ -327,6 +327,23 @@ size_t gabo_points_gram_cyclic_workspace_bytes(int64_t n, int dim);
 int gabo_points_gram_cyclic_hybrid_f64(int kind, const double* X, int64_t n, int64_t ldx, int dim, double beta,
                                        double variance, double* const* K_bases_host, int64_t ldk, int world, int rank,
                                        int recompute_frac256, void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+/* gabo_points_gram_cyclic_staged_f64: the same distributed symmetric Gram, but no SM ever stores to a peer: mirror images
+ *   bound for other ranks are written (transposed) into a LOCAL staging buffer, laid out so that everything a chunk of this
+ *   rank's row tiles owes one peer is a single dense 2-D block; the kernel counts finished tiles per chunk and raises a flag
+ *   when a chunk is complete, and copy-engine transfers (cudaMemcpy2DAsync on per-peer side streams, each released by
+ *   cuStreamWaitValue32 on that flag) move the blocks over NVLink while the kernel computes on.  Chunks: one per local panel,
+ *   the last `split` panels one per 128-row tile.  recompute_frac256 / 256 of each (row panel, destination rank) block list --
+ *   its LOWEST slots, so that the mirrored remainder stays one contiguous row range -- is recomputed by the destination rank
+ *   instead (the recomputed tiles run last and cover the tail of the copies).  On return the caller's stream waits for this
+ *   rank's outgoing copies; completion across ranks is the caller's flag handshake, as for the functions above.
+ *   stage: gabo_points_gram_cyclic_stage_bytes(n, world, rank, recompute_frac256, split) bytes of local device memory;
+ *   progress: >= 2 * (local panels + 3 * split) 32-bit words of local device memory, owned by this call sequence;
+ *   epoch: strictly increasing over successive calls on the same `progress` (> 0).  Bit-identical to the other two. */
+size_t gabo_points_gram_cyclic_stage_bytes(int64_t n, int world, int rank, int recompute_frac256, int split);
+int gabo_points_gram_cyclic_staged_f64(int kind, const double* X, int64_t n, int64_t ldx, int dim, double beta, double variance,
+                                       double* const* K_bases_host, int64_t ldk, int world, int rank, int recompute_frac256,
+                                       int split, double* stage, size_t stage_bytes, uint32_t* progress, int64_t progress_words,
+                                       uint32_t epoch, void* workspace, size_t workspace_bytes, gabo_stream_t stream);
 int gabo_trsm_right_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, double* A, int64_t lda,
                         void* workspace, size_t workspace_bytes, gabo_stream_t stream);
 /* gabo_potrf_diag_f64: factor one diagonal block (nb <= 512) in place AND return the inverses of its 128 x 128 diagonal

@@ -92,6 +92,36 @@ def test_cyclic_mirrored_gram_single_process(cuda, world, mod):
         assert torch.equal(bufs[r], full[rows])
 
 
+@pytest.mark.parametrize('split', [0, 1, 2])
+@pytest.mark.parametrize('frac', [0, 48, 128, 256])
+@pytest.mark.parametrize('world', [1, 2, 3, 8])
+def test_cyclic_staged_gram_single_process(cuda, world, frac, split):
+    """gabo_points_gram_cyclic_staged_f64 with all `world` ranks emulated on one GPU: mirror blocks bound for other ranks go
+    through the local staging buffer and copy-engine 2-D copies released by the kernel's per-chunk flags.  Every entry is written
+    (NaN pre-fill) with the bits of the single-GPU mirrored Gram; run twice to exercise the epoch / counter reset."""
+    from gaboflow_b200 import ops
+    from gaboflow_b200.dist import BlockCyclic
+    from oracle import gabo_oracle as orc
+    n = 512 * 11
+    X = torch.from_numpy(orc.synth_sphere(n, 51, seed=8)).cuda()
+    lays = [BlockCyclic(n, 512, world, r) for r in range(world)]
+    bufs = [torch.full((max(l.local_rows, 1), n), float('nan'), dtype=torch.float64, device='cuda') for l in lays]
+    ptrs = [b.data_ptr() for b in bufs]
+    states = [ops.StagedGramState(n, world, r, frac, split, 'cuda') for r in range(world)]
+    full = ops.points_gram(ops.SPHERE_GAUSSIAN, X, None, beta=2.0, uplo='mirror')
+    for rep in range(2):
+        for b in bufs:
+            b.fill_(float('nan'))
+        for r in range(world):
+            ops.points_gram_cyclic_staged(ops.SPHERE_GAUSSIAN, X, ptrs, n, world, r, states[r], beta=2.0, variance=1.0)
+        torch.cuda.synchronize()
+        for r in range(world):
+            if lays[r].local_rows == 0:
+                continue
+            rows = lays[r].global_rows().cuda()
+            assert torch.equal(bufs[r][:lays[r].local_rows], full[rows]), (rep, r)
+
+
 @pytest.mark.parametrize('kind_name', ['ai_gauss', 'ai_laplace', 'stein'])
 @pytest.mark.parametrize('world', [1, 2, 3, 8])
 def test_cyclic_spd_gram_single_process(cuda, world, kind_name):
