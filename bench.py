@@ -254,7 +254,8 @@ def run_ours(args):
         K = peers.local
         if gram_mode == 'staged':
             gram_staged = make_staged_gram_state(N, lay, dev, recompute_frac256=gram_frac,
-                                                 split=int(os.environ.get('GABO_GRAM_SPLIT', '1')))
+                                                 split=int(os.environ.get('GABO_GRAM_SPLIT', '1')),
+                                                 direct_frac256=int(os.environ.get('GABO_GRAM_DIRECT256', '0')))
     else:
         K = torch.empty((rows, N), dtype=torch.float64, device=dev)
     # panel exchange of the distributed factorisation through peer memory (GABO_DIST_P2P=0: NCCL broadcast + all-gather)

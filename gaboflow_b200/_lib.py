@@ -55,8 +55,8 @@ SIGNATURES = {
     'gabo_points_gram_cyclic_f64': (i32, [i32, vp, i64, i64, i32, f64, f64, vp, i64, i32, i32, vp, sz, vp]),
     'gabo_points_gram_cyclic_workspace_bytes': (sz, [i64, i32]),
     'gabo_points_gram_cyclic_hybrid_f64': (i32, [i32, vp, i64, i64, i32, f64, f64, vp, i64, i32, i32, i32, vp, sz, vp]),
-    'gabo_points_gram_cyclic_stage_bytes': (sz, [i64, i32, i32, i32, i32]),
-    'gabo_points_gram_cyclic_staged_f64': (i32, [i32, vp, i64, i64, i32, f64, f64, vp, i64, i32, i32, i32, i32, vp, sz, vp, i64, C.c_uint32, vp, sz, vp]),
+    'gabo_points_gram_cyclic_stage_bytes': (sz, [i64, i32, i32, i32, i32, i32]),
+    'gabo_points_gram_cyclic_staged_f64': (i32, [i32, vp, i64, i64, i32, f64, f64, vp, i64, i32, i32, i32, i32, i32, vp, sz, vp, i64, C.c_uint32, vp, sz, vp]),
     'gabo_enable_peer_access': (i32, [i32]),
     'gabo_shared_alloc': (i32, [sz, C.POINTER(vp)]),
     'gabo_shared_free': (i32, [vp]),
@@ -75,6 +75,7 @@ SIGNATURES = {
     'gabo_event_create': (i32, [C.POINTER(vp)]),
     'gabo_event_destroy': (i32, [vp]),
     'gabo_potrf_cyclic_p2p_f64': (i32, [i64, i32, i32, i32, vp, i64, f64, vp, vp, vp, C.c_uint32, vp, vp, vp, sz, vp, sz, vp, vp, vp, vp]),
+    'gabo_potrf_cyclic_chain_f64': (i32, [i64, i32, i32, i32, vp, i64, f64, i32, vp, vp, vp, C.c_uint32, vp, vp, vp, sz, vp, sz, vp, vp]),
     'gabo_solve_cyclic_p2p_f64': (i32, [i64, i32, i32, i32, vp, i64, vp, i64, i64, vp, vp, vp, C.c_uint32, vp, sz, vp]),
     'gabo_syrk_cyclic_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, i32, vp]),
     'gabo_solve_update_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]),

@@ -414,8 +414,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) points_gram_kernel_1c(const GramP
                     int col_off, width;
                     const int c = staged_chunk(p, bi, gbi, prev_total, col_off, width);
                     prev_chunk = c;
-                    if (mirror && rj != p.cyc_rank) {   // bound for another rank: into this chunk's staging block for that rank
-                        const StageEnt e = p.stage_tab[c * 8 + rj];
+                    const StageEnt e = p.stage_tab[c * 8 + rj];
+                    // bound for another rank: slots below the staged range are stored remotely from here (kmir_base above),
+                    // the others go into this chunk's staging block for that rank
+                    if (mirror && rj != p.cyc_rank && pj / p.cyc_world >= e.first_slot) {
                         mir_ld = width;
                         kmir_base = p.stage + e.off + ((pj / p.cyc_world - e.first_slot) * (CYC_PT * BT) + (bj % CYC_PT) * BT) * mir_ld
                                     + col_off - grow_tile;
@@ -739,7 +741,7 @@ struct StagePlan {
     std::vector<int> chunk_width;
     size_t stage_doubles;
 };
-StagePlan make_stage_plan(int64_t n, int world, int rank, int frac256, int split) {
+StagePlan make_stage_plan(int64_t n, int world, int rank, int frac256, int direct256, int split) {
     StagePlan sp;
     const int64_t npanels = n / (BT * CYC_PT);
     sp.nslots = (npanels > rank) ? (npanels - 1 - rank) / world + 1 : 0;
@@ -759,7 +761,10 @@ StagePlan make_stage_plan(int64_t n, int world, int rank, int frac256, int split
         sp.chunk_width[(size_t)c] = width;
         for (int r = 0; r < world; ++r) {
             if (r == rank) continue;
-            const int64_t count = staged_slot_count(PI, r, world), first = staged_first_slot(PI, r, world, frac256);
+            // slots [0, a) recomputed by rank r, [a, first) stored remotely by the kernel, [first, count) staged + copy engine
+            const int64_t count = staged_slot_count(PI, r, world), a = staged_first_slot(PI, r, world, frac256);
+            int64_t first = a + ((count * direct256 + 128) >> 8);
+            if (first > count) first = count;
             StageEnt e;
             e.off = off; e.first_slot = (int32_t)first; e.nrows = (int32_t)((count - first) * CYC_PT * BT);
             sp.tab[(size_t)c * 8 + r] = e;
@@ -793,18 +798,22 @@ int copy_ctx_get(CopyCtx* out) {
 }  // namespace
 }  // namespace gabo
 
-extern "C" size_t gabo_points_gram_cyclic_stage_bytes(int64_t n, int world, int rank, int recompute_frac256, int split) {
+extern "C" size_t gabo_points_gram_cyclic_stage_bytes(int64_t n, int world, int rank, int recompute_frac256, int direct_frac256,
+                                                      int split) {
     if (n <= 0 || world < 1 || world > 8 || rank < 0 || rank >= world || n % 512 != 0 || split < 0) return 0;
-    return gabo::make_stage_plan(n, world, rank, recompute_frac256, split).stage_doubles * sizeof(double) + 256;
+    if (recompute_frac256 < 0 || recompute_frac256 > 256 || direct_frac256 < 0 || direct_frac256 > 256) return 0;
+    return gabo::make_stage_plan(n, world, rank, recompute_frac256, direct_frac256, split).stage_doubles * sizeof(double) + 256;
 }
 
 extern "C" int gabo_points_gram_cyclic_staged_f64(int kind, const double* X, int64_t n, int64_t ldx, int dim, double beta,
                                                   double variance, double* const* K_bases_host, int64_t ldk, int world,
-                                                  int rank, int recompute_frac256, int split, double* stage, size_t stage_bytes,
+                                                  int rank, int recompute_frac256, int direct_frac256, int split, double* stage,
+                                                  size_t stage_bytes,
                                                   uint32_t* progress, int64_t progress_words, uint32_t epoch, void* workspace,
                                                   size_t workspace_bytes, gabo_stream_t stream_) {
     using namespace gabo;
     if (recompute_frac256 < 0 || recompute_frac256 > 256) return -12;
+    if (direct_frac256 < 0 || direct_frac256 > 256) return -13;
     if (kind < GABO_SPHERE_GAUSSIAN || kind > GABO_SQDIST_GAUSSIAN) return -1;
     if (n < 0) return -3;
     if (n == 0) return 0;
@@ -816,13 +825,13 @@ extern "C" int gabo_points_gram_cyclic_staged_f64(int kind, const double* X, int
     if (world < 1 || world > 8) return -10;
     if (rank < 0 || rank >= world) return -11;
     if (n % (BT * CYC_PT) != 0) return -3;
-    if (split < 0) return -13;
+    if (split < 0) return -14;
     for (int r = 0; r < world; ++r)
         if (K_bases_host[r] == nullptr) return -8;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    StagePlan sp = make_stage_plan(n, world, rank, recompute_frac256, split);
-    if (sp.stage_doubles > 0 && (stage == nullptr || stage_bytes < sp.stage_doubles * sizeof(double))) return -14;
-    if (progress == nullptr || progress_words < 2 * sp.nchunks) return -16;
+    StagePlan sp = make_stage_plan(n, world, rank, recompute_frac256, direct_frac256, split);
+    if (sp.stage_doubles > 0 && (stage == nullptr || stage_bytes < sp.stage_doubles * sizeof(double))) return -15;
+    if (progress == nullptr || progress_words < 2 * sp.nchunks) return -17;
     PackPlan pl = make_plan(n, n, dim);
     const size_t pack_bytes = align256(pl.bytesA + pl.bytesNorm1);
     if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return -19;

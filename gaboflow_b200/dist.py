@@ -500,11 +500,14 @@ def default_staged_frac256(world: int) -> int:
     return {1: 0, 2: 0, 3: 16, 4: 32}.get(int(world), 48)
 
 
-def make_staged_gram_state(n: int, layout: BlockCyclic, device, recompute_frac256: Optional[int] = None, split: int = 1):
-    """Scratch of the staged Gram for this rank (ops.StagedGramState): allocate once, reuse for every Gram of that size."""
+def make_staged_gram_state(n: int, layout: BlockCyclic, device, recompute_frac256: Optional[int] = None, split: int = 1,
+                           direct_frac256: int = 0):
+    """Scratch of the staged Gram for this rank (ops.StagedGramState): allocate once, reuse for every Gram of that size.
+    Of every (row panel, destination rank) block list, recompute_frac256 / 256 is recomputed by the destination, the next
+    direct_frac256 / 256 stored remotely by the kernel, the rest staged locally and moved by copy engine."""
     from . import ops
     f = default_staged_frac256(layout.world) if recompute_frac256 is None else int(recompute_frac256)
-    return ops.StagedGramState(n, layout.world, layout.rank, f, split, device)
+    return ops.StagedGramState(n, layout.world, layout.rank, f, split, device, direct_frac256=int(direct_frac256))
 
 
 def gram_block_cyclic_mirrored(kind: int, X: torch.Tensor, layout: BlockCyclic, peers: PeerBuffers, beta: float,
@@ -598,6 +601,9 @@ class PanelExchange:
         self.nwb = (self.nb + 127) // 128
         self.p_elems = self.n * self.nb
         self.bc_elems = self.nb * self.nb + self.nwb * 128 * 128
+        # the critical-chain schedule lets the owners run up to `world` panels ahead of a rank that owns none of them, so the
+        # buffers rotate over world + 1 (the look-ahead schedule uses the first three)
+        self.NBUF = max(3, layout.world + 1)
         self.flag_off = self.NBUF * (self.p_elems + self.bc_elems)          # in doubles
         total = self.flag_off + 32
         self.peers = PeerBuffers(1, total, device, group=group)
@@ -671,7 +677,8 @@ class PanelExchange:
                 st = {'npan': npan, 'nslots': nslots, 'rows': rows,
                       'info': torch.zeros((npan,), dtype=torch.int32, device=self.device),
                       'winv': torch.empty((nslots, self.nwb, 128, 128), dtype=torch.float64, device=self.device),
-                      'ws_diag': torch.empty(int(L.gabo_potrf_workspace_bytes(self.nb)), dtype=torch.uint8, device=self.device),
+                      'ws_diag': torch.empty(int(max(L.gabo_potrf_workspace_bytes(self.nb), L.gabo_trsm_right_workspace_bytes(self.nb, self.nb))),
+                                             dtype=torch.uint8, device=self.device),
                       'ws_trsm': torch.empty(int(L.gabo_trsm_right_workspace_bytes(rows, self.nb)), dtype=torch.uint8, device=self.device)}
             self._cstate = st
         return st
@@ -728,15 +735,31 @@ def potrf_block_cyclic_p2p_(A_loc: torch.Tensor, layout: BlockCyclic, sigma2: fl
         import ctypes as C
         from . import _lib
         st = xch.c_state(npan, max(len(my), 1), max(rows_f, 1))
+        if os.environ.get('GABO_DIST_SCHED', 'chain') == 'chain' and nb == 512:
+            # critical-chain schedule (gabo_potrf_cyclic_chain_f64): next owner first, U1 released by one 512-block, deeper buffers
+            nbuf = xch.NBUF
+            Ph = (C.c_void_p * (nbuf * W))(*[xch.p_ptr(r if W > 1 else me, b) for r in range(W) for b in range(nbuf)])
+            Bh = (C.c_void_p * (nbuf * W))(*[xch.bc_ptr(r if W > 1 else me, b) for r in range(W) for b in range(nbuf)])
+            Fh = (C.c_void_p * W)(*[xch.flag_ptr(r if W > 1 else me, 0) for r in range(W)])
+            rc = _lib.lib().gabo_potrf_cyclic_chain_f64(n, nb, W, rank, A_loc.data_ptr(), max(int(A_loc.stride(0)), int(A_loc.shape[1])),
+                                                       float(sigma2), nbuf, C.cast(Ph, C.c_void_p), C.cast(Bh, C.c_void_p),
+                                                       C.cast(Fh, C.c_void_p), base, st['info'].data_ptr(),
+                                                       st['winv'].data_ptr() if winv_store is not None else None,
+                                                       st['ws_diag'].data_ptr(), st['ws_diag'].numel(), st['ws_trsm'].data_ptr(),
+                                                       st['ws_trsm'].numel(), main.cuda_stream, side.cuda_stream)
+            _lib.check('gabo_potrf_cyclic_chain_f64', rc)
+        else:
+            rc = None
         Ph = (C.c_void_p * (3 * W))(*[xch.p_ptr(r if W > 1 else me, b) for r in range(W) for b in range(3)])
         Bh = (C.c_void_p * (3 * W))(*[xch.bc_ptr(r if W > 1 else me, b) for r in range(W) for b in range(3)])
         Fh = (C.c_void_p * W)(*[xch.flag_ptr(r if W > 1 else me, 0) for r in range(W)])
-        rc = _lib.lib().gabo_potrf_cyclic_p2p_f64(n, nb, W, rank, A_loc.data_ptr(), max(int(A_loc.stride(0)), int(A_loc.shape[1])),
-                                                 float(sigma2), C.cast(Ph, C.c_void_p), C.cast(Bh, C.c_void_p), C.cast(Fh, C.c_void_p),
-                                                 base, st['info'].data_ptr(), st['winv'].data_ptr() if winv_store is not None else None,
-                                                 st['ws_diag'].data_ptr(), st['ws_diag'].numel(), st['ws_trsm'].data_ptr(),
-                                                 st['ws_trsm'].numel(), main.cuda_stream, side.cuda_stream, xch.ev_u1, xch.ev_side)
-        _lib.check('gabo_potrf_cyclic_p2p_f64', rc)
+        if rc is None:
+            rc = _lib.lib().gabo_potrf_cyclic_p2p_f64(n, nb, W, rank, A_loc.data_ptr(), max(int(A_loc.stride(0)), int(A_loc.shape[1])),
+                                                     float(sigma2), C.cast(Ph, C.c_void_p), C.cast(Bh, C.c_void_p), C.cast(Fh, C.c_void_p),
+                                                     base, st['info'].data_ptr(), st['winv'].data_ptr() if winv_store is not None else None,
+                                                     st['ws_diag'].data_ptr(), st['ws_diag'].numel(), st['ws_trsm'].data_ptr(),
+                                                     st['ws_trsm'].numel(), main.cuda_stream, side.cuda_stream, xch.ev_u1, xch.ev_side)
+            _lib.check('gabo_potrf_cyclic_p2p_f64', rc)
         if winv_store is not None:
             for p_ in my:                                   # views: valid until the next factorisation through this exchange
                 winv_store[p_] = st['winv'][layout.slot(p_)]

@@ -604,9 +604,9 @@ class StagedGramState:
     share, split): the local staging buffer for the mirror blocks bound for other ranks, the per-chunk progress words and the
     epoch counter."""
 
-    def __init__(self, n: int, world: int, rank: int, recompute_frac256: int, split: int, device):
+    def __init__(self, n: int, world: int, rank: int, recompute_frac256: int, split: int, device, direct_frac256: int = 0):
         L = _lib.lib()
-        self.key = (int(n), int(world), int(rank), int(recompute_frac256), int(split))
+        self.key = (int(n), int(world), int(rank), int(recompute_frac256), int(direct_frac256), int(split))
         nbytes = int(L.gabo_points_gram_cyclic_stage_bytes(*self.key))
         self.stage = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
         npanels = n // 512
@@ -632,7 +632,7 @@ def points_gram_cyclic_staged(kind: int, X: torch.Tensor, bases, ldk: int, world
     state.epoch += 1
     st = L.gabo_points_gram_cyclic_staged_f64(int(kind), X.data_ptr(), n, _ld(X), dim, float(beta), float(variance),
                                               C.cast(arr, C.c_void_p), int(ldk), int(world), int(rank), state.key[3], state.key[4],
-                                              state.stage.data_ptr(), state.stage.numel(), state.progress.data_ptr(),
+                                              state.key[5], state.stage.data_ptr(), state.stage.numel(), state.progress.data_ptr(),
                                               state.progress.numel(), state.epoch, workspace.data_ptr(), workspace.numel(), _stream())
     _lib.check('gabo_points_gram_cyclic_staged_f64', st)
 

@@ -334,16 +334,19 @@ int gabo_points_gram_cyclic_hybrid_f64(int kind, const double* X, int64_t n, int
  *   cuStreamWaitValue32 on that flag) move the blocks over NVLink while the kernel computes on.  Chunks: one per local panel,
  *   the last `split` panels one per 128-row tile.  recompute_frac256 / 256 of each (row panel, destination rank) block list --
  *   its LOWEST slots, so that the mirrored remainder stays one contiguous row range -- is recomputed by the destination rank
- *   instead (the recomputed tiles run last and cover the tail of the copies).  On return the caller's stream waits for this
+ *   instead (the recomputed tiles run last and cover the tail of the copies); the next direct_frac256 / 256 of the slots are
+ *   stored into the peer's HBM by the kernel itself, as in the hybrid function, so that the two transports -- SM stores and copy
+ *   engines, each of which saturates well below NVLink's rate in an 8-GPU all-to-all -- work side by side.  On return the caller's stream waits for this
  *   rank's outgoing copies; completion across ranks is the caller's flag handshake, as for the functions above.
- *   stage: gabo_points_gram_cyclic_stage_bytes(n, world, rank, recompute_frac256, split) bytes of local device memory;
+ *   stage: gabo_points_gram_cyclic_stage_bytes(n, world, rank, recompute_frac256, direct_frac256, split) bytes of local device memory;
  *   progress: >= 2 * (local panels + 3 * split) 32-bit words of local device memory, owned by this call sequence;
  *   epoch: strictly increasing over successive calls on the same `progress` (> 0).  Bit-identical to the other two. */
-size_t gabo_points_gram_cyclic_stage_bytes(int64_t n, int world, int rank, int recompute_frac256, int split);
+size_t gabo_points_gram_cyclic_stage_bytes(int64_t n, int world, int rank, int recompute_frac256, int direct_frac256, int split);
 int gabo_points_gram_cyclic_staged_f64(int kind, const double* X, int64_t n, int64_t ldx, int dim, double beta, double variance,
                                        double* const* K_bases_host, int64_t ldk, int world, int rank, int recompute_frac256,
-                                       int split, double* stage, size_t stage_bytes, uint32_t* progress, int64_t progress_words,
-                                       uint32_t epoch, void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+                                       int direct_frac256, int split, double* stage, size_t stage_bytes, uint32_t* progress,
+                                       int64_t progress_words, uint32_t epoch, void* workspace, size_t workspace_bytes,
+                                       gabo_stream_t stream);
 int gabo_trsm_right_f64(int64_t m, int64_t nb, const double* L, int64_t ldl, double* A, int64_t lda,
                         void* workspace, size_t workspace_bytes, gabo_stream_t stream);
 /* gabo_potrf_diag_f64: factor one diagonal block (nb <= 512) in place AND return the inverses of its 128 x 128 diagonal
@@ -394,6 +397,18 @@ int gabo_potrf_cyclic_p2p_f64(int64_t n, int nb, int world, int rank, double* A_
                               double* const* P_host, double* const* bc_host, uint32_t* const* flag_host, uint32_t base,
                               int32_t* info_dev, double* winv_store, void* ws_diag, size_t ws_diag_bytes, void* ws_trsm,
                               size_t ws_trsm_bytes, gabo_stream_t main_stream, gabo_stream_t side_stream, void* ev_u1, void* ev_side);
+/* gabo_potrf_cyclic_chain_f64: the same factorisation (same arithmetic per entry, same buffers and flags) sequenced along its
+ *   critical chain  D(k) -> push to the owner of k+1 -> that owner solves its own nb rows of block column k -> updates its
+ *   diagonal block -> D(k+1):  the next owner does exactly that on the high-priority stream (and receives the diagonal block and
+ *   its flag before the other ranks); the rest of every rank's row solve runs on a second internal high-priority stream, the
+ *   update of the next block column is released by ONE nb x nb block (flag word [9]) instead of every rank's rows, and only the
+ *   big trailing update waits for all rows.  The owners may run up to `world` panels ahead of a rank that owns none of them, so
+ *   P_host / bc_host hold nbuf >= world + 1 (>= 3) rotating buffers per rank (buffer b of rank r at [nbuf r + b]).
+ *   ws_diag: max(gabo_potrf_workspace_bytes(nb), gabo_trsm_right_workspace_bytes(nb, nb)) bytes. */
+int gabo_potrf_cyclic_chain_f64(int64_t n, int nb, int world, int rank, double* A_loc, int64_t lda, double sigma2, int nbuf,
+                                double* const* P_host, double* const* bc_host, uint32_t* const* flag_host, uint32_t base,
+                                int32_t* info_dev, double* winv_store, void* ws_diag, size_t ws_diag_bytes, void* ws_trsm,
+                                size_t ws_trsm_bytes, gabo_stream_t main_stream, gabo_stream_t side_stream);
 /* gabo_solve_cyclic_p2p_f64: the forward substitution L x = b of the block-cyclically distributed factor (panel p of nb rows on
  *   rank p % world, local slot p / world; A_loc [local_rows, >= n], B_loc [local_rows, nrhs] contiguous, in place) as ONE host
  *   call per rank, no collective: at step kp the owner solves its block (inverses of the 128-blocks of the diagonal block in

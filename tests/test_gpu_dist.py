@@ -92,12 +92,13 @@ def test_cyclic_mirrored_gram_single_process(cuda, world, mod):
         assert torch.equal(bufs[r], full[rows])
 
 
-@pytest.mark.parametrize('split', [0, 1, 2])
+@pytest.mark.parametrize('split,direct', [(0, 0), (1, 0), (2, 64), (1, 128), (1, 256)])
 @pytest.mark.parametrize('frac', [0, 48, 128, 256])
 @pytest.mark.parametrize('world', [1, 2, 3, 8])
-def test_cyclic_staged_gram_single_process(cuda, world, frac, split):
+def test_cyclic_staged_gram_single_process(cuda, world, frac, split, direct):
     """gabo_points_gram_cyclic_staged_f64 with all `world` ranks emulated on one GPU: mirror blocks bound for other ranks go
-    through the local staging buffer and copy-engine 2-D copies released by the kernel's per-chunk flags.  Every entry is written
+    through the local staging buffer and copy-engine 2-D copies released by the kernel's per-chunk flags (`direct`/256 of the
+    slots: remote stores from the kernel instead).  Every entry is written
     (NaN pre-fill) with the bits of the single-GPU mirrored Gram; run twice to exercise the epoch / counter reset."""
     from gaboflow_b200 import ops
     from gaboflow_b200.dist import BlockCyclic
@@ -107,7 +108,7 @@ def test_cyclic_staged_gram_single_process(cuda, world, frac, split):
     lays = [BlockCyclic(n, 512, world, r) for r in range(world)]
     bufs = [torch.full((max(l.local_rows, 1), n), float('nan'), dtype=torch.float64, device='cuda') for l in lays]
     ptrs = [b.data_ptr() for b in bufs]
-    states = [ops.StagedGramState(n, world, r, frac, split, 'cuda') for r in range(world)]
+    states = [ops.StagedGramState(n, world, r, frac, split, 'cuda', direct_frac256=direct) for r in range(world)]
     full = ops.points_gram(ops.SPHERE_GAUSSIAN, X, None, beta=2.0, uplo='mirror')
     for rep in range(2):
         for b in bufs:

@@ -29,10 +29,11 @@ for p in lay.my_panels():
 ws = torch.empty(int(ops._lib.lib().gabo_points_gram_cyclic_workspace_bytes(N, 51)), dtype=torch.uint8, device=dev)
 MODE = os.environ.get('GABO_GRAM_MODE', 'direct')      # direct: remote stores from the kernel; staged: local staging + copy engines
 SPLIT = int(os.environ.get('GABO_GRAM_SPLIT', '1'))
+DIRECT = int(os.environ.get('GABO_GRAM_DIRECT256', '0'))     # staged mode: share of the slots stored remotely by the kernel
 xch = PanelExchange(lay, N, dev) if os.environ.get('GABO_GRAM_XCH', '1') == '1' and world > 1 else None
 ok = True
 for mod in [int(v) for v in os.environ.get("GABO_SWEEP", "0,64,96,128,160,256").split(",")]:   # fraction (of 256) of the cross-rank upper panel pairs recomputed by the row owner
-    staged = make_staged_gram_state(N, lay, dev, recompute_frac256=mod, split=SPLIT) if MODE == 'staged' else None
+    staged = make_staged_gram_state(N, lay, dev, recompute_frac256=mod, split=SPLIT, direct_frac256=DIRECT) if MODE == 'staged' else None
     K.fill_(float('nan'))
     dist.barrier(); torch.cuda.synchronize()
     gram_block_cyclic_mirrored(ops.SPHERE_GAUSSIAN, Xd, lay, peers, 2.0, 1.0, workspace=ws, recompute_frac256=mod, xch=xch, staged=staged)
@@ -53,7 +54,7 @@ for mod in [int(v) for v in os.environ.get("GABO_SWEEP", "0,64,96,128,160,256").
     good = nan == 0 and err == 0.0
     ok = ok and good
     del staged
-    print(f'[rank {rank}/{world}] N={N} mode={MODE} split={SPLIT} recompute_frac256={mod}: max|K-ref|={err:.1e} nan={nan}  {ms:.2f} ms  {"OK" if good else "FAIL"}', flush=True)
+    print(f'[rank {rank}/{world}] N={N} mode={MODE} split={SPLIT} direct256={DIRECT} recompute_frac256={mod}: max|K-ref|={err:.1e} nan={nan}  {ms:.2f} ms  {"OK" if good else "FAIL"}', flush=True)
 dist.barrier()
 del K, ref
 if xch is not None:
