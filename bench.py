@@ -243,7 +243,9 @@ def run_ours(args):
     p2p_mirror = (world >= 2 and N % PANEL == 0 and not args.no_p2p)
     # GABO_GRAM_MODE=staged (default): the mirror blocks for other ranks are staged in local HBM and moved by copy engine while
     # the kernel computes on (no SM stalls on remote stores); =direct: the kernel stores them into the peers' HBM itself.
-    gram_mode = os.environ.get('GABO_GRAM_MODE', 'staged')
+    # Measured (profiles/r02_gram_staged_{2,8}gpu*.txt): at 2 GPUs staging wins (7.75 vs 8.49 ms); in the 8-GPU all-to-all both
+    # transports saturate near 300 GB/s per GPU, the balance point is the same (~2.8 ms), and direct stores need no staging memory.
+    gram_mode = os.environ.get('GABO_GRAM_MODE', 'staged' if world == 2 else 'direct')
     from gaboflow_b200.dist import default_staged_frac256, make_staged_gram_state
     gram_frac = int(os.environ.get('GABO_GRAM_RECOMPUTE_FRAC256',
                                    str(default_staged_frac256(world) if gram_mode == 'staged' else default_recompute_frac256(world))))

@@ -869,10 +869,22 @@ int trsv_persistent(bool trans, int64_t n, const double* L, int64_t ldl, const d
 }
 
 // inverses of the 128 x 128 diagonal blocks, then 256 B for the progress counter of the one-right-hand-side kernel
+// Many right-hand sides, forward substitution: the solve runs on the TRANSPOSED right-hand sides Bt [nrhs][n] (see
+// trsm_forward_blocked), which needs room for Bt and for the staging buffer of the 512-block solves.
+constexpr int64_t TRSM_BLOCKED_MIN_NRHS = 32, TRSM_BLOCKED_MIN_N = 1024;
+static inline bool trsm_blocked_applies(int trans, int64_t n, int64_t nrhs) {
+    return !trans && nrhs >= TRSM_BLOCKED_MIN_NRHS && n >= TRSM_BLOCKED_MIN_N;
+}
+extern "C" size_t gabo_trsm_right_workspace_bytes(int64_t m, int64_t nb);
+static inline size_t trsm_blocked_extra_bytes(int64_t n, int64_t nrhs) {
+    const int64_t ldt = (n + 1) & ~(int64_t)1;
+    return align256((size_t)nrhs * ldt * sizeof(double)) + align256(gabo_trsm_right_workspace_bytes(nrhs, NB_OUT));
+}
 extern "C" size_t gabo_trsm_workspace_bytes(int64_t n, int64_t nrhs) {
-    (void)nrhs;
     if (n <= 0) return 512;
-    return align256((size_t)ceil_div64(n, NB_IN) * NB_IN * NB_IN * sizeof(double)) + 256;
+    size_t need = align256((size_t)ceil_div64(n, NB_IN) * NB_IN * NB_IN * sizeof(double)) + 256;
+    if (trsm_blocked_applies(0, n, nrhs)) need += trsm_blocked_extra_bytes(n, nrhs);
+    return need;
 }
 extern "C" size_t gabo_trsm_winv_workspace_bytes(void) { return 256; }
 
@@ -901,6 +913,80 @@ extern "C" int gabo_trsm_winv_f64(int trans, int64_t n, int64_t nrhs, const doub
     if (scratch != nullptr && scratch_bytes < 256) return -10;
     const int rc = trsm_impl(trans, n, nrhs, L, ldl, Winv_all, B, ldb, scratch, scratch_bytes, stream_);
     return (rc <= -6 && rc > GABO_ERR_CUDA) ? rc - 1 : rc;
+}
+
+// [rows][cols] -> [cols][rows], 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ src, int64_t lds, int64_t rows, int64_t cols,
+                                                        double* __restrict__ dst, int64_t ldd) {
+    __shared__ double tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8)
+        if (r0 + i < rows && c0 + tx < cols) tile[i][tx] = src[(r0 + i) * lds + c0 + tx];
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < cols && r0 + tx < rows) dst[(c0 + i) * ldd + r0 + tx] = tile[tx][i];
+}
+
+struct PanelScatter;
+static int trsm_right_impl(int64_t m, int64_t nb, const double* L, int64_t ldl, const double* Winv_all, double* A,
+                           int64_t lda, void* workspace, size_t workspace_bytes, gabo_stream_t stream_,
+                           const PanelScatter* scatter);
+
+// L X = B with many right-hand sides (forward substitution), B [n][nrhs] in place.  The single-level chain of 128-row steps
+// spends its flops in k = 128 products whose C tile is read and written once per 128 of k (22 TFLOP/s at N = 32768, nrhs =
+// 1024).  Here the right-hand sides are transposed once, Bt [nrhs][n], so that the solve is Xt = Bt L^-T and EVERY product
+// is the k-major x k-major case of the TMA-fed DMMA kernel; two-level and right-looking like the factorisation: per 512-column
+// block, a small solve against the diagonal block (block inverses + left-looking products, trsm_right_impl) and ONE k = 512
+// update of all remaining columns; the next block's small solve runs on the auxiliary stream under that update.
+static int trsm_forward_blocked(int64_t n, int64_t nrhs, const double* L, int64_t ldl, const double* Wall, double* B, int64_t ldb,
+                                void* ws, cudaStream_t stream) {
+    const int64_t ldt = (n + 1) & ~(int64_t)1;
+    double* Bt = static_cast<double*>(ws);
+    void* ws_in = static_cast<unsigned char*>(ws) + align256((size_t)nrhs * ldt * sizeof(double));
+    const size_t ws_in_bytes = gabo_trsm_right_workspace_bytes(nrhs, NB_OUT);
+    int rc;
+    {
+        dim3 g((unsigned)ceil_div64(nrhs, 32), (unsigned)ceil_div64(n, 32));
+        transpose_kernel<<<g, 256, 0, stream>>>(B, ldb, n, nrhs, Bt, ldt);
+        GABO_LAUNCH_CHECK();
+    }
+    AuxCtx ctx;
+    if ((rc = aux_acquire(&ctx))) return rc;
+    auto inner = [&](int64_t k0, cudaStream_t s) -> int {
+        const int64_t kb = (n - k0 < NB_OUT) ? (n - k0) : NB_OUT;
+        return trsm_right_impl(nrhs, kb, L + k0 * ldl + k0, ldl, Wall + (k0 / NB_IN) * NB_IN * NB_IN, Bt + k0, ldt, ws_in, ws_in_bytes,
+                               s, nullptr);
+    };
+    rc = inner(0, stream);
+    for (int64_t k0 = 0; rc == 0 && k0 + NB_OUT < n; k0 += NB_OUT) {
+        const int64_t k1 = k0 + NB_OUT, k2 = (k1 + NB_OUT < n) ? (k1 + NB_OUT) : n;
+        // next block column first, then its small solve on the auxiliary stream under the big update
+        rc = launch_gemm(true, true, nrhs, k2 - k1, NB_OUT, -1.0, Bt + k0, ldt, L + k1 * ldl + k0, ldl, false, Bt + k1, ldt, false, stream);
+        if (rc) break;
+        cudaError_t e = cudaEventRecord(ctx.e_main, stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx.aux, ctx.e_main, 0);
+        if (e != cudaSuccess) { rc = GABO_ERR_CUDA - (int)e; break; }
+        if ((rc = inner(k1, ctx.aux))) break;
+        e = cudaEventRecord(ctx.e_aux, ctx.aux);
+        if (e != cudaSuccess) { rc = GABO_ERR_CUDA - (int)e; break; }
+        if (k2 < n) {
+            rc = launch_gemm(true, true, nrhs, n - k2, NB_OUT, -1.0, Bt + k0, ldt, L + k2 * ldl + k0, ldl, false, Bt + k2, ldt, false, stream);
+            if (rc) break;
+        }
+        e = cudaStreamWaitEvent(stream, ctx.e_aux, 0);
+        if (e != cudaSuccess) { rc = GABO_ERR_CUDA - (int)e; break; }
+    }
+    if (rc != 0) {   // never leave the auxiliary stream running behind the caller's back
+        cudaEventRecord(ctx.e_aux, ctx.aux);
+        cudaStreamWaitEvent(stream, ctx.e_aux, 0);
+    }
+    aux_release(ctx);
+    if (rc) return rc;
+    dim3 g((unsigned)ceil_div64(n, 32), (unsigned)ceil_div64(nrhs, 32));
+    transpose_kernel<<<g, 256, 0, stream>>>(Bt, ldt, nrhs, n, B, ldb);
+    GABO_LAUNCH_CHECK();
+    return 0;
 }
 
 static int trsm_impl(int trans, int64_t n, int64_t nrhs, const double* L, int64_t ldl, const double* Winv_pre, double* B,
@@ -935,6 +1021,14 @@ static int trsm_impl(int trans, int64_t n, int64_t nrhs, const double* L, int64_
         if (Winv_pre == nullptr) scratch = static_cast<unsigned char*>(workspace) + align256((size_t)nblk * NB_IN * NB_IN * sizeof(double));
         else if (workspace != nullptr && workspace_bytes >= 256) scratch = workspace;
         if (nrhs == 1 && scratch != nullptr && !chain) return gabo::trsv_persistent(trans != 0, n, L, ldl, Wall, B, ldb, scratch, stream);
+    }
+    // many right-hand sides, forward: two-level right-looking solve on the transposed right-hand sides (when the caller's
+    // workspace has room for them: gabo_trsm_workspace_bytes says how much)
+    if (trsm_blocked_applies(trans, n, nrhs) && workspace != nullptr) {
+        static const bool single_level = (getenv("GABO_TRSM_SINGLE_LEVEL") != nullptr);   // A/B switch: the 128-row chain
+        const size_t base_bytes = (Winv_pre == nullptr) ? align256((size_t)nblk * NB_IN * NB_IN * sizeof(double)) + 256 : 0;
+        if (!single_level && workspace_bytes >= base_bytes + trsm_blocked_extra_bytes(n, nrhs))
+            return trsm_forward_blocked(n, nrhs, L, ldl, Wall, B, ldb, static_cast<unsigned char*>(workspace) + base_bytes, stream);
     }
     const unsigned rhs_chunks = (unsigned)ceil_div64(nrhs, CH);
     for (int64_t b = 0; b < nblk; ++b) {

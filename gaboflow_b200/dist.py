@@ -496,8 +496,11 @@ def default_recompute_frac256(world: int) -> int:
 def default_staged_frac256(world: int) -> int:
     """Recomputed share (of 256) for the STAGED Gram (copy-engine mirror blocks): the SMs no longer stall on remote stores, so
     the balance point is FP64 pipe vs NVLink bandwidth alone -- lower-tile time (1 + 0.88 f) against (1 - f) x cross-rank bytes
-    per rank / ~750 GB/s.  Measured on B200 / NVSwitch at N = 65536, D = 51 (tools/dist_gram_check.py, GABO_GRAM_MODE=staged)."""
-    return {1: 0, 2: 0, 3: 16, 4: 32}.get(int(world), 48)
+    per rank / the copy rate.  Measured on B200 / NVSwitch at N = 65536, D = 51 (tools/dist_gram_check.py, GABO_GRAM_MODE=staged;
+    profiles/r02_gram_staged_*): 2 GPUs: share 0 -> 7.75 ms (direct stores: 8.49), the copy engines sustain >= 555 GB/s; 8 GPUs:
+    the copy engines sustain only ~300-350 GB/s per GPU in the all-to-all pattern (32: 5.3 ms, 64: 4.65, 112: 3.72; with 64/256 of
+    the slots as direct stores on top: 128: 2.78 ms = the direct-store optimum 2.79), so staging is the default at 2 GPUs only."""
+    return {1: 0, 2: 0, 3: 64, 4: 96}.get(int(world), 128)
 
 
 def make_staged_gram_state(n: int, layout: BlockCyclic, device, recompute_frac256: Optional[int] = None, split: int = 1,

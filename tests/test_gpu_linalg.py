@@ -58,6 +58,29 @@ def test_trsm_vs_scipy(cuda, n, nrhs, trans):
     assert np.max(np.abs(Bd.cpu().numpy() - ref)) / np.max(np.abs(ref)) < 1e-12
 
 
+@pytest.mark.parametrize('n,nrhs', [(1024, 32), (1025, 33), (1536, 64), (2049, 130), (3000, 257), (4096, 1024)])
+def test_trsm_many_rhs_blocked_path(cuda, n, nrhs):
+    """Forward solve with many right-hand sides: the two-level right-looking solve on the transposed right-hand sides
+    (trsm_forward_blocked: n >= 1024, nrhs >= 32), odd sizes and leading dimensions included, against SciPy and against the
+    single-level path on a strided view."""
+    from gaboflow_b200 import ops
+    L = np.linalg.cholesky(spd_matrix(n, 3 * n))
+    B = np.random.default_rng(n + nrhs).standard_normal((n, nrhs))
+    ref = sla.solve_triangular(L, B, lower=True)
+    Ld = torch.from_numpy(L).cuda()
+    Bd = torch.from_numpy(B).cuda()
+    ops.trsm_(Ld, Bd)
+    assert np.max(np.abs(Bd.cpu().numpy() - ref)) / np.max(np.abs(ref)) < 1e-12
+    # L and B as views into larger buffers (leading dimensions n + 3 and nrhs + 5)
+    Lbig = torch.zeros((n, n + 3), dtype=torch.float64, device='cuda')
+    Lbig[:, :n] = Ld
+    Bbig = torch.zeros((n, nrhs + 5), dtype=torch.float64, device='cuda')
+    Bbig[:, :nrhs] = torch.from_numpy(B).cuda()
+    ops.trsm_(Lbig[:, :n], Bbig[:, :nrhs])
+    assert np.max(np.abs(Bbig[:, :nrhs].cpu().numpy() - ref)) / np.max(np.abs(ref)) < 1e-12
+    assert float(Bbig[:, nrhs:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize('m,n,k,lower', [(128, 128, 16, False), (300, 200, 77, False), (513, 513, 128, True), (260, 130, 512, True)])
 def test_gemm_nt_sub(cuda, m, n, k, lower):
     from gaboflow_b200 import ops

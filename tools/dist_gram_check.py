@@ -32,7 +32,11 @@ SPLIT = int(os.environ.get('GABO_GRAM_SPLIT', '1'))
 DIRECT = int(os.environ.get('GABO_GRAM_DIRECT256', '0'))     # staged mode: share of the slots stored remotely by the kernel
 xch = PanelExchange(lay, N, dev) if os.environ.get('GABO_GRAM_XCH', '1') == '1' and world > 1 else None
 ok = True
-for mod in [int(v) for v in os.environ.get("GABO_SWEEP", "0,64,96,128,160,256").split(",")]:   # fraction (of 256) of the cross-rank upper panel pairs recomputed by the row owner
+for item in os.environ.get("GABO_SWEEP", "0,64,96,128,160,256").split(","):   # "f" or "f:d" (staged mode: d/256 of the slots by remote stores)
+    mod = int(item.split(':')[0])
+    if ':' in item:
+        DIRECT = int(item.split(':')[1])
+    # mod =   # fraction (of 256) of the cross-rank upper panel pairs recomputed by the row owner
     staged = make_staged_gram_state(N, lay, dev, recompute_frac256=mod, split=SPLIT, direct_frac256=DIRECT) if MODE == 'staged' else None
     K.fill_(float('nan'))
     dist.barrier(); torch.cuda.synchronize()
