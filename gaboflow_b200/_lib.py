@@ -21,6 +21,8 @@ SIGNATURES = {
     'gabo_points_gram_workspace_bytes': (sz, [i64, i64, i32]),
     'gabo_points_gram_f64': (i32, [i32, vp, i64, i64, vp, i64, i64, i32, f64, f64, vp, i64, i64, i64, i32, vp, sz, vp]),
     'gabo_points_gram_f32': (i32, [i32, vp, i64, i64, vp, i64, i64, i32, f32, f32, vp, i64, i64, i64, i32, vp, sz, vp]),
+    'gabo_points_gram_i8_workspace_bytes': (sz, [i64, i64]),
+    'gabo_points_gram_i8_f64': (i32, [i32, vp, i64, i64, vp, i64, i64, i32, f64, f64, vp, i64, i64, i64, i32, i32, i32, vp, sz, vp]),
     'gabo_kdiag_const_f64': (i32, [i64, f64, vp, vp]),
     'gabo_spd_prep_f64': (i32, [vp, i64, i64, i32, vp, vp, vp, vp, vp, i64, vp, vp]),
     'gabo_spd_gram_f64': (i32, [i32, i32, vp, vp, vp, i64, vp, vp, i64, vp, i64, i32, f64, f64, vp, i64, i64, i64, i32, vp]),

@@ -54,9 +54,29 @@ def device_info():
 
 
 # --------------------------------------------------------------------------------------------------
+I8_MIN_ENTRIES = 1 << 22     # below this the Gram is launch-bound and the extra slicing pass of the int8 engine does not pay
+
+
+def gram_engine(kind: int, dtype, dim: int, n1: int, n2: int, engine: Optional[str] = None) -> str:
+    """Which kernel forms an FP64 Gram: 'i8' = inner products on the integer tensor cores (csrc/points_gram_i8.cu: sphere kinds,
+    dim <= 64), 'dmma' = FP64 tensor instruction (csrc/points_gram.cu: every kind and size).  ``engine`` or the environment
+    variable GABO_GRAM_ENGINE force one; the default is 'i8' wherever it applies and the problem is large enough."""
+    import os
+    choice = engine or os.environ.get('GABO_GRAM_ENGINE', 'auto')
+    ok = dtype == torch.float64 and kind in (SPHERE_GAUSSIAN, SPHERE_LAPLACE) and 1 <= dim <= 64
+    if choice == 'i8':
+        if not ok:
+            raise ValueError('the int8 Gram engine covers the FP64 sphere kernels with dim <= 64')
+        return 'i8'
+    if choice == 'dmma' or not ok:
+        return 'dmma'
+    return 'i8' if n1 * n2 >= I8_MIN_ENTRIES else 'dmma'
+
+
 def points_gram(kind: int, X: torch.Tensor, X2: Optional[torch.Tensor] = None, beta: float = 1.0,
                 variance: float = 1.0, out: Optional[torch.Tensor] = None, row0: int = 0,
-                row1: Optional[int] = None, uplo='full', workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+                row1: Optional[int] = None, uplo='full', workspace: Optional[torch.Tensor] = None,
+                engine: Optional[str] = None) -> torch.Tensor:
     """K[row0:row1, :] of the sphere Gaussian / Laplace or squared-distance Gaussian Gram (FP64 or FP32 by X.dtype)."""
     L = _lib.lib()
     dtype = X.dtype
@@ -80,6 +100,16 @@ def points_gram(kind: int, X: torch.Tensor, X2: Optional[torch.Tensor] = None, b
         _req(out, 'out', dtype)
         if out.dim() != 2 or out.shape[0] < rows or out.shape[1] != n2 or (n2 > 1 and out.stride(1) != 1):
             raise ValueError('out must be a row-major [row1-row0, n2] tensor')
+    if gram_engine(kind, dtype, dim, rows, n2, engine) == 'i8':
+        nbytes = int(L.gabo_points_gram_i8_workspace_bytes(n1, n2))
+        if workspace is None or workspace.numel() < nbytes or workspace.data_ptr() % 128:
+            workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=X.device)
+        st = L.gabo_points_gram_i8_f64(int(kind), X.data_ptr(), n1, _ld(X), X2.data_ptr() if X2 is not None else None, n2,
+                                       _ld(X2) if X2 is not None else 0, dim, float(beta), float(variance), out.data_ptr(),
+                                       _ld(out) if rows > 1 else max(n2, int(out.stride(0))), int(row0), int(row1), _UPLO[uplo], 0, 0,
+                                       workspace.data_ptr(), workspace.numel(), _stream())
+        _lib.check('gabo_points_gram_i8_f64', st)
+        return out
     nbytes = int(L.gabo_points_gram_workspace_bytes(n1, n2, dim))
     if workspace is None or workspace.numel() < nbytes:
         workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=X.device)
@@ -597,6 +627,24 @@ def points_gram_cyclic(kind: int, X: torch.Tensor, bases, ldk: int, world: int, 
                                               C.cast(arr, C.c_void_p), int(ldk), int(world), int(rank), int(recompute_frac256),
                                               workspace.data_ptr(), workspace.numel(), _stream())
     _lib.check('gabo_points_gram_cyclic_hybrid_f64', st)
+
+
+def points_gram_cyclic_rows_i8(kind: int, X: torch.Tensor, K_local: torch.Tensor, world: int, rank: int, beta: float = 1.0,
+                               variance: float = 1.0, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Multi-GPU Gram with no exchange at all: this rank computes the FULL rows of its 512-row panels (block-cyclic) into its
+    local buffer with the int8-tensor-core engine (gabo_points_gram_i8_f64, cyc_world > 0)."""
+    L = _lib.lib()
+    X = _rowmajor2d(_req(X, 'X'))
+    _req(K_local, 'K_local')
+    n, dim = int(X.shape[0]), int(X.shape[1])
+    nbytes = int(L.gabo_points_gram_i8_workspace_bytes(n, n))
+    if workspace is None or workspace.numel() < nbytes or workspace.data_ptr() % 128:
+        workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=X.device)
+    st = L.gabo_points_gram_i8_f64(int(kind), X.data_ptr(), n, _ld(X), None, n, 0, dim, float(beta), float(variance),
+                                   K_local.data_ptr(), int(K_local.stride(0)), 0, n, FULL, int(world), int(rank),
+                                   workspace.data_ptr(), workspace.numel(), _stream())
+    _lib.check('gabo_points_gram_i8_f64', st)
+    return K_local
 
 
 class StagedGramState:

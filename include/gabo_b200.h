@@ -227,6 +227,22 @@ int gabo_sphere_acq_fused_f64(int kind, int64_t n, int64_t M, int dim, const dou
 int gabo_expected_improvement_f64(int64_t M, const double* mean, const double* var, double fmin, double* out,
                                   gabo_stream_t stream);
 
+/* ---- FP64 sphere Gram with integer-tensor-core inner products (csrc/points_gram_i8.cu) --------------------------------------
+ * Same contract and arguments as gabo_points_gram_f64 for kind = GABO_SPHERE_GAUSSIAN / GABO_SPHERE_LAPLACE and dim <= 64
+ * (sphere_utils_tf.py:11-60 + kernels_sphere_tf.py:59-88, 179-204), FP64 in and out.  The inner products x.y are formed on the
+ * 5th-generation tensor cores in 8-bit integer arithmetic (tcgen05.mma kind::i8, S32 accumulators in TMEM) from an exact
+ * 8 x 7-bit slicing of 56-bit fixed-point coordinates; 36 of the 64 slice products are kept: |error of x.y| < 6e-15 (max |x|)^2
+ * worst case at dim = 52, i.e. < ~1e-14 beta relative on a Gaussian Gram entry (north_star tolerance: 1e-12).  The FP64 pipe,
+ * which DMMA shares with DFMA on B200, is left to the clamp / acos / exp epilogue.  Coordinates must be finite.
+ * cyc_world > 0: block-cyclic row sharding for one NVSwitch node -- this rank computes the FULL rows of its 512-row panels
+ * (panel P on rank P % cyc_world, local slot P / cyc_world) into its local [local_rows, ldk] buffer K; uplo must be GABO_FULL,
+ * n1 a multiple of 512, row0 / row1 are ignored.  No data leaves the GPU.
+ * workspace: gabo_points_gram_i8_workspace_bytes(n1, n2) bytes, 128-byte aligned. */
+size_t gabo_points_gram_i8_workspace_bytes(int64_t n1, int64_t n2);
+int gabo_points_gram_i8_f64(int kind, const double* X, int64_t n1, int64_t ldx, const double* X2, int64_t n2, int64_t ldx2,
+                            int dim, double beta, double variance, double* K, int64_t ldk, int64_t row0, int64_t row1, int uplo,
+                            int cyc_world, int cyc_rank, void* workspace, size_t workspace_bytes, gabo_stream_t stream);
+
 /* ---- small-N batched GP evaluation (csrc/gp_small.cu) -----------------------------------------------------------------
  * The reference's small configurations (examples/kernels/sphere/sphere_kernels.py:125-139, examples/bo_sphere/benchmark_examples/
  * bo_sphere_ackley_manifold.py:137-160, examples/bo_spd/benchmark_examples/bo_spd_ackley_manifold.py:159-187) evaluate GPflow 0.5's
