@@ -50,6 +50,8 @@ constexpr int STAGE_COLS = NSL * SUBN;       // 256 columns per stage
 constexpr int OSEG = 8;                      // column tiles per work item
 constexpr int ONBST = 2;                     // B ring depth
 constexpr int O_THREADS = 576;               // warp 0 producer, warp 1 MMA, warps 2..17 epilogue
+constexpr int BCHUNK = NSL * SUBN * 16;      // B layout: one 16-byte k-chunk of the 8 stacked slices of a sub-tile (4 KB)
+constexpr int BSUB = (OKP / 16) * BCHUNK;    // B layout: one sub-tile (16 KB)
 
 struct OzParams {
     const int8_t* Ap;
@@ -84,16 +86,20 @@ __global__ void oz_exponent_fix_kernel(int* expo, int symmetric) {
     else if (expo[1] == -1000) expo[1] = 0;
 }
 
-// pass 2: X [n, dim] -> tiles [n_pad / 128][8 slices][4 chunks][128 rows][16 B]; one warp per row, a lane per coordinate pair
+// pass 2: X [n, dim] -> two copies of every 128-row tile (64 KB each), one warp per row, a lane per coordinate:
+//   A layout  [slice 0..7][k-chunk 0..3][row 0..127][16 B]              : operand A of MMA (s, kk) = slice s, chunks 2kk, 2kk+1
+//   B layout  [sub-tile 0..3][k-chunk 0..3][slice 0..7][row 0..31][16 B]  : for one 32-column sub-tile, the slices are stacked
+//             along N (row index t * 32 + j), so ONE MMA multiplies A_s with B_0 .. B_(7-s) at once (see the kernel)
 __global__ void oz_pack_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int dim, const int* __restrict__ expo,
-                               int8_t* __restrict__ P, int64_t n_pad) {
+                               int8_t* __restrict__ PA, int8_t* __restrict__ PB, int64_t n_pad) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (row >= n_pad) return;
     const int E = expo[0];
     const int64_t tile = row / OT;
     const int r = (int)(row - tile * OT);
-    int8_t* base = P + tile * (int64_t)OTILE;
+    int8_t* baseA = PA != nullptr ? PA + tile * (int64_t)OTILE : nullptr;
+    int8_t* baseB = PB != nullptr ? PB + tile * (int64_t)OTILE : nullptr;
     for (int k = lane; k < OKP; k += 32) {
         double x = 0.0;
         if (row < n && k < dim) x = X[row * ldx + k];
@@ -107,9 +113,16 @@ __global__ void oz_pack_kernel(const double* __restrict__ X, int64_t n, int64_t 
             v = (v - dd) >> 7;                              // exact: v - dd is a multiple of 128
         }
         d[0] = (int8_t)v;                                   // |v| <= 65
-        const int64_t off = (int64_t)(k >> 4) * OCHUNK + r * 16 + (k & 15);
+        if (baseA != nullptr) {
+            const int64_t off = (int64_t)(k >> 4) * OCHUNK + r * 16 + (k & 15);
 #pragma unroll
-        for (int s = 0; s < NSL; ++s) base[(int64_t)s * OSLICE + off] = d[s];
+            for (int s = 0; s < NSL; ++s) baseA[(int64_t)s * OSLICE + off] = d[s];
+        }
+        if (baseB != nullptr) {
+            const int64_t off = (int64_t)(r >> 5) * BSUB + (int64_t)(k >> 4) * BCHUNK + (r & 31) * 16 + (k & 15);
+#pragma unroll
+            for (int s = 0; s < NSL; ++s) baseB[off + s * (SUBN * 16)] = d[s];
+        }
     }
 }
 
@@ -134,17 +147,17 @@ __device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(zero)
         : "memory");
 }
-// K-major, no swizzle: core matrix = 8 rows x 16 B; SBO (next 8 rows) = 128 B, LBO (next 16 B of K) = 2048 B
-__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t smem_addr) {
+// K-major, no swizzle: core matrix = 8 rows x 16 B; SBO (next 8 rows) = 128 B, LBO (next 16 B of K) = the chunk stride
+__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
-    d |= (uint64_t)(OCHUNK >> 4) << 16;
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
     d |= (uint64_t)(128 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     return d;
 }
 // c_format S32 (2) | a_format S8 (1) | b_format S8 (1) | K-major A and B | N >> 3 | M >> 4
-constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SUBN >> 3) << 17) | ((uint32_t)(OT >> 4) << 24);
+constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OT >> 4) << 24);      // | (N >> 3) << 17 per MMA
 
 __device__ __forceinline__ void oz_ld8(uint32_t taddr, int (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
@@ -265,20 +278,19 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
                         const uint32_t aph = (uint32_t)((scount >> 1) & 1);
                         mbar_wait(&bar_acc_empty[as], aph ^ 1);               // that set of epilogue warps has drained the stage
                         oz_fence_after();
-                        const uint32_t b_sub = b_addr + (uint32_t)(sub * SUBN * 16);     // rows sub*32 .. of every chunk
+                        // 16 MMAs per 128 x 32 sub-tile: A_s (k-step kk) times the STACK B_0 .. B_(7-s) of the sub-tile's columns
+                        // (N = 32 (8 - s)), accumulated into the accumulators g = s .. 7 -- exactly the pairs s + t = g <= 7.
+                        // An MMA costs ~130 cycles whatever N (A streams through at one row per cycle), so the 72 narrow
+                        // products of the first version (one per pair and k-step) were 4.5x slower than these 16 wide ones.
+                        const uint32_t b_sub = b_addr + (uint32_t)(sub * BSUB);
 #pragma unroll 1
-                        for (int g = 0; g < NSL; ++g) {
-                            const uint32_t d_tmem = tmem_base + (uint32_t)(as * STAGE_COLS + g * SUBN);
-                            uint32_t acc = 0;
-                            for (int sa = 0; sa <= ((p.debug & 1) ? 0 : g); ++sa) {
-                                const int sb = g - sa;
+                        for (int sa = 0; sa < ((p.debug & 1) ? 1 : NSL); ++sa) {
+                            const uint32_t idesc = kIdescI8 | ((uint32_t)(((NSL - sa) * SUBN) >> 3) << 17);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(as * STAGE_COLS + sa * SUBN);
 #pragma unroll
-                                for (int kk = 0; kk < OKP / 32; ++kk) {
-                                    oz_mma_i8(d_tmem, oz_smem_desc(a_addr + (uint32_t)(sa * OSLICE + kk * 2 * OCHUNK)),
-                                              oz_smem_desc(b_sub + (uint32_t)(sb * OSLICE + kk * 2 * OCHUNK)), kIdescI8, acc);
-                                    acc = 1;
-                                }
-                            }
+                            for (int kk = 0; kk < OKP / 32; ++kk)
+                                oz_mma_i8(d_tmem, oz_smem_desc(a_addr + (uint32_t)(sa * OSLICE + kk * 2 * OCHUNK), OCHUNK),
+                                          oz_smem_desc(b_sub + (uint32_t)(kk * 2 * BCHUNK), BCHUNK), idesc, (sa | kk) != 0);
                         }
                         oz_commit(&bar_acc_full[as]);
                     }
@@ -430,7 +442,7 @@ bool points_gram_i8_supported(int kind, int dim) {
 
 size_t points_gram_i8_workspace_bytes(int64_t n1, int64_t n2) {
     const int64_t n1p = ceil_div64(n1, OT) * OT, n2p = ceil_div64(n2, OT) * OT;
-    return oz_align256((size_t)n1p * OKP * NSL) + oz_align256((size_t)n2p * OKP * NSL) + 256;
+    return oz_align256((size_t)n1p * OKP * NSL) + oz_align256((size_t)n2p * OKP * NSL) + 256;   // A layout of X + B layout of X2
 }
 
 // cyc_world > 0: block-cyclic row sharding (512-row panels of this rank, K = the rank's local [local_rows, ldk] buffer, FULL only)
@@ -439,13 +451,13 @@ int points_gram_i8(int kind, const double* X, int64_t n1, int64_t ldx, const dou
                    int cyc_rank, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     const int64_t n1p = ceil_div64(n1, OT) * OT, n2p = ceil_div64(n2, OT) * OT;
     const size_t bytesA = oz_align256((size_t)n1p * OKP * NSL), bytesB = oz_align256((size_t)n2p * OKP * NSL);
-    const size_t need = bytesA + (symmetric ? 0 : bytesB) + 256;
+    const size_t need = bytesA + bytesB + 256;
     if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 127) != 0) return -16;
     if (workspace_bytes < need) return -17;
     unsigned char* ws = static_cast<unsigned char*>(workspace);
-    int8_t* Ap = reinterpret_cast<int8_t*>(ws);
-    int8_t* Bp = symmetric ? Ap : reinterpret_cast<int8_t*>(ws + bytesA);
-    int* expo = reinterpret_cast<int*>(ws + bytesA + (symmetric ? 0 : bytesB));
+    int8_t* Ap = reinterpret_cast<int8_t*>(ws);                  // X in the A layout
+    int8_t* Bp = reinterpret_cast<int8_t*>(ws + bytesA);         // X2 (or X again) in the B layout
+    int* expo = reinterpret_cast<int*>(ws + bytesA + bytesB);
     const int warps = 8;
     oz_exponent_init_kernel<<<1, 1, 0, stream>>>(expo);
     GABO_LAUNCH_CHECK();
@@ -457,10 +469,10 @@ int points_gram_i8(int kind, const double* X, int64_t n1, int64_t ldx, const dou
     }
     oz_exponent_fix_kernel<<<1, 1, 0, stream>>>(expo, symmetric ? 1 : 0);
     GABO_LAUNCH_CHECK();
-    oz_pack_kernel<<<(unsigned)ceil_div64(n1p, warps), warps * 32, 0, stream>>>(X, n1, ldx, dim, expo, Ap, n1p);
+    oz_pack_kernel<<<(unsigned)ceil_div64(n1p, warps), warps * 32, 0, stream>>>(X, n1, ldx, dim, expo, Ap, symmetric ? Bp : nullptr, n1p);
     GABO_LAUNCH_CHECK();
     if (!symmetric) {
-        oz_pack_kernel<<<(unsigned)ceil_div64(n2p, warps), warps * 32, 0, stream>>>(X2, n2, ldx2, dim, expo + 1, Bp, n2p);
+        oz_pack_kernel<<<(unsigned)ceil_div64(n2p, warps), warps * 32, 0, stream>>>(X2, n2, ldx2, dim, expo + 1, nullptr, Bp, n2p);
         GABO_LAUNCH_CHECK();
     }
     OzParams p;
