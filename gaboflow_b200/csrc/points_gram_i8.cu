@@ -159,10 +159,30 @@ __device__ __forceinline__ uint64_t oz_smem_desc(uint32_t smem_addr, uint32_t lb
 // c_format S32 (2) | a_format S8 (1) | b_format S8 (1) | K-major A and B | N >> 3 | M >> 4
 constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OT >> 4) << 24);      // | (N >> 3) << 17 per MMA
 
-__device__ __forceinline__ void oz_ld8(uint32_t taddr, int (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+// 16 TMEM lanes x 8 columns: thread t gets rows t/4 and t/4 + 8 (of the 16), columns 2 (t%4) and 2 (t%4) + 1 -- the layout of an
+// MMA accumulator fragment, in which BOTH the direct tile (4 lanes x 2 doubles = 64 B of a row) and its mirror image (8 lanes =
+// 8 consecutive rows = 64 B of a mirrored row) store in whole 64-byte segments without any transposition.
+__device__ __forceinline__ void oz_ld16x8(uint32_t taddr, int (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                  : "r"(taddr));
+}
+// producer / MMA-issuer threads wait with a back-off: their try_wait loops otherwise take issue slots from the epilogue warps
+__device__ __forceinline__ void oz_mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
 }
 __device__ __forceinline__ void oz_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
@@ -181,22 +201,6 @@ __device__ __forceinline__ void oz_advance(const OzParams& p, OzWalk& w, int64_t
         adv -= left;
         ++w.bi;
         w.seg = 0;
-    }
-}
-
-// 8 x 8 transpose inside each quarter-warp: before, lane l holds row (l & 7) of its quarter, v[c] = column c; after, lane l
-// holds column (l & 7), v[c] = row c of its quarter.
-__device__ __forceinline__ void transpose8(double (&v)[8], int lane) {
-#pragma unroll
-    for (int s = 4; s >= 1; s >>= 1) {
-        const bool up = (lane & s) != 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (i & s) continue;
-            const double send = up ? v[i] : v[i + s];
-            const double recv = __shfl_xor_sync(0xffffffffu, send, s);
-            if (up) v[i] = recv; else v[i + s] = recv;
-        }
     }
 }
 
@@ -239,14 +243,14 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
                 const int64_t T = oz_row_tiles(p, w.bi);
                 const int64_t bj0 = w.seg * OSEG;
                 const int cnt = (int)((T - bj0) < OSEG ? (T - bj0) : OSEG);
-                mbar_wait(&bar_a_empty, a_phase ^ 1);
+                oz_mbar_wait_idle(&bar_a_empty, a_phase ^ 1);
                 mbar_arrive_expect_tx(&bar_a_full, OTILE);
                 tma_bulk_g2s(sA, p.Ap + oz_global_tile(p, w.bi) * (int64_t)OTILE, OTILE, &bar_a_full);
                 a_phase ^= 1;
                 for (int j = 0; j < cnt; ++j, ++bcount) {
                     const int s = (int)(bcount % ONBST);
                     const uint32_t ph = (uint32_t)((bcount / ONBST) & 1);
-                    mbar_wait(&bar_b_empty[s], ph ^ 1);
+                    oz_mbar_wait_idle(&bar_b_empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&bar_b_full[s], OTILE);
                     tma_bulk_g2s(sB + (size_t)s * OTILE, p.Bp + (bj0 + j) * (int64_t)OTILE, OTILE, &bar_b_full[s]);
                 }
@@ -265,18 +269,18 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
                 const int64_t T = oz_row_tiles(p, w.bi);
                 const int64_t bj0 = w.seg * OSEG;
                 const int cnt = (int)((T - bj0) < OSEG ? (T - bj0) : OSEG);
-                mbar_wait(&bar_a_full, a_phase);
+                oz_mbar_wait_idle(&bar_a_full, a_phase);
                 a_phase ^= 1;
                 for (int j = 0; j < cnt; ++j, ++bcount) {
                     const int s = (int)(bcount % ONBST);
                     const uint32_t ph = (uint32_t)((bcount / ONBST) & 1);
-                    mbar_wait(&bar_b_full[s], ph);
+                    oz_mbar_wait_idle(&bar_b_full[s], ph);
                     const uint32_t b_addr = smem_u32(sB + (size_t)s * OTILE);
 #pragma unroll 1
                     for (int sub = 0; sub < NSUB; ++sub, ++scount) {
                         const int as = (int)(scount & 1);
                         const uint32_t aph = (uint32_t)((scount >> 1) & 1);
-                        mbar_wait(&bar_acc_empty[as], aph ^ 1);               // that set of epilogue warps has drained the stage
+                        oz_mbar_wait_idle(&bar_acc_empty[as], aph ^ 1);               // that set of epilogue warps has drained the stage
                         oz_fence_after();
                         // 16 MMAs per 128 x 32 sub-tile: A_s (k-step kk) times the STACK B_0 .. B_(7-s) of the sub-tile's columns
                         // (N = 32 (8 - s)), accumulated into the accumulators g = s .. 7 -- exactly the pairs s + t = g <= 7.
@@ -310,6 +314,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
         const int exp_slow_hi = exp_slow_threshold_hi(variance);
         const bool mirror_mode = (p.uplo == GABO_SYMM_MIRROR);
         const int64_t ldk = p.ldk;
+        const bool vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15) == 0);   // 16-byte row-pair stores
         // dot = (H 2^28 + Lo) 2^(E_A + E_B - 110 + 49)
         const double c0 = scalbn(1.0, p.expo[0] + p.expo[1] - 61), c1 = scalbn(1.0, p.expo[0] + p.expo[1] - 33);
         const double kMagic = 6755399441055744.0;            // 2^52 + 2^51
@@ -323,7 +328,6 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
             const int cnt = (int)((T - bj0) < OSEG ? (T - bj0) : OSEG);
             const int64_t grow_tile = oz_global_tile(p, w.bi) * OT;
             const int64_t lrow_tile = p.cyc_world > 0 ? w.bi * OT : grow_tile - p.row0;   // row of K (local buffer)
-            const int64_t grow = grow_tile + q * 32 + lane;          // this thread's (global) row
             for (int j = 0; j < cnt; ++j) {
                 const int64_t gcol_tile = (bj0 + j) * OT;
                 const bool diag_tile = p.symmetric && (gcol_tile == grow_tile);
@@ -335,14 +339,22 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
                     oz_fence_after();
                     const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * STAGE_COLS + h * 16);
                     const bool rows_all = grow_tile + OT <= p.row1;
-                    const bool interior = rows_all && (gcol_tile + OT <= p.n2) && !(mirror_mode && diag_tile);
+                    const bool interior = rows_all && (gcol_tile + OT <= p.n2) && !(mirror_mode && diag_tile) && vec_ok;
+                    const int lr = lane >> 2, lc = (lane & 3) * 2;      // fragment coordinates: rows lr + 8 rg, columns lc, lc + 1
 #pragma unroll 1
                     for (int pass = 0; pass < 2; ++pass) {
+                        // v[2 rg + e] = entry (row 32 q + 8 rg + lr, column gcol0 + lc + e)
+                        const uint32_t ta = tbase + pass * 8, tb = ta + (16u << 16);
                         int d0[8], d1[8], d2[8], d3[8];
-                        oz_ld8(tbase + 0 * SUBN + pass * 8, d0);
-                        oz_ld8(tbase + 1 * SUBN + pass * 8, d1);
-                        oz_ld8(tbase + 2 * SUBN + pass * 8, d2);
-                        oz_ld8(tbase + 3 * SUBN + pass * 8, d3);
+#define OZ_LD_GROUP(G, D)                                                          \
+    do {                                                                           \
+        int lo_[4], hi_[4];                                                        \
+        oz_ld16x8(ta + (G) * SUBN, lo_);                                           \
+        oz_ld16x8(tb + (G) * SUBN, hi_);                                           \
+        D[0] = lo_[0]; D[1] = lo_[1]; D[2] = lo_[2]; D[3] = lo_[3];                \
+        D[4] = hi_[0]; D[5] = hi_[1]; D[6] = hi_[2]; D[7] = hi_[3];                \
+    } while (0)
+                        OZ_LD_GROUP(0, d0); OZ_LD_GROUP(1, d1); OZ_LD_GROUP(2, d2); OZ_LD_GROUP(3, d3);
                         oz_ld_wait();
                         double v[8];
 #pragma unroll
@@ -351,10 +363,8 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
                             const long long H = (long long)p01 * 16384 + (long long)p23;            // < 2^44
                             v[i] = __hiloint2double((int)(H >> 32) + 0x43380000, (int)(H & 0xffffffffll)) - kMagic;   // exact
                         }
-                        oz_ld8(tbase + 4 * SUBN + pass * 8, d0);
-                        oz_ld8(tbase + 5 * SUBN + pass * 8, d1);
-                        oz_ld8(tbase + 6 * SUBN + pass * 8, d2);
-                        oz_ld8(tbase + 7 * SUBN + pass * 8, d3);
+                        OZ_LD_GROUP(4, d0); OZ_LD_GROUP(5, d1); OZ_LD_GROUP(6, d2); OZ_LD_GROUP(7, d3);
+#undef OZ_LD_GROUP
                         oz_ld_wait();
                         if (pass == 1) {            // every accumulator of this stage is in registers: hand the stage back
                             oz_fence_before();
@@ -382,33 +392,33 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
                             }
                         }
                         const int64_t gcol0 = gcol_tile + sub * SUBN + h * 16 + pass * 8;
-                        if (diag_tile) {                                       // K(X,X) diagonal is exactly `variance`
+                        const int64_t gc = gcol0 + lc;                             // this thread's first column
+                        const int64_t gr0 = grow_tile + q * 32 + lr;               // ... and first row (then + 8 rg)
+                        if (diag_tile) {                                           // K(X,X) diagonal is exactly `variance`
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                if (gcol0 + i == grow) v[i] = variance;
+                                if (gc + (i & 1) == gr0 + 8 * (i >> 1)) v[i] = variance;
                         }
-                        // mirror image: register i across the warp = 32 consecutive doubles of row (gcol0 + i)
-                        if (mirror && grow < p.row1) {
-                            double* kmir = p.K + gcol0 * ldk + grow;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) st_cs(kmir + i * ldk, v[i]);
-                        }
-                        // direct tile: 8 x 8 transposes, then every quarter-warp stores 64-byte segments of its own rows
-                        transpose8(v, lane);
-                        const int64_t gc = gcol0 + (lane & 7);
-                        const int64_t r_base = q * 32 + (lane >> 3) * 8;          // tile-local row of v[0]
-                        double* kdir = p.K + (lrow_tile + r_base) * ldk + gc;
+                        double* kdir = p.K + (lrow_tile + q * 32 + lr) * ldk + gc;
                         if (interior) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) st_cs(kdir + i * ldk, v[i]);
+                            for (int rg = 0; rg < 4; ++rg) st_cs_v2(kdir + (int64_t)(8 * rg) * ldk, v[2 * rg], v[2 * rg + 1]);
+                            if (mirror) {     // K[col][row]: the 8 lanes of equal lc write 8 consecutive rows = 64 B
+                                double* kmir = p.K + gc * ldk + gr0;
+#pragma unroll
+                                for (int rg = 0; rg < 4; ++rg) {
+                                    st_cs(kmir + 8 * rg, v[2 * rg]);
+                                    st_cs(kmir + ldk + 8 * rg, v[2 * rg + 1]);
+                                }
+                            }
                         } else {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const int64_t gr = grow_tile + r_base + i;
-                                const bool keep = !(mirror_mode && diag_tile) || gc <= gr;   // mirrored diagonal tile: lower part + diagonal
-                                if (gr < p.row1 && gc < p.n2 && keep) st_cs(kdir + i * ldk, v[i]);
-                                // ... and its upper part as the transpose of the lower one
-                                if (mirror_mode && diag_tile && gr < p.row1 && gc < gr) st_cs(p.K + gc * ldk + gr, v[i]);
+                                const int64_t gr = gr0 + 8 * (i >> 1), gcc = gc + (i & 1);
+                                const bool keep = !(mirror_mode && diag_tile) || gcc <= gr;   // mirrored diagonal tile: lower part + diagonal
+                                if (gr < p.row1 && gcc < p.n2 && keep) st_cs(kdir + (int64_t)(8 * (i >> 1)) * ldk + (i & 1), v[i]);
+                                // mirror image (for the diagonal tile: its upper part as the transpose of the lower one)
+                                if (mirror_mode && gr < p.row1 && gcc < gr && (mirror || diag_tile)) st_cs(p.K + gcc * ldk + gr, v[i]);
                             }
                         }
                     }
