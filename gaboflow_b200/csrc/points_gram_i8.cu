@@ -30,6 +30,7 @@
 // accumulators, integer recombination, FP64 epilogue, mirror image K[col][row] stored straight from the registers (lane = row:
 // a register across the warp is 32 consecutive doubles of a mirrored row), direct tile stored after a 16 x 16 shuffle transpose
 // (two 128-byte row segments per store).
+#include <cstdio>
 #include <cstdlib>
 #include "gabo_common.cuh"
 #include "gabo_math.cuh"
@@ -263,7 +264,8 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
             OzWalk w{0, 0};
             oz_advance(p, w, first);
             uint32_t a_phase = 0;
-            int64_t bcount = 0, scount = 0;      // B tiles / sub-tiles issued so far
+            int64_t bcount = 0, scount = 0;
+            long long dbg_cycles = 0, dbg_n = 0;      // B tiles / sub-tiles issued so far
             const uint32_t a_addr = smem_u32(sA);
             for (int64_t it = first; it < p.nitems; it += stride) {
                 const int64_t T = oz_row_tiles(p, w.bi);
@@ -287,6 +289,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
                         // An MMA costs ~130 cycles whatever N (A streams through at one row per cycle), so the 72 narrow
                         // products of the first version (one per pair and k-step) were 4.5x slower than these 16 wide ones.
                         const uint32_t b_sub = b_addr + (uint32_t)(sub * BSUB);
+                        const long long dbg_t0 = clock64();
 #pragma unroll 1
                         for (int sa = 0; sa < ((p.debug & 1) ? 1 : NSL); ++sa) {
                             const uint32_t idesc = kIdescI8 | ((uint32_t)(((NSL - sa) * SUBN) >> 3) << 17);
@@ -297,12 +300,19 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
                                           oz_smem_desc(b_sub + (uint32_t)(kk * 2 * BCHUNK), BCHUNK), idesc, (sa | kk) != 0);
                         }
                         oz_commit(&bar_acc_full[as]);
+                        if (p.debug & 16) {        // diagnostic: issue -> completion time of one sub-tile's MMAs (serialises them)
+                            mbar_wait(&bar_acc_full[as], aph);
+                            dbg_cycles += clock64() - dbg_t0;
+                            ++dbg_n;
+                        }
                     }
                     oz_commit(&bar_b_empty[s]);
                     if (j == cnt - 1) oz_commit(&bar_a_empty);
                 }
                 oz_advance(p, w, stride);
             }
+            if ((p.debug & 16) && blockIdx.x == 0)
+                printf("i8 gram: %lld sub-tiles, %.0f cycles from first MMA issue to completion per sub-tile\n", dbg_n, (double)dbg_cycles / (double)(dbg_n > 0 ? dbg_n : 1));
         }
     } else {
         // ===== epilogue: set 0 = warps 2..9 (TMEM stage 0), set 1 = warps 10..17 (stage 1) =====
@@ -313,7 +323,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
         const double nbeta = -p.beta, variance = p.variance;
         const int exp_slow_hi = exp_slow_threshold_hi(variance);
         const bool mirror_mode = (p.uplo == GABO_SYMM_MIRROR);
-        const int64_t ldk = p.ldk;
+        const int64_t ldk = p.ldk, ldk8 = 8 * p.ldk;
         const bool vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15) == 0);   // 16-byte row-pair stores
         // dot = (H 2^28 + Lo) 2^(E_A + E_B - 110 + 49)
         const double c0 = scalbn(1.0, p.expo[0] + p.expo[1] - 61), c1 = scalbn(1.0, p.expo[0] + p.expo[1] - 33);
@@ -339,8 +349,17 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
                     oz_fence_after();
                     const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * STAGE_COLS + h * 16);
                     const bool rows_all = grow_tile + OT <= p.row1;
-                    const bool interior = rows_all && (gcol_tile + OT <= p.n2) && !(mirror_mode && diag_tile) && vec_ok;
+                    // fast store path: whole tile inside the matrix, no diagonal entries to overwrite (those tiles take the generic
+                    // path below); everything that does not depend on the pass is computed once per sub-tile
+                    const bool interior = rows_all && (gcol_tile + OT <= p.n2) && !diag_tile && vec_ok;
                     const int lr = lane >> 2, lc = (lane & 3) * 2;      // fragment coordinates: rows lr + 8 rg, columns lc, lc + 1
+                    const int64_t gc_sub = gcol_tile + sub * SUBN + h * 16 + lc;      // this thread's first column of pass 0
+                    const int64_t gr0 = grow_tile + q * 32 + lr;                      // ... and first row (then + 8 rg)
+                    double* kdir_sub = p.K + (lrow_tile + q * 32 + lr) * ldk + gc_sub;
+                    double* kmir_sub = p.K + gc_sub * ldk + gr0;
+                    unsigned store_mode = (interior ? 1u : 0u) | (mirror ? 2u : 0u);
+                    // opaque to the compiler, which otherwise re-derives all three (64-bit multiplies, ~50 instructions) in every pass
+                    asm volatile("" : "+l"(kdir_sub), "+l"(kmir_sub), "+r"(store_mode));
 #pragma unroll 1
                     for (int pass = 0; pass < 2; ++pass) {
                         // v[2 rg + e] = entry (row 32 q + 8 rg + lr, column gcol0 + lc + e)
@@ -391,34 +410,30 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
                             exp_neg_scaled_fast_n<8>(dot, v, exptab, variance, exp_slow_hi);                    // kernels_sphere_tf.py:88, 204
                             }
                         }
-                        const int64_t gcol0 = gcol_tile + sub * SUBN + h * 16 + pass * 8;
-                        const int64_t gc = gcol0 + lc;                             // this thread's first column
-                        const int64_t gr0 = grow_tile + q * 32 + lr;               // ... and first row (then + 8 rg)
-                        if (diag_tile) {                                           // K(X,X) diagonal is exactly `variance`
+                        double* const kdir = kdir_sub + pass * 8;
+                        if (store_mode & 1u) {
+                            double* kd = kdir;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (gc + (i & 1) == gr0 + 8 * (i >> 1)) v[i] = variance;
-                        }
-                        double* kdir = p.K + (lrow_tile + q * 32 + lr) * ldk + gc;
-                        if (interior) {
-#pragma unroll
-                            for (int rg = 0; rg < 4; ++rg) st_cs_v2(kdir + (int64_t)(8 * rg) * ldk, v[2 * rg], v[2 * rg + 1]);
-                            if (mirror) {     // K[col][row]: the 8 lanes of equal lc write 8 consecutive rows = 64 B
-                                double* kmir = p.K + gc * ldk + gr0;
+                            for (int rg = 0; rg < 4; ++rg, kd += ldk8) st_cs_v2(kd, v[2 * rg], v[2 * rg + 1]);
+                            if (store_mode & 2u) {     // K[col][row]: the 8 lanes of equal lc write 8 consecutive rows = 64 B
+                                double* const kmir = pass ? kmir_sub + ldk8 : kmir_sub;
+                                double* const kmir1 = kmir + ldk;
 #pragma unroll
                                 for (int rg = 0; rg < 4; ++rg) {
                                     st_cs(kmir + 8 * rg, v[2 * rg]);
-                                    st_cs(kmir + ldk + 8 * rg, v[2 * rg + 1]);
+                                    st_cs(kmir1 + 8 * rg, v[2 * rg + 1]);
                                 }
                             }
                         } else {
+                            const int64_t gc = gc_sub + pass * 8;
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const int64_t gr = gr0 + 8 * (i >> 1), gcc = gc + (i & 1);
+                                const double val = (diag_tile && gcc == gr) ? variance : v[i];   // K(X,X) diagonal is exactly `variance`
                                 const bool keep = !(mirror_mode && diag_tile) || gcc <= gr;   // mirrored diagonal tile: lower part + diagonal
-                                if (gr < p.row1 && gcc < p.n2 && keep) st_cs(kdir + (int64_t)(8 * (i >> 1)) * ldk + (i & 1), v[i]);
+                                if (gr < p.row1 && gcc < p.n2 && keep) st_cs(kdir + (int64_t)(8 * (i >> 1)) * ldk + (i & 1), val);
                                 // mirror image (for the diagonal tile: its upper part as the transpose of the lower one)
-                                if (mirror_mode && gr < p.row1 && gcc < gr && (mirror || diag_tile)) st_cs(p.K + gcc * ldk + gr, v[i]);
+                                if (mirror_mode && gr < p.row1 && gcc < gr && (mirror || diag_tile)) st_cs(p.K + gcc * ldk + gr, val);
                             }
                         }
                     }

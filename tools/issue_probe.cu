@@ -21,7 +21,28 @@ __global__ void probe(double* outd, float* outf, double a, float b) {
             if (MODE == 0 || MODE == 2 || MODE == 3 || MODE == 4) x[i] = fma(x[i], a, a);
             if (MODE == 1 || MODE == 2 || MODE == 3) y[i] = fmaf(y[i], b, b);
             if (MODE == 3) y[i + NCH] = fmaf(y[i + NCH], b, b);
-            if (MODE == 4) z[i] = (z[i] ^ it) + 0x9e37;
+            if (MODE == 4 || MODE == 5) z[i] = (z[i] ^ it) + 0x9e37;
+            if (MODE == 6) z[i] = z[i] * 0x80 + it;
+        }
+        // modes 7 / 8: the shape of the int8 Gram epilogue -- 88 DFMA and 176 integer instructions per iteration, either as two
+        // bursts (7: what a warp's instruction stream looks like when the phases follow each other) or finely interleaved (8)
+        if (MODE == 7) {
+#pragma unroll
+            for (int r = 0; r < 11; ++r)
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) x[i] = fma(x[i], a, a);
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < 11; ++r)
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) z[i] = ((z[i] ^ it) + 0x9e37) * 0x80 + r;
+            asm volatile("" ::: "memory");
+        }
+        if (MODE == 8) {
+#pragma unroll
+            for (int r = 0; r < 11; ++r)
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) { x[i] = fma(x[i], a, a); z[i] = ((z[i] ^ it) + 0x9e37) * 0x80 + r; }
         }
     }
     double s = 0; float t = 0; int u = 0;
@@ -52,12 +73,16 @@ void run(const char* name, int threads, double* od, float* of) {
 int main() {
     double* od; float* of;
     cudaMalloc(&od, 148 * 1024 * 8); cudaMalloc(&of, 148 * 1024 * 4);
-    for (int threads : {512, 1024}) {
+    for (int threads : {128, 512, 1024}) {
         run<0>("DFMA", threads, od, of);
         run<1>("FFMA", threads, od, of);
         run<2>("DFMA+FFMA", threads, od, of);
         run<3>("DFMA+2FFMA", threads, od, of);
         run<4>("DFMA+2INT(LOP,IADD)", threads, od, of);
+        run<5>("2INT(LOP,IADD)", threads, od, of);
+        run<6>("IMAD", threads, od, of);
+        run<7>("88 DFMA then 88x(LOP,IADD,IMAD)", threads, od, of);
+        run<8>("88x(DFMA,LOP,IADD,IMAD) mixed", threads, od, of);
     }
     return 0;
 }
