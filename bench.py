@@ -264,8 +264,10 @@ def run_ours(args):
     xch = None
     if world > 1 and NC % PANEL == 0 and os.environ.get('GABO_DIST_P2P', '1') != '0':
         xch = PanelExchange(BlockCyclic(NC, PANEL, world, rank), NC, dev)
-    ws = torch.empty(int(max(lib.gabo_points_gram_workspace_bytes(N, N, DIM), lib.gabo_points_gram_cyclic_workspace_bytes(N, DIM))),
-                     dtype=torch.uint8, device=dev)
+    ws = torch.empty(int(max(lib.gabo_points_gram_workspace_bytes(N, N, DIM), lib.gabo_points_gram_cyclic_workspace_bytes(N, DIM),
+                             lib.gabo_points_gram_i8_workspace_bytes(N, N))), dtype=torch.uint8, device=dev)
+    # single GPU: ops.points_gram picks the int8-tensor-core engine for the FP64 sphere Gram (GABO_GRAM_ENGINE=dmma forces the other)
+    gram_engine = ops.gram_engine(ops.SPHERE_GAUSSIAN, torch.float64, DIM, N, N) if world == 1 else 'dmma'
     grow = lay.global_rows()
     y_rows = grow[grow < NC].to(dev)
     V = torch.empty((int(y_rows.numel()) if world > 1 else NC, 1), dtype=torch.float64, device=dev)
@@ -532,7 +534,7 @@ def run_ours(args):
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'sphere Gaussian Gram N={N} on S^50 (D={DIM}) + FP64 Cholesky of K+1e-2 I at N={NC} + solve + loglik',
                    'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2, 'seeds': [SEED_X, SEED_Y],
-                   'gram_mode': 'lower tiles computed once, mirror-stored (full dense K)' if world == 1 else
+                   'gram_mode': f'lower tiles computed once, mirror-stored (full dense K); engine {gram_engine}' if world == 1 else
                                 (f'{PANEL}-row panels block-cyclic over {world} ranks; lower tiles computed by the row owner; upper tiles: '
                                  f'{gram_frac}/256 of the cross-GPU panel pairs recomputed by their row owner, the rest ' +
                                  ('staged (transposed) in local HBM by the kernel and moved to the owning GPU by copy-engine 2-D '
@@ -579,11 +581,22 @@ def run_ours(args):
                             '(gabo_profile_trailing_updates); flops = 2*128*64*512 per lower tile',
                      'peak_source': 'FP64 tensor peak is not in MEASURED_PEAKS.json: measured on this pool with tools/fp64_probe.cu '
                                     '(profiles/r01_fp64_probe.txt, DMMA 37.2 TFLOP/s = 148 SM x 64 FMA x 2 x 1.965 GHz; cuBLAS DGEMM 36.2)'},
-        'roofline_gram': {'bound': 'fp64', 'kernel': 'points_gram_kernel_1c<52> (DMMA inner products + fused acos/exp epilogue)', 'achieved': gram_flops / (gram_ms * 1e-3) * 1e-12,
-                          'peak': FP64_PEAK_TFLOPS * world, 'unit': 'TFLOP/s',
-                          'frac': gram_flops / (gram_ms * 1e-3) * 1e-12 / (FP64_PEAK_TFLOPS * world),
-                          'hbm_write_gbs_per_gpu': rows * N * 8 / (gram_ms * 1e-3) * 1e-9, 'hbm_peak_gbs': hbm_peak, 'hbm_peak_source': hbm_src,
-                          'flops_per_entry_declared': 2 * DIM + F_TR},
+        # DMMA engine: DMMA and DFMA share one pipe, so the bound is the FP64 pipe (declared flops of SURVEY 8d).  int8 engine: the
+        # inner products run on the integer tensor cores, what is left on the FP64 pipe is the acos/exp epilogue (~34 pipe slots per
+        # computed entry, tools/epi_math_probe.cu: 4.3 ms at this size), less than the 8 B/entry HBM write -> the bound is HBM.
+        'roofline_gram': ({'bound': 'hbm', 'kernel': 'points_gram_i8_kernel (tcgen05.mma kind::i8 inner products on 8 x 7-bit slices, S32 accumulators in '
+                                                     'TMEM, tcgen05.ld + FP64 acos/exp epilogue)',
+                           'achieved': rows * N * 8 / (gram_ms * 1e-3) * 1e-9, 'peak': hbm_peak, 'unit': 'GB/s',
+                           'frac': rows * N * 8 / (gram_ms * 1e-3) * 1e-9 / hbm_peak, 'hbm_peak_source': hbm_src,
+                           'algorithmic_bytes_per_entry': 8, 'fp64_declared_tflops': gram_flops / (gram_ms * 1e-3) * 1e-12,
+                           'fp64_declared_frac': gram_flops / (gram_ms * 1e-3) * 1e-12 / (FP64_PEAK_TFLOPS * world),
+                           'flops_per_entry_declared': 2 * DIM + F_TR} if gram_engine == 'i8' else
+                          {'bound': 'fp64', 'kernel': 'points_gram_kernel_1c<52> (DMMA inner products + fused acos/exp epilogue)',
+                           'achieved': gram_flops / (gram_ms * 1e-3) * 1e-12,
+                           'peak': FP64_PEAK_TFLOPS * world, 'unit': 'TFLOP/s',
+                           'frac': gram_flops / (gram_ms * 1e-3) * 1e-12 / (FP64_PEAK_TFLOPS * world),
+                           'hbm_write_gbs_per_gpu': rows * N * 8 / (gram_ms * 1e-3) * 1e-9, 'hbm_peak_gbs': hbm_peak, 'hbm_peak_source': hbm_src,
+                           'flops_per_entry_declared': 2 * DIM + F_TR}),
     }
     if spd is not None:
         line['spd'] = spd

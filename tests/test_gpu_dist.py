@@ -86,7 +86,7 @@ def test_cyclic_mirrored_gram_single_process(cuda, world, mod):
     for r in range(world):
         ops.points_gram_cyclic(ops.SPHERE_GAUSSIAN, X, ptrs, n, world, r, beta=2.0, variance=1.0, recompute_frac256=mod)
     torch.cuda.synchronize()
-    full = ops.points_gram(ops.SPHERE_GAUSSIAN, X, None, beta=2.0, uplo='mirror')
+    full = ops.points_gram(ops.SPHERE_GAUSSIAN, X, None, beta=2.0, uplo='mirror', engine='dmma')   # same kernel family: bit-identical
     for r in range(world):
         rows = lays[r].global_rows().cuda()
         assert torch.equal(bufs[r], full[rows])
@@ -109,7 +109,7 @@ def test_cyclic_staged_gram_single_process(cuda, world, frac, split, direct):
     bufs = [torch.full((max(l.local_rows, 1), n), float('nan'), dtype=torch.float64, device='cuda') for l in lays]
     ptrs = [b.data_ptr() for b in bufs]
     states = [ops.StagedGramState(n, world, r, frac, split, 'cuda', direct_frac256=direct) for r in range(world)]
-    full = ops.points_gram(ops.SPHERE_GAUSSIAN, X, None, beta=2.0, uplo='mirror')
+    full = ops.points_gram(ops.SPHERE_GAUSSIAN, X, None, beta=2.0, uplo='mirror', engine='dmma')   # same kernel family: bit-identical
     for rep in range(2):
         for b in bufs:
             b.fill_(float('nan'))
