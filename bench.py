@@ -245,7 +245,9 @@ def run_ours(args):
     # the kernel computes on (no SM stalls on remote stores); =direct: the kernel stores them into the peers' HBM itself.
     # Measured (profiles/r02_gram_staged_{2,8}gpu*.txt): at 2 GPUs staging wins (7.75 vs 8.49 ms); in the 8-GPU all-to-all both
     # transports saturate near 300 GB/s per GPU, the balance point is the same (~2.8 ms), and direct stores need no staging memory.
-    gram_mode = os.environ.get('GABO_GRAM_MODE', 'staged' if world == 2 else 'direct')
+    # =i8rows (default from 4 GPUs on): no exchange at all, every rank forms the full rows of its panels on the int8 tensor cores.
+    from gaboflow_b200.dist import default_gram_mode, gram_block_cyclic_rows_i8
+    gram_mode = os.environ.get('GABO_GRAM_MODE', default_gram_mode(world, N, DIM))
     from gaboflow_b200.dist import default_staged_frac256, make_staged_gram_state
     gram_frac = int(os.environ.get('GABO_GRAM_RECOMPUTE_FRAC256',
                                    str(default_staged_frac256(world) if gram_mode == 'staged' else default_recompute_frac256(world))))
@@ -267,7 +269,8 @@ def run_ours(args):
     ws = torch.empty(int(max(lib.gabo_points_gram_workspace_bytes(N, N, DIM), lib.gabo_points_gram_cyclic_workspace_bytes(N, DIM),
                              lib.gabo_points_gram_i8_workspace_bytes(N, N))), dtype=torch.uint8, device=dev)
     # single GPU: ops.points_gram picks the int8-tensor-core engine for the FP64 sphere Gram (GABO_GRAM_ENGINE=dmma forces the other)
-    gram_engine = ops.gram_engine(ops.SPHERE_GAUSSIAN, torch.float64, DIM, N, N) if world == 1 else 'dmma'
+    gram_engine = ops.gram_engine(ops.SPHERE_GAUSSIAN, torch.float64, DIM, N, N) if world == 1 else \
+        ('i8' if (p2p_mirror and gram_mode == 'i8rows') else 'dmma')
     grow = lay.global_rows()
     y_rows = grow[grow < NC].to(dev)
     V = torch.empty((int(y_rows.numel()) if world > 1 else NC, 1), dtype=torch.float64, device=dev)
@@ -294,6 +297,8 @@ def run_ours(args):
             events[0].record()
         if world == 1:
             ops.points_gram(ops.SPHERE_GAUSSIAN, Xd, None, beta=BETA, variance=VARIANCE, out=K, uplo='mirror', workspace=ws)
+        elif p2p_mirror and gram_mode == 'i8rows':
+            gram_block_cyclic_rows_i8(ops.SPHERE_GAUSSIAN, Xd, lay, K, BETA, VARIANCE, workspace=ws)
         elif p2p_mirror:
             gram_block_cyclic_mirrored(ops.SPHERE_GAUSSIAN, Xd, lay, peers, BETA, VARIANCE, workspace=ws, sync=True,
                                        recompute_frac256=gram_frac, xch=xch, staged=gram_staged)
@@ -416,7 +421,9 @@ def run_ours(args):
         loc = np.r_[0:64, N // 2 + 100:N // 2 + 164, N - 64:N]
         gl = loc
     else:
-        if p2p_mirror:
+        if p2p_mirror and gram_mode == 'i8rows':        # the same Gram path as the timed steps
+            gram_block_cyclic_rows_i8(ops.SPHERE_GAUSSIAN, X, lay, K, BETA, VARIANCE, workspace=ws)
+        elif p2p_mirror:
             gram_block_cyclic_mirrored(ops.SPHERE_GAUSSIAN, X, lay, peers, BETA, VARIANCE, workspace=ws, sync=True,
                                        recompute_frac256=gram_frac, xch=xch, staged=gram_staged)
         else:
@@ -525,7 +532,7 @@ def run_ours(args):
     value = entries / (gram_ms * 1e-3)
     potrf_s = potrf_ms * 1e-3
     potrf_tflops = (NC ** 3 / 3) / potrf_s * 1e-12 if potrf_s > 0 else None
-    sym = (world == 1) or p2p_mirror
+    sym = (world == 1) or (p2p_mirror and gram_mode != 'i8rows')
     gram_flops = entries * (2 * DIM + F_TR) * (0.5 if sym else 1.0)    # symmetric tiles are computed once and mirrored
     step_ms = total_ms / args.steps
     line = {
@@ -535,6 +542,8 @@ def run_ours(args):
         'config': {'workload': f'sphere Gaussian Gram N={N} on S^50 (D={DIM}) + FP64 Cholesky of K+1e-2 I at N={NC} + solve + loglik',
                    'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2, 'seeds': [SEED_X, SEED_Y],
                    'gram_mode': f'lower tiles computed once, mirror-stored (full dense K); engine {gram_engine}' if world == 1 else
+                                (f'{PANEL}-row panels block-cyclic over {world} ranks; every rank forms the FULL rows of its panels on the int8 '
+                                 f'tensor cores (no exchange, no symmetry across GPUs; full dense K)') if (p2p_mirror and gram_mode == 'i8rows') else
                                 (f'{PANEL}-row panels block-cyclic over {world} ranks; lower tiles computed by the row owner; upper tiles: '
                                  f'{gram_frac}/256 of the cross-GPU panel pairs recomputed by their row owner, the rest ' +
                                  ('staged (transposed) in local HBM by the kernel and moved to the owning GPU by copy-engine 2-D '
@@ -588,7 +597,10 @@ def run_ours(args):
                                                      'TMEM, tcgen05.ld + FP64 acos/exp epilogue)',
                            'achieved': rows * N * 8 / (gram_ms * 1e-3) * 1e-9, 'peak': hbm_peak, 'unit': 'GB/s',
                            'frac': rows * N * 8 / (gram_ms * 1e-3) * 1e-9 / hbm_peak, 'hbm_peak_source': hbm_src,
-                           'algorithmic_bytes_per_entry': 8, 'fp64_declared_tflops': gram_flops / (gram_ms * 1e-3) * 1e-12,
+                           'algorithmic_bytes_per_entry': 8,
+                           'traffic': {'case': 'N=16384 lower tiles (one launch, ncu --set full, profiles/r02_points_gram_i8_ncu.txt)',
+                                       'dram_read_plus_write_bytes': 1.045e9, 'algorithmic_bytes': 8256 * 128 * 128 * 8},
+                           'fp64_declared_tflops': gram_flops / (gram_ms * 1e-3) * 1e-12,
                            'fp64_declared_frac': gram_flops / (gram_ms * 1e-3) * 1e-12 / (FP64_PEAK_TFLOPS * world),
                            'flops_per_entry_declared': 2 * DIM + F_TR} if gram_engine == 'i8' else
                           {'bound': 'fp64', 'kernel': 'points_gram_kernel_1c<52> (DMMA inner products + fused acos/exp epilogue)',

@@ -108,3 +108,24 @@ def test_bench_reference_arm_runs_small():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'
     assert line['e2e']['h2d_bytes_per_step'] == 0
+
+
+def test_gram_engine_and_multi_gpu_mode_selection():
+    """Host-side dispatch only (no device work): which Gram kernel / multi-GPU mode a problem gets."""
+    import torch
+    from gaboflow_b200 import ops
+    from gaboflow_b200.dist import default_gram_mode
+    f64 = torch.float64
+    assert ops.gram_engine(ops.SPHERE_GAUSSIAN, f64, 51, 65536, 65536) == 'i8'
+    assert ops.gram_engine(ops.SPHERE_LAPLACE, f64, 64, 4096, 4096) == 'i8'
+    assert ops.gram_engine(ops.SPHERE_GAUSSIAN, f64, 65, 65536, 65536) == 'dmma'         # more than 64 coordinates
+    assert ops.gram_engine(ops.SPHERE_GAUSSIAN, f64, 51, 30, 30) == 'dmma'               # launch-bound sizes (configs 1-3)
+    assert ops.gram_engine(ops.SQDIST_GAUSSIAN, f64, 21, 16384, 16384) == 'dmma'         # not a sphere kind
+    assert ops.gram_engine(ops.SPHERE_GAUSSIAN, torch.float32, 51, 65536, 65536) == 'dmma'
+    assert ops.gram_engine(ops.SPHERE_GAUSSIAN, f64, 51, 65536, 65536, engine='dmma') == 'dmma'
+    with pytest.raises(ValueError):
+        ops.gram_engine(ops.SPHERE_GAUSSIAN, f64, 100, 65536, 65536, engine='i8')
+    assert default_gram_mode(2, 65536, 51) == 'staged'
+    assert default_gram_mode(4, 65536, 51) == 'i8rows' and default_gram_mode(8, 65536, 51) == 'i8rows'
+    assert default_gram_mode(8, 65536 + 100, 51) == 'direct' and default_gram_mode(8, 65536, 100) == 'direct'
+    assert default_gram_mode(3, 65536, 51) == 'direct'
