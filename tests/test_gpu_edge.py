@@ -136,3 +136,69 @@ def test_spd_kernel_classes_reject_non_spd_input(cuda):
             k.compute_K_symm(X)
         with pytest.raises(ValueError, match='matrix 7'):
             GPR(X, np.zeros((20, 1)), kern=k).compute_log_likelihood()
+
+
+def test_no_out_of_bounds_writes(cuda):
+    """Canary frames around the output of every Gram / factorisation / solve entry point at ragged sizes and with leading
+    dimensions larger than the row length (compute-sanitizer is not available on the pool, profiles/r02_sanitizer_note.txt):
+    nothing outside the window the call was given may change."""
+    from gaboflow_b200 import ops
+    pad, CAN = 3, float(np.e)
+
+    def framed(rows, cols, dtype=torch.float64):
+        big = torch.full((rows + 2 * pad, cols + 2 * pad), CAN, dtype=dtype, device='cuda')
+        return big, big[pad:pad + rows, pad:pad + cols]
+
+    def frame_intact(big, rows, cols):
+        b = big.cpu().numpy()
+        m = np.ones(b.shape, dtype=bool)
+        m[pad:pad + rows, pad:pad + cols] = False
+        return bool(np.all(b[m] == b.dtype.type(CAN)))
+
+    # point Grams: both FP64 engines and the FP32 tensor-core kernel, every uplo mode, a row range, a cross Gram
+    for (n, dim) in [(389, 37), (131, 3), (257, 64)]:
+        Xn = orc.synth_sphere(n, dim, seed=n)
+        X = torch.from_numpy(Xn).cuda()
+        X2 = torch.from_numpy(orc.synth_sphere(200, dim, seed=n + 1)).cuda()
+        for eng in ('dmma', 'i8'):
+            for uplo in ('full', 'lower', 'mirror'):
+                big, out = framed(n, n)
+                ops.points_gram(ops.SPHERE_GAUSSIAN, X, None, beta=1.5, uplo=uplo, engine=eng, out=out)
+                assert frame_intact(big, n, n), (n, dim, eng, uplo)
+            big, out = framed(n - 128, n)
+            ops.points_gram(ops.SPHERE_LAPLACE, X, None, beta=1.5, row0=128, row1=n, engine=eng, out=out)
+            assert frame_intact(big, n - 128, n), (n, dim, eng, 'rows')
+            big, out = framed(n, 200)
+            ops.points_gram(ops.SPHERE_GAUSSIAN, X, X2, beta=1.5, engine=eng, out=out)
+            assert frame_intact(big, n, 200), (n, dim, eng, 'cross')
+        for uplo in ('full', 'mirror'):
+            big, out = framed(n, n, torch.float32)
+            ops.points_gram(ops.SPHERE_GAUSSIAN, X.float(), None, beta=1.5, uplo=uplo, out=out)
+            assert frame_intact(big, n, n), (n, dim, 'f32', uplo)
+    # SPD pair Grams
+    for d, n in [(2, 150), (6, 77)]:
+        p = ops.spd_prep(torch.from_numpy(orc.synth_spd_mandel(n, d, seed=d)).cuda(), d, want_logm=True)
+        for kind in (ops.SPD_AI_GAUSSIAN, ops.SPD_STEIN):
+            for uplo in ('full', 'mirror'):
+                big, out = framed(n, n)
+                ops.spd_gram(kind, p, None, beta=0.7, out=out, uplo=uplo)
+                assert frame_intact(big, n, n), (d, n, kind, uplo)
+    # factorisation in a framed window (also: strictly upper triangle untouched), solves with 1 / 3 / 70 right-hand sides
+    n = 700
+    G = np.random.default_rng(3).standard_normal((n, 900))
+    A = G @ G.T / 900 + np.eye(n)
+    big, win = framed(n, n)
+    win.copy_(torch.from_numpy(A).cuda())
+    ops.potrf_(win, 0.25)
+    assert frame_intact(big, n, n)
+    L = win.cpu().numpy()
+    assert np.array_equal(np.triu(L, 1), np.triu(A, 1))
+    assert np.max(np.abs(np.tril(L) - sla.cholesky(A + 0.25 * np.eye(n), lower=True))) < 1e-12
+    Lc = torch.from_numpy(np.tril(L)).cuda()
+    for nrhs in (1, 3, 70):
+        big, B = framed(n, nrhs)
+        Bn = np.random.default_rng(nrhs).standard_normal((n, nrhs))
+        B.copy_(torch.from_numpy(Bn).cuda())
+        ops.trsm_(Lc, B)
+        assert frame_intact(big, n, nrhs), nrhs
+        assert np.max(np.abs(np.tril(L) @ B.cpu().numpy() - Bn)) < 1e-10

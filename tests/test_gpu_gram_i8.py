@@ -185,3 +185,31 @@ def test_i8_default_engine_through_kernel_class(cuda):
     off = ~np.eye(n, dtype=bool)
     assert _rel(K[off], Ko[off]) < RTOL64
     assert np.array_equal(K, K.T) and np.all(np.diag(K) == 1.0)
+
+
+def test_i8_no_out_of_bounds_writes(cuda):
+    """Canary-padded output buffers (compute-sanitizer is not available on the pool): the int8 kernel writes nothing outside
+    the [row1-row0, n2] window it was given, on ragged sizes, with a leading dimension larger than n2, in every mode."""
+    from gaboflow_b200 import ops
+    pad = 3
+    for (n, dim, uplo, row0, row1) in [(389, 37, 'full', 128, 389), (389, 37, 'mirror', 0, 389), (260, 64, 'lower', 0, 260),
+                                       (1, 3, 'full', 0, 1), (300, 51, 'full', 0, 1)]:
+        Xn = orc.synth_sphere(n, dim, seed=n + dim)
+        X = torch.from_numpy(Xn).to(cuda)
+        rows = row1 - row0
+        big = torch.full((rows + 2 * pad, n + 2 * pad), np.pi, dtype=torch.float64, device=cuda)
+        out = big[pad:pad + rows, pad:pad + n]
+        ops.points_gram(ops.SPHERE_GAUSSIAN, X, None, beta=1.5, uplo=uplo, row0=row0, row1=row1, engine='i8', out=out)
+        torch.cuda.synchronize()
+        b = big.cpu().numpy()
+        frame = np.ones_like(b, dtype=bool)
+        frame[pad:pad + rows, pad:pad + n] = False
+        assert np.all(b[frame] == np.pi), (n, dim, uplo)
+        Ko = orc.sphere_gaussian_K(Xn, beta=1.5)[row0:row1]
+        got = b[pad:pad + rows, pad:pad + n]
+        m = got != np.pi
+        if uplo != 'lower':
+            assert m.all()
+        off = m & (np.arange(row0, row1)[:, None] != np.arange(n)[None, :])
+        if off.any():
+            assert _rel(got[off], Ko[off]) < RTOL64
