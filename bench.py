@@ -7,6 +7,8 @@ manifold Gram entries/s + FP64 Cholesky time of K + sigma^2 I at N = 32,768.
 
 A step is one pass of the hot path over one synthetic batch (BASELINE.json configs[3]):
     gram   sphere Gaussian Gram K(X,X), N = 65,536 points on S^50 (D = 51), beta = 2, variance = 1, full dense FP64
+           (single GPU: inner products on the int8 tensor cores, exact slicing -- ops.gram_engine; GABO_GRAM_ENGINE=dmma for the
+           FP64 tensor instruction)
     potrf  in-place FP64 Cholesky of the leading 32,768 block of K + 1e-2 I            (the metric's Cholesky)
     solve  alpha = L^-1 y, log marginal likelihood (one scalar)
 `value` = Gram entries per second over the gram phase (max over ranks); `ms_per_step` covers the whole step and
@@ -23,8 +25,10 @@ the Cholesky info word, sampled Gram rows of every kernel against the NumPy orac
 on sampled tiles, and the log-likelihood of a 4096-point sub-problem against the oracle.
 
 N > 1 (one rank per GPU under torchrun, strong scaling: the same matrices on more GPUs).  K lives in 512-row panels, 1-D
-block-cyclic over the ranks.  sphere gram: lower tiles by the row owner; upper tiles either stored into the owning GPU over
-NVLink from inside the kernel or recomputed by their row owner (hashed split, dist.default_recompute_frac256).  SPD gram: the
+block-cyclic over the ranks.  sphere gram (dist.default_gram_mode; GABO_GRAM_MODE overrides): from 4 GPUs on every rank forms the
+FULL rows of its panels on the int8 tensor cores (no exchange); at 2 GPUs the lower tiles are computed by the row owner and the
+mirror blocks travel by copy engine from a local staging buffer ('staged'); 'direct' = upper tiles either stored into the owning
+GPU over NVLink from inside the kernel or recomputed by their row owner (hashed split, dist.default_recompute_frac256).  SPD gram: the
 lower 32 x 128 blocks are dealt round-robin to the ranks and stored, with their mirror images, straight into the owners' HBM.
 Completion is a stream-ordered flag handshake.  potrf: right-looking over panels with one panel of look-ahead; the block
 column reaches every rank by NVLink stores from the row-solve kernel, the diagonal block by copy engines, ordering by
