@@ -48,6 +48,8 @@ class GPR(Parameterized):
         if Yd.shape[0] != self.X.shape[0]:
             Yd = Yd.t().contiguous()
         self.Y = Yd.contiguous()
+        if getattr(kern, 'float_type', torch.float64) != torch.float64:
+            raise ValueError('GPR factors K + sigma^2 I in FP64: the kernel must be in float64 mode (kern.set_float_type("float64"))')
         self.kern = kern
         self.mean_function = mean_function if mean_function is not None else Zero()
         self.likelihood = Gaussian()

@@ -11,6 +11,8 @@ Structure (instead of the reference's per-PAIR inverse / sqrtm / SVD / logm on N
 """
 from __future__ import annotations
 
+import torch
+
 from .. import ops
 from ..param import Kern, Param, to_device
 
@@ -52,12 +54,20 @@ class _SpdPairKernel(Kern):
         if X2 is not None:
             p2 = X2 if isinstance(X2, ops.SpdPrep) else self.prepare(X2)
         uplo = _resolve_uplo(p2, uplo, row0, row1, p1.n)
+        if self.float_type == torch.float32:
+            # FP32 mode: FP64 arithmetic inside the pair kernel (see param.Kern.float_type), float32 result
+            K = ops.spd_gram(self._kind, p1, p2, beta=self._beta_eff(), variance=float(self.variance),
+                             row0=row0, row1=row1, uplo=uplo)
+            if out is not None:
+                out.copy_(K)
+                return out
+            return K.to(torch.float32)
         return ops.spd_gram(self._kind, p1, p2, beta=self._beta_eff(), variance=float(self.variance),
                             out=out, row0=row0, row1=row1, uplo=uplo)
 
     def Kdiag(self, X):
         Xd = to_device(X)
-        return ops.kdiag_const(int(Xd.shape[0]), float(self.variance), Xd.device)
+        return ops.kdiag_const(int(Xd.shape[0]), float(self.variance), Xd.device).to(self.float_type)
 
 
 class SpdSteinGaussianKernel(_SpdPairKernel):
@@ -79,7 +89,7 @@ class SpdSteinGaussianKernel(_SpdPairKernel):
     def Kdiag(self, X):
         """``diag_part(K(X))`` (:129) without forming K: ``variance * det(X_i)^beta``."""
         p = X if isinstance(X, ops.SpdPrep) else self.prepare(X)
-        return ops.spd_stein_kdiag(p, self._beta_eff(), float(self.variance))
+        return ops.spd_stein_kdiag(p, self._beta_eff(), float(self.variance)).to(self.float_type)
 
     def update_beta(self, beta):
         self.beta_shifted = (beta - self.continuous_param_space_limit)   # :144
@@ -132,13 +142,16 @@ class _SpdSqdistKernel(Kern):
     def K(self, X, X2=None, uplo='mirror', out=None, row0=0, row1=None):
         F1 = self._features(X)
         F2 = self._features(X2) if X2 is not None else None
+        if self.float_type == torch.float32:       # FP32 mode: features (FP64 logm for Log-Euclid) rounded once, TF32 tcgen05 tiles
+            F1 = F1.to(torch.float32)
+            F2 = F2.to(torch.float32) if F2 is not None else None
         uplo = _resolve_uplo(F2, uplo, row0, row1, int(F1.shape[0]))
         return ops.points_gram(ops.SQDIST_GAUSSIAN, F1, F2, beta=float(self.beta_param), variance=float(self.variance),
                                out=out, row0=row0, row1=row1, uplo=uplo)
 
     def Kdiag(self, X):
         Xd = to_device(X)
-        return ops.kdiag_const(int(Xd.shape[0]), float(self.variance), Xd.device)
+        return ops.kdiag_const(int(Xd.shape[0]), float(self.variance), Xd.device).to(self.float_type)
 
 
 class SpdFrobeniusGaussianKernel(_SpdSqdistKernel):

@@ -2,7 +2,8 @@
 
 Drop-in for ``BoManifolds/kernel_utils/kernels_sphere_tf.py`` (GPflow-0.5 branch, :15-221): same class names,
 constructor arguments, Param attributes and methods.  ``K`` / ``Kdiag`` take NumPy arrays or torch CUDA tensors and
-return torch CUDA tensors (FP64); ``compute_K*`` return NumPy like GPflow's AutoFlow wrappers.
+return torch CUDA tensors (FP64; float32 after ``set_float_type('float32')``: TF32 tcgen05 kernel, 1e-5); ``compute_K*`` return
+NumPy like GPflow's AutoFlow wrappers.
 """
 from __future__ import annotations
 
@@ -23,8 +24,8 @@ class _SphereKernelBase(Kern):
         symmetric matrix while computing each off-diagonal tile once.  ``uplo='lower'`` writes only the tiles the
         Cholesky reads; ``row0/row1`` select a row block (multi-GPU sharding, multiples of 128).
         """
-        Xd = to_device(X)
-        X2d = to_device(X2) if X2 is not None else None
+        Xd = to_device(X, self.float_type)
+        X2d = to_device(X2, self.float_type) if X2 is not None else None
         if X2d is None and (row0 != 0 or (row1 is not None and row1 != Xd.shape[0])) and uplo == 'mirror':
             uplo = 'full'
         if X2d is not None:
@@ -34,8 +35,8 @@ class _SphereKernelBase(Kern):
 
     def Kdiag(self, X):
         """``fill([N], variance)`` (``kernels_sphere_tf.py:90-105, 206-221``)."""
-        Xd = to_device(X)
-        return ops.kdiag_const(int(Xd.shape[0]), float(self.variance), Xd.device)
+        Xd = to_device(X, self.float_type)
+        return ops.kdiag_const(int(Xd.shape[0]), float(self.variance), Xd.device).to(self.float_type)
 
 
 class SphereGaussianKernel(_SphereKernelBase):

@@ -87,10 +87,24 @@ def to_device(X, dtype=torch.float64):
 class Kern(Parameterized):
     """Base of the manifold kernels: the slice of ``gpflow.kernels.Kern`` (0.5) that the reference uses."""
 
+    # GPflow's ``settings.float_type``, per kernel object: torch.float64 (default) or torch.float32 ("FP32 mode", north_star
+    # tolerance 1e-5): K / Kdiag then take and return float32 tensors.  Sphere and squared-distance kernels run the TF32
+    # tcgen05 Gram kernel; the SPD pair kernels (affine-invariant, Stein) keep FP64 arithmetic inside -- a 6 x 6 eigen-solve in
+    # FP32 does not hold 1e-5 on ill-conditioned pairs -- and store float32.  The GP algebra (GPR) is FP64 only.
+    float_type = torch.float64
+
     def __init__(self, input_dim, active_dims=None):
         self.input_dim = int(input_dim)
         # accepted and stored, never applied -- same as the reference, whose K() bodies do not call _slice
         self.active_dims = list(active_dims) if active_dims is not None else list(range(self.input_dim))
+
+    def set_float_type(self, float_type):
+        """'float64' / 'float32' (or the torch / NumPy dtype); returns self."""
+        name = str(float_type).replace('torch.', '').replace("<class 'numpy.", '').replace("'>", '')
+        if name not in ('float64', 'float32'):
+            raise ValueError('float_type must be float64 or float32')
+        self.__dict__['float_type'] = torch.float64 if name == 'float64' else torch.float32
+        return self
 
     # subclasses implement K(X, X2=None) and Kdiag(X) on device tensors
     def K(self, X, X2=None):

@@ -202,3 +202,53 @@ def test_no_out_of_bounds_writes(cuda):
         ops.trsm_(Lc, B)
         assert frame_intact(big, n, nrhs), nrhs
         assert np.max(np.abs(np.tril(L) @ B.cpu().numpy() - Bn)) < 1e-10
+
+
+def test_fp32_mode_of_every_kernel_class(cuda):
+    """north_star: within 1e-5 in FP32 mode.  `set_float_type('float32')` on any kernel class: float32 in, float32 out; sphere
+    and squared-distance kernels on the TF32 tcgen05 Gram kernel, SPD pair kernels with FP64 arithmetic inside."""
+    from gaboflow_b200 import (SphereGaussianKernel, SphereLaplaceKernel, SpdAffineInvariantGaussianKernel,
+                               SpdAffineInvariantLaplaceKernel, SpdSteinGaussianKernel, SpdFrobeniusGaussianKernel,
+                               SpdLogEuclideanGaussianKernel, GPR)
+    X = orc.synth_sphere(300, 51, seed=5)
+    X2 = orc.synth_sphere(130, 51, seed=6)
+    for k, ref in [(SphereGaussianKernel(51, range(51), beta_min=0.5, beta=1.5, variance=1.2), lambda a, b: orc.sphere_gaussian_K(a, b, beta=2.0, variance=1.2)),
+                   (SphereLaplaceKernel(51, range(51), beta=2.0, variance=0.8), lambda a, b: orc.sphere_laplace_K(a, b, beta=2.0, variance=0.8))]:
+        k.set_float_type('float32')
+        K = k.K(X.astype(np.float32))
+        assert K.dtype == torch.float32
+        Kn = K.cpu().numpy().astype(np.float64)
+        Ko = ref(X, None)
+        off = ~np.eye(300, dtype=bool)
+        # 1e-5 of the entry, plus the conditioning of acos at FP32 input rounding (6e-8 on the dot product)
+        assert np.max(np.abs(Kn - Ko)[off] / Ko[off]) < 2e-5
+        assert np.array_equal(Kn, Kn.T) and np.all(np.diag(Kn) == np.float32(float(k.variance)))
+        K12 = k.compute_K(X.astype(np.float32), X2.astype(np.float32))
+        assert K12.dtype == np.float32 and np.max(np.abs(K12 / ref(X, X2) - 1)) < 2e-5
+        assert k.Kdiag(X).dtype == torch.float32
+        with pytest.raises(ValueError):
+            GPR(X, np.zeros((300, 1)), kern=k)
+        k.set_float_type('float64')
+        assert k.K(X).dtype == torch.float64
+    V = orc.synth_spd_mandel(150, 3, seed=7)
+    V2 = orc.synth_spd_mandel(60, 3, seed=8)
+    cases = [(SpdAffineInvariantGaussianKernel(6, range(6), beta_min=0.2, beta=0.5), lambda a, b: orc.spd_ai_gaussian_K(a, b, beta=0.7)),
+             (SpdAffineInvariantLaplaceKernel(6, range(6), beta=0.7), lambda a, b: orc.spd_ai_laplace_K(a, b, beta=0.7)),
+             (SpdSteinGaussianKernel(6, range(6), beta=1.5), lambda a, b: orc.spd_stein_K(a, b, beta=1.5)),
+             (SpdFrobeniusGaussianKernel(6, range(6), beta=0.3), lambda a, b: orc.spd_frobenius_K(a, b, beta=0.3)),
+             (SpdLogEuclideanGaussianKernel(6, range(6), beta=0.6), lambda a, b: orc.spd_logeuclid_K(a, b, beta=0.6))]
+    for k, ref in cases:
+        k.set_float_type('float32')
+        K = k.K(V.astype(np.float32))
+        K12 = k.K(V.astype(np.float32), V2.astype(np.float32))
+        assert K.dtype == torch.float32 and K12.dtype == torch.float32
+        # the oracle sees the same float32-rounded inputs
+        Vr, V2r = V.astype(np.float32).astype(np.float64), V2.astype(np.float32).astype(np.float64)
+        Ko, K12o = ref(Vr, None), ref(Vr, V2r)
+        off = ~np.eye(150, dtype=bool)
+        # pair kernels: FP64 inside, only the float32 rounding of the result remains; squared-distance kernels: TF32x3 tiles,
+        # relative error of exp(-beta d^2) = beta d^2 * 1e-6
+        tol = 2e-5 if isinstance(k, (SpdFrobeniusGaussianKernel, SpdLogEuclideanGaussianKernel)) else 2e-7
+        assert np.max(np.abs(K.cpu().numpy() - Ko)[off] / Ko[off]) < tol, type(k).__name__
+        assert np.max(np.abs(K12.cpu().numpy() / K12o - 1)) < tol, type(k).__name__
+        assert k.Kdiag(V.astype(np.float32)).dtype == torch.float32
