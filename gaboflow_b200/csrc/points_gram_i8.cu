@@ -24,12 +24,14 @@
 // (64 KB, K padded to 64) is ONE contiguous TMA bulk copy and every shared-memory descriptor is base + constant.
 //
 // Kernel: persistent CTAs (one per SM, 576 threads).  Warp 0 lane 0: TMA producer (A tile per work item, B tiles through a
-// 2-deep ring).  Warp 1 lane 0: MMA issuer -- per 128 x 32 output sub-tile, 36 slice pairs x 2 k-steps of tcgen05.mma
-// (M = 128, N = 32, K = 32) into one of two TMEM stages of 8 x 32 columns (the whole 512-column TMEM).  Warps 2..17: two sets
-// of 8 epilogue warps, one set per TMEM stage; a warp owns 32 rows (its TMEM lane quarter) x 16 columns: tcgen05.ld of the 8
-// accumulators, integer recombination, FP64 epilogue, mirror image K[col][row] stored straight from the registers (lane = row:
-// a register across the warp is 32 consecutive doubles of a mirrored row), direct tile stored after a 16 x 16 shuffle transpose
-// (two 128-byte row segments per store).
+// 2-deep ring).  Warp 1 lane 0: MMA issuer -- per 128 x 32 output sub-tile, 8 slices x 2 k-steps = 16 tcgen05.mma (M = 128,
+// N = 32 (8 - s): A_s against the STACK B_0 .. B_(7-s), K = 32) into one of two TMEM stages of 8 x 32 columns (the whole
+// 512-column TMEM).  Warps 2..17: two sets of 8 epilogue warps, one set per TMEM stage; a warp owns 32 rows (its TMEM lane
+// quarter) x 16 columns, in two passes of 8 columns: tcgen05.ld.16x256b of the 8 accumulators (the MMA-fragment layout: thread =
+// rows r, r + 8 x columns c, c + 1), integer recombination, FP64 epilogue, then stores straight from the registers -- in that
+// layout both the direct tile (4 lanes x 16 B = 64 B of a row) and its mirror image K[col][row] (8 lanes = 8 consecutive rows =
+// 64 B of a mirrored row) go out in whole 64-byte segments with no transposition.
+// Measurements, diagnostic knobs and the variants that were tried and dropped: DESIGN.md section 4.1b.
 #include <cstdio>
 #include <cstdlib>
 #include "gabo_common.cuh"
@@ -286,8 +288,9 @@ __global__ void __launch_bounds__(O_THREADS, 1) points_gram_i8_kernel(const OzPa
                         oz_fence_after();
                         // 16 MMAs per 128 x 32 sub-tile: A_s (k-step kk) times the STACK B_0 .. B_(7-s) of the sub-tile's columns
                         // (N = 32 (8 - s)), accumulated into the accumulators g = s .. 7 -- exactly the pairs s + t = g <= 7.
-                        // An MMA costs ~130 cycles whatever N (A streams through at one row per cycle), so the 72 narrow
-                        // products of the first version (one per pair and k-step) were 4.5x slower than these 16 wide ones.
+                        // The 72 narrow products of the first version (one per pair and k-step, each re-streaming its A slice) took
+                        // 4.5x the tensor time of these 16 wide ones, which run at the MAC rate of the unit (~1150 cycles of MMA
+                        // per sub-tile, 1711 from first issue to completion).
                         const uint32_t b_sub = b_addr + (uint32_t)(sub * BSUB);
                         const long long dbg_t0 = clock64();
 #pragma unroll 1
