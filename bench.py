@@ -170,6 +170,11 @@ def cpu_reference_sample(n_gram, n_chol_sample=8192, gram_rows=2048, n_chol_metr
     return out
 
 
+def workload_l2_note(n_gram, world):
+    """`config.l2` (timing rule: flush L2 or use inputs larger than L2, and say which) -- the same string in both arms."""
+    return f'no flush: {n_gram * n_gram * 8 / world / 1e9:.1f} GB of K per GPU >> 126 MB L2'
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -190,7 +195,8 @@ def run_reference(args):
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'sphere Gaussian Gram N={n_gram} on S^50 (D=51) + FP64 Cholesky of K+1e-2 I at N={n_chol} + solve + loglik',
                    'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2, 'seeds': [SEED_X, SEED_Y],
-                   'note': 'each step is a bounded sample of the workload on the host CPU cores (see cpu_baseline.sample)'},
+                   'l2': workload_l2_note(n_gram, max(int(os.environ.get('WORLD_SIZE', '1')), 1))},
+        'config_detail': {'note': 'each step is a bounded sample of the workload on the host CPU cores (see cpu_baseline.sample)'},
         'cholesky': chol,
         'step_entries_per_s': last['step_entries_per_s'], 'step_seconds_extrapolated': last['step_seconds_extrapolated'],
         'cpu_baseline': {k: last[k] for k in ('unit', 'cores', 'kind', 'sample', 'step_seconds_extrapolated', 'step_note')} | {'value': val},
@@ -545,6 +551,8 @@ def run_ours(args):
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'sphere Gaussian Gram N={N} on S^50 (D={DIM}) + FP64 Cholesky of K+1e-2 I at N={NC} + solve + loglik',
                    'beta': BETA, 'variance': VARIANCE, 'sigma2': SIGMA2, 'seeds': [SEED_X, SEED_Y],
+                   'l2': workload_l2_note(N, world)},
+        'config_detail': {
                    'gram_mode': f'lower tiles computed once, mirror-stored (full dense K); engine {gram_engine}' if world == 1 else
                                 (f'{PANEL}-row panels block-cyclic over {world} ranks; every rank forms the FULL rows of its panels on the int8 '
                                  f'tensor cores (no exchange, no symmetry across GPUs; full dense K)') if (p2p_mirror and gram_mode == 'i8rows') else
@@ -554,7 +562,6 @@ def run_ours(args):
                                   'copies released per chunk by device flags, overlapping the kernel' if gram_staged is not None else
                                   'stored into the owning GPU over NVLink from inside the kernel') + ' (full dense K)' if p2p_mirror else
                                  f'full rows of the dense K in {PANEL}-row panels, 1-D block-cyclic over {world} ranks'),
-                   'l2': f'no flush: {rows * N * 8 / 1e9:.1f} GB of K per GPU >> 126 MB L2',
                    'parallelism': 'single GPU' if world == 1 else
                                   f'Gram: row panels block-cyclic over {world} ranks, no collective; Cholesky: right-looking over panels, ' +
                                   ('one panel of look-ahead, block column delivered to every rank by NVLink stores from the row-solve '
