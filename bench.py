@@ -609,8 +609,9 @@ def run_ours(args):
                            'achieved': rows * N * 8 / (gram_ms * 1e-3) * 1e-9, 'peak': hbm_peak, 'unit': 'GB/s',
                            'frac': rows * N * 8 / (gram_ms * 1e-3) * 1e-9 / hbm_peak, 'hbm_peak_source': hbm_src,
                            'algorithmic_bytes_per_entry': 8,
-                           'traffic': {'case': 'N=16384 lower tiles (one launch, ncu --set full, profiles/r02_points_gram_i8_ncu.txt)',
-                                       'dram_read_plus_write_bytes': 1.045e9, 'algorithmic_bytes': 8256 * 128 * 128 * 8},
+                           'traffic': 34.892e9 if (world == 1 and N == 65536) else None,
+                           'traffic_note': 'dram read + write bytes of ONE launch at N=65536 mirrored (ncu --set full, '
+                                           'profiles/r02_points_gram_i8_n65536_ncu.txt: 34.31 GB written, 0.58 GB read); algorithmic 34.36 GB',
                            'fp64_declared_tflops': gram_flops / (gram_ms * 1e-3) * 1e-12,
                            'fp64_declared_frac': gram_flops / (gram_ms * 1e-3) * 1e-12 / (FP64_PEAK_TFLOPS * world),
                            'flops_per_entry_declared': 2 * DIM + F_TR} if gram_engine == 'i8' else
