@@ -39,6 +39,7 @@ SIGNATURES = {
     'gabo_gp_grad_beta_workspace_bytes': (sz, []),
     'gabo_gp_grad_beta_f64': (i32, [i64, i64, vp, i64, vp, i64, vp, i64, f64, f64, vp, vp, sz, vp]),
     'gabo_gp_predict_f64': (i32, [i64, i64, i64, vp, i64, vp, i64, vp, f64, vp, vp, vp]),
+    'gabo_gp_append_row_f64': (i32, [i64, i64, vp, i64, f64, vp, i64, vp, f64, vp, vp, vp, vp]),
     'gabo_sphere_posterior_grad_f64': (i32, [i32, i64, i64, i32, vp, i64, vp, i64, vp, vp, i64, f64, f64, vp, vp, f64, vp, vp, vp, vp]),
     'gabo_spd_ai_posterior_grad_f64': (i32, [i32, i32, i64, i64, vp, vp, vp, vp, i64, f64, f64, vp, vp, f64, vp, vp, vp, vp]),
     'gabo_sphere_acq_fused_f64': (i32, [i32, i64, i64, i32, vp, i64, vp, i64, vp, i64, vp, vp, f64, f64, f64, f64, vp, vp, vp, vp, vp, vp, vp]),

@@ -657,6 +657,38 @@ __global__ void __launch_bounds__(1024) loglik_kernel(int64_t n, int64_t p, cons
     }
 }
 
+// ---- rank-1 growth of a cached factor (GPR.append) -----------------------------------------------------
+// l = L^-1 k is given (gabo_trsm_f64, one right-hand side).  One CTA: d^2 = kss - l.l; on success writes the new factor row
+// Lrow[0..n) = l, Lrow[n] = d and vnew[c] = (ynew[c] - mean_const - l.V[:, c]) / d; info = 0 / 1 (extended matrix not PD: nothing
+// is written).  Fixed-order block reductions: deterministic.
+__global__ void __launch_bounds__(1024) append_row_kernel(int64_t n, int64_t p, const double* __restrict__ l, int64_t ldl_,
+                                                          double kss, const double* __restrict__ V, int64_t ldv,
+                                                          const double* __restrict__ ynew, double mean_const,
+                                                          double* __restrict__ Lrow, double* __restrict__ vnew,
+                                                          int* __restrict__ info) {
+    __shared__ double sred[32];
+    __shared__ double sd;
+    double ll = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const double a = l[i * ldl_]; ll = fma(a, a, ll); }
+    const double tll = block_sum(ll, sred);
+    if (threadIdx.x == 0) {
+        const double d2 = kss - tll;
+        sd = (d2 > 0.0) ? sqrt(d2) : 0.0;
+        *info = (d2 > 0.0) ? 0 : 1;
+    }
+    __syncthreads();
+    const double d = sd;
+    if (!(d > 0.0)) return;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) Lrow[i] = l[i * ldl_];
+    if (threadIdx.x == 0) Lrow[n] = d;
+    for (int64_t c = 0; c < p; ++c) {
+        double acc = 0.0;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc = fma(l[i * ldl_], V[i * ldv + c], acc);
+        const double t = block_sum(acc, sred);
+        if (threadIdx.x == 0) vnew[c] = (ynew[c] - mean_const - t) / d;
+    }
+}
+
 // ---- gradient of the log marginal likelihood w.r.t. the kernel's beta -----------------------------
 // Every kernel of the path is K = variance * exp(beta * g(x, x')), so dK/dbeta = K log(K / variance) / beta, and
 //   d ll / d beta = 1/2 sum_ij G_ij dK_ij/dbeta,   G = alpha alpha^T - p Kinv   (alpha = Ky^-1 (y - m), [n, p]).
@@ -1129,6 +1161,24 @@ extern "C" int gabo_gp_loglik_f64(int64_t n, int64_t p, const double* L, int64_t
     if (ldalpha < p) return -6;
     if (out == nullptr) return -7;
     loglik_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(n, p, L, ldl, alpha, ldalpha, out);
+    GABO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gabo_gp_append_row_f64(int64_t n, int64_t p, const double* l, int64_t ldl, double kss, const double* V, int64_t ldv,
+                                      const double* ynew, double mean_const, double* Lrow, double* vnew, int* info,
+                                      gabo_stream_t stream) {
+    if (n < 0) return -1;
+    if (p < 1) return -2;
+    if (n > 0 && l == nullptr) return -3;
+    if (ldl < 1) return -4;
+    if (n > 0 && V == nullptr) return -6;
+    if (ldv < p) return -7;
+    if (ynew == nullptr) return -8;
+    if (Lrow == nullptr) return -10;
+    if (vnew == nullptr) return -11;
+    if (info == nullptr) return -12;
+    append_row_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(n, p, l, ldl, kss, V, ldv, ynew, mean_const, Lrow, vnew, info);
     GABO_LAUNCH_CHECK();
     return 0;
 }

@@ -136,21 +136,27 @@ class GPR(Parameterized):
         xn = to_device(x_new).reshape(1, -1)
         yn = to_device(y_new).reshape(1, P)
         k = self.kern.K(self._kern_input(), xn).contiguous()          # [n, 1]
-        kss = float(self.kern.Kdiag(xn)[0].item()) + float(self.likelihood.variance)
+        # k(x*, x*): the kernels of the path with a constant diagonal report it without a device read
+        kss = self._kdiag_scalar(xn) + float(self.likelihood.variance)
         ops.trsm_(L, k, trans=False)                                  # l
-        d2 = kss - float((k * k).sum().item())
-        if not d2 > 0.0:
-            raise np.linalg.LinAlgError('append: the extended covariance is not positive definite')
-        d = float(np.sqrt(d2))
         Lnew = self._factor_view(n + 1)                               # may move the factor into a larger buffer
-        Lnew[n, :n].copy_(k[:, 0])
-        Lnew[n, n] = d
-        vnew = (yn - self._mean_const() - k.t() @ V) / d              # [1, P]
+        vnew = torch.empty((1, P), dtype=torch.float64, device=V.device)
+        # d, the new factor row and the new entry of V in one launch (gabo_gp_append_row_f64); one host read: the info word
+        info = ops.gp_append_row(k, kss, V, yn, self._mean_const(), Lnew[n], vnew)
+        if int(info.item()) != 0:
+            raise np.linalg.LinAlgError('append: the extended covariance is not positive definite')
         self.X = torch.cat([self.X, xn], dim=0)
         self.Y = torch.cat([self.Y, yn], dim=0)
         self._L = Lnew
         self._V = torch.cat([V, vnew], dim=0)
         self._cache_key = self._key()
+
+    def _kdiag_scalar(self, xn) -> float:
+        """k(x, x) of one point: `variance` for every kernel of the path except Stein (det(X)^beta, one device read)."""
+        from .kernel_utils.kernels_spd import SpdSteinGaussianKernel
+        if isinstance(self.kern, SpdSteinGaussianKernel):
+            return float(self.kern.Kdiag(xn)[0].item())
+        return float(self.kern.variance)
 
     # ---- device-level graph pieces (GPflow: build_likelihood / build_predict) --------------------------
     def build_likelihood(self) -> torch.Tensor:
@@ -194,15 +200,16 @@ class GPR(Parameterized):
         Zt = Z.t().contiguous()
         neg_kinv = Z.zero_()                                          # reuse the buffer: lower triangle of -Ky^-1
         ops.gemm_nt_sub_(neg_kinv, Zt, Zt, lower=True)
-        tr_kinv = -float(neg_kinv.diagonal().sum().item())
         resid = self.Y - self._mean_const()
-        aa = float((alpha * alpha).sum().item())
-        ay = float((alpha * resid).sum().item())
+        # the four scalar reductions come back in ONE device -> host read
+        tr_neg, aa, ay, asum = torch.stack([neg_kinv.diagonal().sum(), (alpha * alpha).sum(), (alpha * resid).sum(),
+                                            alpha.sum()]).tolist()
+        tr_kinv = -tr_neg
         s2 = float(self.likelihood.variance)
         v = float(self.kern.variance)
         grads = {'likelihood.variance': 0.5 * (aa - P * tr_kinv),
                  'kern.variance': 0.5 * ((ay - s2 * aa) - P * (n - s2 * tr_kinv)) / v,
-                 'mean_function.c': float(alpha.sum().item())}
+                 'mean_function.c': asum}
         bname = self.kern.beta_param_name()
         if bname is not None:
             Kf = Zt                                                    # reuse: noise-free Gram, lower tiles

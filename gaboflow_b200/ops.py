@@ -384,6 +384,20 @@ def gp_loglik(L_: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gp_append_row(l: torch.Tensor, kss: float, V: torch.Tensor, ynew: torch.Tensor, mean_const: float, Lrow: torch.Tensor,
+                  vnew: torch.Tensor) -> torch.Tensor:
+    """Finish a rank-1 growth of the factor on the device (gabo_gp_append_row_f64): l = L^-1 k [n, 1], V [n, p], ynew [p];
+    writes Lrow [n + 1] and vnew [p]; returns the device info word (1: extended matrix not positive definite)."""
+    _req(l, 'l'); _req(V, 'V'); _req(ynew, 'ynew'); _req(Lrow, 'Lrow'); _req(vnew, 'vnew')
+    n, p = int(V.shape[0]), int(V.shape[1])
+    info = torch.zeros((1,), dtype=torch.int32, device=V.device)
+    st = _lib.lib().gabo_gp_append_row_f64(n, p, l.data_ptr(), max(int(l.stride(0)), 1), float(kss), V.data_ptr(),
+                                           max(int(V.stride(0)), p), ynew.data_ptr(), float(mean_const), Lrow.data_ptr(),
+                                           vnew.data_ptr(), info.data_ptr(), _stream())
+    _lib.check('gabo_gp_append_row_f64', st)
+    return info
+
+
 def gp_grad_beta(K: torch.Tensor, neg_kinv: torch.Tensor, alpha: torch.Tensor, variance: float, beta: float) -> torch.Tensor:
     """d loglik / d beta for a kernel variance * exp(beta g): 1/(2 beta) sum_ij (alpha alpha^T - p Kinv)_ij K_ij log(K_ij/variance),
     from the lower triangles of the noise-free Gram K and of neg_kinv = -(K + sigma^2 I)^-1 (gabo_gp_grad_beta_f64)."""

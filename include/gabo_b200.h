@@ -169,6 +169,13 @@ int gabo_logdet_f64(int64_t n, const double* L, int64_t ldl, double* out, gabo_s
  *   [n,p] row-major (GPflow 0.5 densities.multivariate_normal summed over the p output columns). */
 int gabo_gp_loglik_f64(int64_t n, int64_t p, const double* L, int64_t ldl,
                        const double* alpha, int64_t ldalpha, double* out, gabo_stream_t stream);
+/* Rank-1 growth of a cached factor by one observation (what the BO loop does every iteration instead of rebuilding the GPflow
+ *   model: examples/bo_sphere/benchmark_examples/bo_sphere_ackley_manifold.py:137-160).  With Ky' = [[Ky, k], [k^T, kss]]:
+ *   l = L^-1 k is given ([n] with stride ldl; gabo_trsm_f64 with one right-hand side), kss = k(x*,x*) + sigma^2.
+ *   d = sqrt(kss - l.l);  Lrow[0..n) = l, Lrow[n] = d (the new row of the factor);  vnew[c] = (ynew[c] - mean_const - l.V[:,c]) / d
+ *   (the new entry of V = L^-1 (y - m), [p]).  *info = 1 and nothing written if kss - l.l <= 0 (extended matrix not PD). */
+int gabo_gp_append_row_f64(int64_t n, int64_t p, const double* l, int64_t ldl, double kss, const double* V, int64_t ldv,
+                           const double* ynew, double mean_const, double* Lrow, double* vnew, int* info, gabo_stream_t stream);
 /* Posterior at M test points from A = L^-1 K(X,X*) [n,M] and V = L^-1 (y-m) [n,p]:
  *   mean[M,p] = A^T V + mean_const ;  var[M] = kdiag[M] - colsum(A*A)   (GPR.build_predict, full_cov False). */
 /* gabo_gp_grad_beta_f64: derivative of the log marginal likelihood w.r.t. the kernel's beta (the

@@ -319,6 +319,22 @@ def test_gpr_append_matches_refactorisation(cuda):
         m2.likelihood.variance = 1e-300
         m2.compute_log_likelihood()
         m2.append(X[3], y[3])
+    # a failed append leaves the model as it was
+    ll_before = m.compute_log_likelihood()
+    m.likelihood.variance = 0.05
+    assert m.X.shape[0] == n0 + extra and abs(m.compute_log_likelihood() - ll_before) == 0.0
+    # two output columns and the Stein kernel (whose diagonal is det(X)^beta, not `variance`)
+    from gaboflow_b200 import SpdSteinGaussianKernel
+    V = orc.synth_spd_mandel(60, 2, seed=44)
+    Y2 = np.random.default_rng(45).standard_normal((60, 2))
+    ks = lambda: SpdSteinGaussianKernel(3, range(3), beta=1.5)
+    a = GPR(V[:55], Y2[:55], kern=ks()); a.likelihood.variance = 0.1
+    a.compute_log_likelihood()
+    for i in range(55, 60):
+        a.append(V[i], Y2[i])
+    b = GPR(V, Y2, kern=ks()); b.likelihood.variance = 0.1
+    assert abs(a.compute_log_likelihood() / b.compute_log_likelihood() - 1) < 1e-11
+    assert float((a._factorise()[1] - b._factorise()[1]).abs().max()) < 1e-10
 
 
 @pytest.mark.parametrize('laplace', [False, True])
