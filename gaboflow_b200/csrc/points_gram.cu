@@ -776,7 +776,7 @@ StagePlan make_stage_plan(int64_t n, int world, int rank, int frac256, int direc
 }
 
 // per-device copy streams (one per destination rank) and their join events: created on first use, reused afterwards
-struct CopyCtx { int dev; cudaStream_t st[GABO_MAX_PEERS]; cudaEvent_t ev[GABO_MAX_PEERS]; };
+struct CopyCtx { int dev; cudaStream_t st[GABO_MAX_PEERS]; cudaEvent_t ev[GABO_MAX_PEERS]; cudaEvent_t start; };
 std::mutex g_copy_mutex;
 std::vector<CopyCtx> g_copy_ctx;
 int copy_ctx_get(CopyCtx* out) {
@@ -791,6 +791,7 @@ int copy_ctx_get(CopyCtx* out) {
         GABO_CUDA_TRY(cudaStreamCreateWithFlags(&c.st[i], cudaStreamNonBlocking));
         GABO_CUDA_TRY(cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming));
     }
+    GABO_CUDA_TRY(cudaEventCreateWithFlags(&c.start, cudaEventDisableTiming));
     g_copy_ctx.push_back(c);
     *out = c;
     return 0;
@@ -877,17 +878,25 @@ extern "C" int gabo_points_gram_cyclic_staged_f64(int kind, const double* X, int
     p.stage = stage != nullptr ? stage : reinterpret_cast<double*>(ws);   // non-null selects the staged kernel (world == 1: unused)
     p.stage_tab = dtab; p.prog_cnt = progress; p.prog_flag = progress + sp.nchunks; p.epoch = epoch;
     if (sp.nchunks > 0) GABO_CUDA_TRY(cudaMemsetAsync(progress, 0, (size_t)sp.nchunks * sizeof(uint32_t), stream));
+    // The copy streams (a per-device pool, not ordered with the caller's stream) must not look at the flag words before
+    // everything the caller enqueued so far has run -- in particular the zero-initialisation of a freshly allocated `progress`
+    // (recycled memory may hold a stale flag >= epoch: the copy would fire before the kernel produced the chunk; seen once in
+    // the emulated-ranks test after other tests had freed such buffers).  Recorded BEFORE the kernel launch: the overlap stays.
+    CopyCtx cc;
+    if (world > 1) {
+        if ((rc = copy_ctx_get(&cc))) return rc;
+        GABO_CUDA_TRY(cudaEventRecord(cc.start, stream));
+    }
     if (pl.kld == 4) rc = launch_points_gram<4>(p, stream);
     else if (pl.kld == 20) rc = launch_points_gram<20>(p, stream);
     else rc = launch_points_gram<52>(p, stream);
     if (rc) return rc;
     if (world == 1) return 0;
     // copy streams: per destination rank, chunk by chunk as the kernel completes them
-    CopyCtx cc;
-    if ((rc = copy_ctx_get(&cc))) return rc;
     for (int r = 0; r < world; ++r) {
         if (r == rank) continue;
         bool any = false;
+        GABO_CUDA_TRY(cudaStreamWaitEvent(cc.st[r], cc.start, 0));
         for (int64_t c = 0; c < sp.nchunks; ++c) {
             const StageEnt& e = sp.tab[(size_t)c * 8 + r];
             if (e.nrows <= 0) continue;

@@ -251,3 +251,42 @@ def test_p2p_driver_ragged_last_panel(cuda):
         assert float(np.max(np.abs(torch.tril(B).cpu().numpy() - ref))) < 1e-12
     finally:
         xch.close()
+
+
+def test_cyclic_staged_gram_fresh_state_on_recycled_memory(cuda):
+    """A StagedGramState built on recycled device memory (stale flag words of an earlier state) while the stream still has a
+    backlog: the copy streams must not evaluate the flags before the state's zero-initialisation has run (they are ordered
+    after the caller's stream by an event since round 2; before that the copies could fire early and ship unwritten staging
+    memory)."""
+    from gaboflow_b200 import ops
+    from gaboflow_b200.dist import BlockCyclic
+    from oracle import gabo_oracle as orc
+    world, frac, split, direct = 3, 48, 1, 128
+    n = 512 * 11
+    X = torch.from_numpy(orc.synth_sphere(n, 51, seed=8)).cuda()
+    lays = [BlockCyclic(n, 512, world, r) for r in range(world)]
+    bufs = [torch.full((max(l.local_rows, 1), n), float('nan'), dtype=torch.float64, device='cuda') for l in lays]
+    ptrs = [b.data_ptr() for b in bufs]
+    full = ops.points_gram(ops.SPHERE_GAUSSIAN, X, None, beta=2.0, uplo='mirror', engine='dmma')
+    big = torch.from_numpy(orc.synth_sphere(8192, 51, seed=9)).cuda()
+    scratch = torch.empty((8192, 8192), dtype=torch.float64, device='cuda')
+    for attempt in range(4):
+        # a state that leaves flag words = 2 behind, then goes back to the allocator
+        states = [ops.StagedGramState(n, world, r, frac, split, 'cuda', direct_frac256=direct) for r in range(world)]
+        for rep in range(2):
+            for r in range(world):
+                ops.points_gram_cyclic_staged(ops.SPHERE_GAUSSIAN, X, ptrs, n, world, r, states[r], beta=2.0, variance=1.0)
+        torch.cuda.synchronize()
+        del states
+        for b in bufs:
+            b.fill_(float('nan'))
+        # backlog on the stream, then fresh states (same sizes: the caching allocator hands the same blocks back) used at once
+        for _ in range(3):
+            ops.points_gram(ops.SPHERE_GAUSSIAN, big, None, beta=2.0, out=scratch, uplo='mirror', engine='dmma')
+        states = [ops.StagedGramState(n, world, r, frac, split, 'cuda', direct_frac256=direct) for r in range(world)]
+        for r in range(world):
+            ops.points_gram_cyclic_staged(ops.SPHERE_GAUSSIAN, X, ptrs, n, world, r, states[r], beta=2.0, variance=1.0)
+        torch.cuda.synchronize()
+        for r in range(world):
+            rows = lays[r].global_rows().cuda()
+            assert torch.equal(bufs[r][:lays[r].local_rows], full[rows]), (attempt, r)
