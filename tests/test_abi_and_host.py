@@ -108,6 +108,10 @@ def test_bench_reference_arm_runs_small():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'
     assert line['e2e']['h2d_bytes_per_step'] == 0
+    # both arms print the same `config` dict (the driver compares them): workload, parameters, seeds and the L2 note only
+    assert set(line['config']) == {'workload', 'beta', 'variance', 'sigma2', 'seeds', 'l2'}
+    assert line['config']['workload'].startswith('sphere Gaussian Gram N=2048 on S^50 (D=51) + FP64 Cholesky of K+1e-2 I at N=1024')
+    assert line['metric'] == 'sphere_gram_entries_per_s' and line['unit'] == 'entries/s' and line['higher_is_better'] is True
 
 
 def test_gram_engine_and_multi_gpu_mode_selection():
